@@ -1,0 +1,160 @@
+/* limap_b200.h — C ABI of the B200-native line-triangulation / line-refinement engine.
+ *
+ * This is the drop-in boundary for the hot path of cvg/limap. The
+ * reference has no C ABI: its C++ classes are reached through pybind11
+ * (src/limap/triangulation/bindings.cc:78-119, src/limap/optimize/{line_refinement,hybrid_bundle_adjustment}/bindings.cc,
+ * src/limap/vplib/JLinkage/bindings.cc). Each entry point below names the
+ * reference interface it replaces (paths relative to /root/reference/src/limap/).
+ * Plain pointers and sizes only; no torch / pybind types. All functions return
+ * LM_OK (0) or a negative error code; lm_last_error() gives the message
+ * (the reference throws std::runtime_error / THROW_CHECK instead).
+ *
+ * Host pointers unless a parameter is named d_*. Image ids are arbitrary ints
+ * (as in ImageCollection); lines of an image are indexed 0..L-1.
+ * Limits (same as the reference's Node2d = pair<uint16,uint16>, util/types.h:16):
+ * n_views <= 65535, lines per image <= 65535.
+ */
+#ifndef LIMAP_B200_H
+#define LIMAP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LM_OK 0
+#define LM_ERR_INVALID -1   /* bad argument / index out of range */
+#define LM_ERR_CUDA -2      /* CUDA runtime failure */
+#define LM_ERR_STATE -3     /* call order (e.g. run before scene upload) */
+#define LM_ERR_NOGPU -4     /* no usable CUDA device: there is NO CPU fallback */
+
+typedef struct lm_ctx lm_ctx;
+
+/* base/line_linker.h:18-46 (LineLinker2dConfig) and :80-143 (LineLinker3dConfig). */
+typedef struct lm_linker_config {
+  double score_th, th_angle, th_overlap, th_smartoverlap, th_smartangle, th_perp, th_innerseg,
+      th_scaleinv;
+  int32_t use_angle, use_overlap, use_smartangle, use_perp, use_innerseg, use_scaleinv;
+} lm_linker_config;
+
+/* triangulation/base_line_triangulator.h:22-43 + global_line_triangulator.h:11-25.
+ * Field defaults are the C++ defaults; the Python mirror applies a dict over them the way
+ * ASSIGN_PYDICT_ITEM does (internal/helpers.h:25-27). */
+typedef struct lm_tri_config {
+  double min_length_2d, line_tri_angle_threshold, IoU_threshold, sensitivity_threshold, var2d,
+      fullscore_th;
+  int32_t debug_mode, add_halfpix, use_vp, use_endpoints_triangulation;
+  int32_t disable_many_points_triangulation, disable_one_point_triangulation;
+  int32_t disable_algebraic_triangulation, disable_vp_triangulation;
+  int32_t max_valid_conns, min_num_outer_edges, num_outliers_aggregator;
+  int32_t merging_strategy; /* 0 = "greedy" (the only strategy on the hot path) */
+  lm_linker_config linker2d, linker3d;
+} lm_tri_config;
+
+typedef struct lm_tri_stats {
+  int64_t n_rows;        /* match rows tested (the M1 numerator) */
+  int64_t n_candidates;  /* surviving 3D candidates */
+  int64_t n_valid_edges; /* candidates kept as valid connections */
+  int64_t n_nodes;       /* 2D lines in the scene */
+  int64_t n_kernel_launches; /* kernels this library launched since ctx creation */
+  int64_t n_fp64_pair_fallbacks; /* pair scores re-evaluated in fp64 by the guard band */
+  int64_t max_rows_per_node;
+  double last_run_ms;    /* device time of the last lm_tri_run (CUDA events on the ctx stream) */
+} lm_tri_stats;
+
+const char *lm_last_error(void);
+const char *lm_version(void);
+
+/* ---- context ------------------------------------------------------------------------ */
+int lm_ctx_create(int device, lm_ctx **out);
+void lm_ctx_destroy(lm_ctx *ctx);
+/* Run all work of this context on an existing CUDA stream (e.g. torch's current stream). */
+int lm_ctx_set_stream(lm_ctx *ctx, void *cuda_stream);
+int lm_ctx_synchronize(lm_ctx *ctx);
+
+/* ---- scene: BaseLineTriangulator::Init (triangulation/base_line_triangulator.cc:45-63) +
+ *      GlobalLineTriangulator::Init (global_line_triangulator.cc:32-57).
+ * model_ids: 0 SIMPLE_PINHOLE, 1 PINHOLE (base/camera_models.h:29-44); kvec = [fx,fy,cx,cy];
+ * qvec wxyz, tvec (base/camera.h:89-112); line_off[n_views+1]; segs[sum L][4] = x1,y1,x2,y2. */
+int lm_scene_upload(lm_ctx *ctx, int32_t n_views, const int32_t *img_ids, const int32_t *model_ids,
+                    const double *kvec, const double *qvec, const double *tvec,
+                    const int64_t *line_off, const double *segs);
+
+/* ---- triangulator: GlobalLineTriangulator(config) (global_line_triangulator.h:27-35) */
+int lm_tri_configure(lm_ctx *ctx, const lm_tri_config *cfg);
+/* SetRanges / UnsetRanges (base_line_triangulator.h:62-66) */
+int lm_tri_set_ranges(lm_ctx *ctx, const double lo[3], const double hi[3]);
+int lm_tri_unset_ranges(lm_ctx *ctx);
+/* InitVPResults (base_line_triangulator.h:56-58): labels[label_off[i]..] per line (-1 none),
+ * vps[vp_off[i]..][3] per image. */
+int lm_tri_set_vps(lm_ctx *ctx, int32_t n_images, const int32_t *img_ids, const int64_t *label_off,
+                   const int32_t *labels, const int64_t *vp_off, const double *vps);
+
+/* TriangulateImage(img_id, map<int, MatrixXi>) (base_line_triangulator.cc:71-109).
+ * ng_ids[n_ng], row_off[n_ng+1], pairs[row_off[n_ng]][2] = (line_id, ng_line_id).
+ * The work is enqueued; it runs (batched over all enqueued images) at lm_tri_run or at the first
+ * getter. Out-of-range line ids fail here like the reference's IndexError (:87-94). */
+int lm_tri_add_image_matches(lm_ctx *ctx, int32_t img_id, int32_t n_ng, const int32_t *ng_ids,
+                             const int64_t *row_off, const int32_t *pairs);
+/* Same, pairs already in device memory (zero-copy ingress from a GPU matcher). */
+int lm_tri_add_image_matches_device(lm_ctx *ctx, int32_t img_id, int32_t n_ng, const int32_t *ng_ids,
+                                    const int64_t *row_off, const int32_t *d_pairs);
+/* TriangulateImageExhaustiveMatch(img_id, neighbors) (base_line_triangulator.cc:111-136). */
+int lm_tri_add_image_exhaustive(lm_ctx *ctx, int32_t img_id, int32_t n_ng, const int32_t *ng_ids);
+/* Drop all enqueued matches and results (scene and config stay). */
+int lm_tri_clear(lm_ctx *ctx);
+/* Restrict the next lm_tri_run to source images with view index in [begin, end) of the ascending
+ * img_id order (multi-GPU sharding by source image). Default: all. */
+int lm_tri_set_shard(lm_ctx *ctx, int32_t view_begin, int32_t view_end);
+
+/* Candidate generation + scoring + selection for every enqueued image:
+ * triangulateOneNode (base_line_triangulator.cc:161-337) + scoreOneNode
+ * (global_line_triangulator.cc:71-161), fused, one CTA per 2D line. Work is issued on the ctx stream;
+ * the call returns after it completed (device time of the run: lm_tri_stats.last_run_ms).
+ * May be called repeatedly on the same staged matches (benchmarking). */
+int lm_tri_run(lm_ctx *ctx);
+int lm_tri_get_stats(lm_ctx *ctx, lm_tri_stats *out);
+
+/* GetBestScoredTriNode for every line of an image (global_line_triangulator.cc:536-540):
+ * out_line[L][10] = start3, end3, depths2, uncertainty, score; out_ng[L][2] = (ng_img_id, ng_line_id);
+ * out_ncand[L] = number of candidates of the node (may be NULL). Nodes without candidates return
+ * zeros, uncertainty -1, score 0, ng (0,0) (the reference leaves the Line3d uninitialised). */
+int lm_tri_get_best(lm_ctx *ctx, int32_t img_id, double *out_line, int32_t *out_ng, int32_t *out_ncand);
+/* valid_edges_ of an image (global_line_triangulator.cc:130-142) as (ng_img_id, ng_line_id) in
+ * candidate order; off[L+1]. Pass edges = NULL to get the count. Returns count or <0. */
+int64_t lm_tri_get_valid_edges(lm_ctx *ctx, int32_t img_id, int64_t *off, int32_t *edges);
+/* GetScoredTrisNode (global_line_triangulator.cc:374-378); requires debug_mode. Returns the number
+ * of candidates of the node (writes at most cap). */
+int lm_tri_get_cands_node(lm_ctx *ctx, int32_t img_id, int32_t line_id, int32_t cap, double *out_line,
+                          int32_t *out_ng);
+
+/* Per-node results as one device-resident record array (for the multi-GPU all-gather).
+ * Record layout: lm_node_record below. d_out must hold lm_tri_num_nodes records. */
+typedef struct lm_node_record {
+  double line[9]; /* start3, end3, depths2, uncertainty */
+  double score;
+  int32_t ng_view, ng_line, n_cand, n_valid;
+} lm_node_record;
+int64_t lm_tri_num_nodes(lm_ctx *ctx);
+int lm_tri_export_nodes(lm_ctx *ctx, int64_t node_begin, int64_t node_end, void *d_out);
+int lm_tri_import_nodes(lm_ctx *ctx, int64_t node_begin, int64_t node_end, const void *d_in);
+/* Valid edges as device-resident (src_node, dst_node) int64 pairs of this context's shard. */
+int64_t lm_tri_num_valid_edges(lm_ctx *ctx);
+int lm_tri_export_edges(lm_ctx *ctx, void *d_out /* int64[n][2] */);
+int lm_tri_import_edges(lm_ctx *ctx, int64_t n, const void *d_in /* int64[n][2] */, int32_t append);
+/* first node index of a view (ascending img_id order) */
+int64_t lm_scene_node_offset(lm_ctx *ctx, int32_t view_index);
+
+/* ComputeLineTracks (global_line_triangulator.cc:353-359): run_clustering (:234-291) +
+ * ComputeLineTrackLabelsGreedy (merging/merging.cc:18-103) + Aggregator::aggregate_line3d_list
+ * (merging/aggregator.cc:53-101). Returns the number of tracks (>= 0) or <0. */
+int64_t lm_tri_build_tracks(lm_ctx *ctx, int64_t *n_support_total);
+/* track_off[T+1]; per supporting line: img id, line id, graph node id, line3d[10] (start3,end3,
+ * depths2,uncertainty,score); per track: line[7] = start3,end3,uncertainty. */
+int lm_tri_get_tracks(lm_ctx *ctx, int64_t *track_off, int32_t *img_ids, int32_t *line_ids,
+                      int32_t *node_ids, double *node_line3d, double *track_line);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIMAP_B200_H */

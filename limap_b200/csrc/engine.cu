@@ -1,0 +1,1056 @@
+// engine.cu — host side of the C ABI declared in include/limap_b200.h: context, scene upload,
+// batched TriangulateImage, result getters and ComputeLineTracks.
+//
+// Mirrors (file:line under /root/reference/src/limap/):
+//   BaseLineTriangulator::{Init,TriangulateImage,TriangulateImageExhaustiveMatch}
+//       triangulation/base_line_triangulator.cc:45-136
+//   GlobalLineTriangulator::{ScoringCallback,run_clustering,build_tracks_from_clusters,ComputeLineTracks}
+//       triangulation/global_line_triangulator.cc:59-69, 234-359
+//   merging::ComputeLineTrackLabelsGreedy      merging/merging.cc:18-103
+//   merging::Aggregator::aggregate_line3d_list merging/aggregator.cc:53-101
+// There is no CPU fallback: without a CUDA device lm_ctx_create fails with LM_ERR_NOGPU.
+#include "../../include/limap_b200.h"
+#include "tri_kernels.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <map>
+#include <queue>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+static_assert(sizeof(lm_node_record) == sizeof(lm::NodeRecord), "record layout");
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                                    \
+  do {                                                                                                              \
+    cudaError_t e_ = (call);                                                                                        \
+    if (e_ != cudaSuccess)                                                                                          \
+      return fail(LM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                                 \
+  } while (0)
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct MatchBlock {
+  int src_view, ng_view;
+  int64_t n_rows;
+  int64_t pair_off; // row offset into the device pairs store (-1: exhaustive)
+  int order;        // insertion order within the source image (exhaustive mode keeps the given order)
+};
+
+struct M3h {
+  double m[9];
+};
+static M3h quat_to_R(const double q_in[4]) { // base/pose.cc:12-18 (Eigen toRotationMatrix)
+  double n = std::sqrt(q_in[0] * q_in[0] + q_in[1] * q_in[1] + q_in[2] * q_in[2] + q_in[3] * q_in[3]);
+  double q[4];
+  if (n == 0) { q[0] = 1; q[1] = q_in[1]; q[2] = q_in[2]; q[3] = q_in[3]; }
+  else for (int i = 0; i < 4; ++i) q[i] = q_in[i] / n;
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z, twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  M3h R;
+  R.m[0] = 1 - (tyy + tzz); R.m[1] = txy - twz; R.m[2] = txz + twy;
+  R.m[3] = txy + twz; R.m[4] = 1 - (txx + tzz); R.m[5] = tyz - twx;
+  R.m[6] = txz - twy; R.m[7] = tyz + twx; R.m[8] = 1 - (txx + tyy);
+  return R;
+}
+
+template <typename T> lm::LinkerDev<T> to_dev(const lm_linker_config &c) {
+  lm::LinkerDev<T> d;
+  d.score_th = (T)c.score_th; d.th_angle = (T)c.th_angle; d.th_overlap = (T)c.th_overlap;
+  d.th_smartoverlap = (T)c.th_smartoverlap; d.th_smartangle = (T)c.th_smartangle; d.th_perp = (T)c.th_perp;
+  d.th_innerseg = (T)c.th_innerseg; d.th_scaleinv = (T)c.th_scaleinv;
+  d.mult = (T)(1.0 / std::sqrt(-std::log(c.score_th) * 2.0)); // line_linker.cc:9-13
+  d.use_angle = c.use_angle; d.use_overlap = c.use_overlap; d.use_smartangle = c.use_smartangle;
+  d.use_perp = c.use_perp; d.use_innerseg = c.use_innerseg; d.use_scaleinv = c.use_scaleinv;
+  return d;
+}
+
+struct Track {
+  std::vector<int> img, line, node;
+  std::vector<int64_t> gid;
+  double agg[7];
+};
+
+} // namespace
+
+struct lm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+  // scene
+  bool have_scene = false;
+  int V = 0;
+  std::vector<int> img_ids;
+  std::unordered_map<int, int> id2view;
+  std::vector<int64_t> line_off;
+  std::vector<double> h_segs; // after add_halfpix
+  std::vector<double> h_segs_raw;
+  int64_t n_nodes = 0;
+  DevBuf d_views, d_segs, d_node_view, d_line_off;
+  // config
+  bool have_cfg = false;
+  lm_tri_config cfg;
+  bool ranges_flag = false;
+  double rlo[3] = {0, 0, 0}, rhi[3] = {0, 0, 0};
+  // staged matches
+  std::vector<MatchBlock> blocks;
+  std::vector<char> image_added;
+  std::vector<int> image_norder;
+  DevBuf d_pairs;
+  int64_t pairs_rows = 0;
+  bool any_exhaustive = false, any_matches = false;
+  int shard_begin = 0, shard_end = -1;
+  // run buffers
+  DevBuf d_blk_row_off, d_blk_src, d_blk_ng, d_blk_pair_off;
+  DevBuf d_key, d_key2, d_val, d_val2, d_sort_tmp;
+  DevBuf d_node_row_off, d_scalars; // scalars: [0] max_rows(uint) [1] err(int) ; counters at +16
+  DevBuf d_nodes, d_row_state, d_row_cand, d_slab;
+  DevBuf d_edges, d_edges2, d_edge_keys, d_edge_keys2, d_edge_w, d_edge_cnt;
+  uint32_t *sorted_val = nullptr;
+  uint32_t *sorted_key = nullptr;
+  int64_t n_rows = 0;
+  int64_t node_begin = 0, node_end = 0;
+  bool ran = false;
+  lm_tri_stats stats;
+  // host caches (filled lazily after a run)
+  bool h_nodes_valid = false;
+  std::vector<lm::NodeRecord> h_nodes;
+  bool h_rows_valid = false;
+  std::vector<uint32_t> h_node_row_off, h_row_ng;
+  std::vector<uint8_t> h_row_state;
+  std::vector<double> h_row_cand;
+  int64_t n_edges_dev = 0; // directed valid edges collected on device
+  bool edges_collected = false;
+  // tracks
+  std::vector<Track> tracks;
+  std::vector<std::pair<int, int>> graph_nodes;
+};
+
+namespace {
+
+int sync_stream(lm_ctx *c) {
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int fetch_nodes(lm_ctx *c) {
+  if (c->h_nodes_valid) return LM_OK;
+  c->h_nodes.resize(c->n_nodes);
+  CU(cudaMemcpyAsync(c->h_nodes.data(), c->d_nodes.p, sizeof(lm::NodeRecord) * c->n_nodes, cudaMemcpyDeviceToHost,
+                     c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->h_nodes_valid = true;
+  return LM_OK;
+}
+int fetch_rows(lm_ctx *c) {
+  if (c->h_rows_valid) return LM_OK;
+  c->h_node_row_off.resize(c->n_nodes + 1);
+  c->h_row_ng.resize(c->n_rows);
+  c->h_row_state.resize(c->n_rows);
+  CU(cudaMemcpyAsync(c->h_node_row_off.data(), c->d_node_row_off.p, 4 * (c->n_nodes + 1), cudaMemcpyDeviceToHost,
+                     c->stream));
+  if (c->n_rows) {
+    CU(cudaMemcpyAsync(c->h_row_ng.data(), c->sorted_val, 4 * c->n_rows, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_row_state.data(), c->d_row_state.p, c->n_rows, cudaMemcpyDeviceToHost, c->stream));
+    if (c->cfg.debug_mode) {
+      c->h_row_cand.resize(c->n_rows * 10);
+      CU(cudaMemcpyAsync(c->h_row_cand.data(), c->d_row_cand.p, 80 * c->n_rows, cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  c->h_rows_valid = true;
+  return LM_OK;
+}
+
+int ensure_ran(lm_ctx *c) {
+  if (c->ran) return LM_OK;
+  return lm_tri_run(c);
+}
+
+} // namespace
+
+extern "C" {
+
+const char *lm_last_error(void) { return g_err.c_str(); }
+const char *lm_version(void) { return "limap_b200 0.1 (sm_100a)"; }
+
+int lm_ctx_create(int device, lm_ctx **out) {
+  if (!out) return fail(LM_ERR_INVALID, "out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(LM_ERR_NOGPU, std::string("no CUDA device (") + cudaGetErrorString(e) +
+                                  "); limap_b200 has no CPU fallback");
+  if (device < 0 || device >= n) return fail(LM_ERR_INVALID, "device index out of range");
+  CU(cudaSetDevice(device));
+  lm_ctx *c = new lm_ctx();
+  c->device = device;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  memset(&c->stats, 0, sizeof(c->stats));
+  *out = c;
+  return LM_OK;
+}
+
+void lm_ctx_destroy(lm_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf *bufs[] = {&c->d_views, &c->d_segs, &c->d_node_view, &c->d_line_off, &c->d_pairs, &c->d_blk_row_off,
+                    &c->d_blk_src, &c->d_blk_ng, &c->d_blk_pair_off, &c->d_key, &c->d_key2, &c->d_val, &c->d_val2,
+                    &c->d_sort_tmp, &c->d_node_row_off, &c->d_scalars, &c->d_nodes, &c->d_row_state, &c->d_row_cand,
+                    &c->d_slab, &c->d_edges, &c->d_edges2, &c->d_edge_keys, &c->d_edge_keys2, &c->d_edge_w,
+                    &c->d_edge_cnt};
+  for (DevBuf *b : bufs) b->release();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int lm_ctx_set_stream(lm_ctx *c, void *s) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)s;
+  c->own_stream = false;
+  return LM_OK;
+}
+int lm_ctx_synchronize(lm_ctx *c) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  return sync_stream(c);
+}
+
+static int upload_segs(lm_ctx *c) {
+  // add_halfpix (base_line_triangulator.cc:32-43) is applied when both scene and config are known.
+  c->h_segs = c->h_segs_raw;
+  if (c->have_cfg && c->cfg.add_halfpix)
+    for (double &v : c->h_segs) v += 0.5;
+  CU(c->d_segs.ensure(std::max<size_t>(32, c->h_segs.size() * 8)));
+  if (!c->h_segs.empty())
+    CU(cudaMemcpyAsync(c->d_segs.p, c->h_segs.data(), c->h_segs.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int lm_scene_upload(lm_ctx *c, int32_t n_views, const int32_t *img_ids, const int32_t *model_ids, const double *kvec,
+                    const double *qvec, const double *tvec, const int64_t *line_off, const double *segs) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  if (n_views <= 0 || n_views > 65535) return fail(LM_ERR_INVALID, "n_views must be in [1, 65535]");
+  CU(cudaSetDevice(c->device));
+  for (int v = 1; v < n_views; ++v)
+    if (img_ids[v] <= img_ids[v - 1]) return fail(LM_ERR_INVALID, "img_ids must be strictly ascending");
+  c->V = n_views;
+  c->img_ids.assign(img_ids, img_ids + n_views);
+  c->id2view.clear();
+  for (int v = 0; v < n_views; ++v) c->id2view[img_ids[v]] = v;
+  c->line_off.assign(line_off, line_off + n_views + 1);
+  c->n_nodes = line_off[n_views];
+  if (c->n_nodes >= (int64_t)1 << 32) return fail(LM_ERR_INVALID, "too many 2D lines");
+  std::vector<lm::ViewD> views(n_views);
+  std::vector<uint16_t> node_view(c->n_nodes);
+  for (int v = 0; v < n_views; ++v) {
+    if (model_ids[v] != 0 && model_ids[v] != 1)
+      return fail(LM_ERR_INVALID, "only SIMPLE_PINHOLE / PINHOLE are legal on this path (IsUndistorted check)");
+    if (line_off[v + 1] - line_off[v] > 65535) return fail(LM_ERR_INVALID, "more than 65535 lines in one image");
+    const double fx = kvec[4 * v], fy = kvec[4 * v + 1], cx = kvec[4 * v + 2], cy = kvec[4 * v + 3];
+    // CameraPose(qvec, tvec) normalises qvec (base/camera.h:92-93)
+    M3h R = quat_to_R(qvec + 4 * v);
+    const double *t = tvec + 3 * v;
+    lm::ViewD &d = views[v];
+    // K^-1 (closed form of Eigen's cofactor inverse for the pinhole K)
+    const double ki[9] = {1.0 / fx, 0, -cx / fx, 0, 1.0 / fy, -cy / fy, 0, 0, 1};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) // M = R^T * Kinv
+        d.M[3 * i + j] = R.m[0 * 3 + i] * ki[0 * 3 + j] + R.m[1 * 3 + i] * ki[1 * 3 + j] + R.m[2 * 3 + i] * ki[2 * 3 + j];
+    for (int i = 0; i < 3; ++i) d.C[i] = -(R.m[0 * 3 + i] * t[0] + R.m[1 * 3 + i] * t[1] + R.m[2 * 3 + i] * t[2]);
+    const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j)
+        d.P[4 * i + j] = K[3 * i] * R.m[j] + K[3 * i + 1] * R.m[3 + j] + K[3 * i + 2] * R.m[6 + j];
+      d.P[4 * i + 3] = K[3 * i] * t[0] + K[3 * i + 1] * t[1] + K[3 * i + 2] * t[2];
+    }
+    d.fbar = (model_ids[v] == 0) ? fx : (fx + fy) / 2.0;
+    d.pad = 0;
+    for (int64_t l = line_off[v]; l < line_off[v + 1]; ++l) node_view[l] = (uint16_t)v;
+  }
+  c->h_segs_raw.assign(segs, segs + 4 * c->n_nodes);
+  CU(c->d_views.ensure(sizeof(lm::ViewD) * n_views));
+  CU(c->d_node_view.ensure(std::max<size_t>(2, 2 * c->n_nodes)));
+  CU(c->d_line_off.ensure(8 * (n_views + 1)));
+  CU(cudaMemcpyAsync(c->d_views.p, views.data(), sizeof(lm::ViewD) * n_views, cudaMemcpyHostToDevice, c->stream));
+  if (c->n_nodes)
+    CU(cudaMemcpyAsync(c->d_node_view.p, node_view.data(), 2 * c->n_nodes, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_line_off.p, c->line_off.data(), 8 * (n_views + 1), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream)); // host vectors above go out of scope
+  c->have_scene = true;
+  int rc = upload_segs(c);
+  if (rc) return rc;
+  c->image_added.assign(n_views, 0);
+  c->image_norder.assign(n_views, 0);
+  c->stats.n_nodes = c->n_nodes;
+  return lm_tri_clear(c);
+}
+
+int lm_tri_configure(lm_ctx *c, const lm_tri_config *cfg) {
+  if (!c || !cfg) return fail(LM_ERR_INVALID, "NULL argument");
+  if (cfg->merging_strategy != 0)
+    return fail(LM_ERR_INVALID, "Error!The given merging strategy is not implemented"); // global_line_triangulator.cc:318
+  if (cfg->use_vp && !cfg->disable_vp_triangulation)
+    return fail(LM_ERR_INVALID, "use_vp triangulation proposals are not built yet (SURVEY §8 a5)");
+  const bool halfpix_changed = !c->have_cfg || (c->cfg.add_halfpix != cfg->add_halfpix);
+  c->cfg = *cfg;
+  c->have_cfg = true;
+  c->ran = false;
+  if (c->have_scene && halfpix_changed) return upload_segs(c);
+  return LM_OK;
+}
+int lm_tri_set_ranges(lm_ctx *c, const double lo[3], const double hi[3]) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  c->ranges_flag = true;
+  for (int i = 0; i < 3; ++i) { c->rlo[i] = lo[i]; c->rhi[i] = hi[i]; }
+  c->ran = false;
+  return LM_OK;
+}
+int lm_tri_unset_ranges(lm_ctx *c) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  c->ranges_flag = false;
+  c->ran = false;
+  return LM_OK;
+}
+int lm_tri_set_vps(lm_ctx *, int32_t, const int32_t *, const int64_t *, const int32_t *, const int64_t *,
+                   const double *) {
+  return fail(LM_ERR_INVALID, "VP proposals are not built yet (SURVEY §8 a5)");
+}
+
+int lm_tri_clear(lm_ctx *c) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  c->blocks.clear();
+  std::fill(c->image_added.begin(), c->image_added.end(), 0);
+  std::fill(c->image_norder.begin(), c->image_norder.end(), 0);
+  c->pairs_rows = 0;
+  c->any_exhaustive = c->any_matches = false;
+  c->ran = false;
+  c->h_nodes_valid = c->h_rows_valid = false;
+  c->edges_collected = false;
+  c->tracks.clear();
+  c->graph_nodes.clear();
+  return LM_OK;
+}
+int lm_tri_set_shard(lm_ctx *c, int32_t b, int32_t e) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  c->shard_begin = b;
+  c->shard_end = e;
+  c->ran = false;
+  return LM_OK;
+}
+
+static int add_matches_impl(lm_ctx *c, int32_t img_id, int32_t n_ng, const int32_t *ng_ids, const int64_t *row_off,
+                            const int32_t *pairs, bool on_device) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  if (!c->have_scene) return fail(LM_ERR_STATE, "lm_scene_upload must precede TriangulateImage");
+  CU(cudaSetDevice(c->device));
+  auto it = c->id2view.find(img_id);
+  if (it == c->id2view.end()) return fail(LM_ERR_INVALID, "unknown image id " + std::to_string(img_id));
+  const int sv = it->second;
+  if (c->image_added[sv]) return fail(LM_ERR_STATE, "image " + std::to_string(img_id) + " was already triangulated");
+  if (c->any_exhaustive) return fail(LM_ERR_STATE, "cannot mix exhaustive and match-based triangulation in one run");
+  const int64_t total = n_ng > 0 ? row_off[n_ng] : 0;
+  std::set<int> seen;
+  for (int g = 0; g < n_ng; ++g) {
+    if (c->id2view.find(ng_ids[g]) == c->id2view.end())
+      return fail(LM_ERR_INVALID, "unknown neighbor image id " + std::to_string(ng_ids[g]));
+    if (!seen.insert(ng_ids[g]).second) return fail(LM_ERR_INVALID, "duplicate neighbor id in one TriangulateImage call");
+    if (row_off[g + 1] < row_off[g]) return fail(LM_ERR_INVALID, "row_off must be non-decreasing");
+  }
+  // grow the device pairs store (amortised doubling, old content preserved)
+  if ((size_t)(c->pairs_rows + total) * 8 > c->d_pairs.cap) {
+    DevBuf nb;
+    CU(nb.ensure(std::max<size_t>((size_t)(c->pairs_rows + total) * 8 * 2, 1 << 20)));
+    if (c->pairs_rows) CU(cudaMemcpyAsync(nb.p, c->d_pairs.p, c->pairs_rows * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->d_pairs.release();
+    c->d_pairs = nb;
+  }
+  if (total)
+    CU(cudaMemcpyAsync(c->d_pairs.as<char>() + c->pairs_rows * 8, pairs, total * 8,
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  for (int g = 0; g < n_ng; ++g) {
+    MatchBlock b;
+    b.src_view = sv;
+    b.ng_view = c->id2view[ng_ids[g]];
+    b.n_rows = row_off[g + 1] - row_off[g];
+    b.pair_off = c->pairs_rows + row_off[g];
+    b.order = 0; // std::map order = ascending neighbour id (base_line_triangulator.cc:74)
+    c->blocks.push_back(b);
+  }
+  c->pairs_rows += total;
+  c->image_added[sv] = 1;
+  c->any_matches = true;
+  c->ran = false;
+  return LM_OK;
+}
+int lm_tri_add_image_matches(lm_ctx *c, int32_t img_id, int32_t n_ng, const int32_t *ng_ids, const int64_t *row_off,
+                             const int32_t *pairs) {
+  return add_matches_impl(c, img_id, n_ng, ng_ids, row_off, pairs, false);
+}
+int lm_tri_add_image_matches_device(lm_ctx *c, int32_t img_id, int32_t n_ng, const int32_t *ng_ids,
+                                    const int64_t *row_off, const int32_t *d_pairs) {
+  return add_matches_impl(c, img_id, n_ng, ng_ids, row_off, d_pairs, true);
+}
+int lm_tri_add_image_exhaustive(lm_ctx *c, int32_t img_id, int32_t n_ng, const int32_t *ng_ids) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  if (!c->have_scene) return fail(LM_ERR_STATE, "lm_scene_upload must precede TriangulateImageExhaustiveMatch");
+  auto it = c->id2view.find(img_id);
+  if (it == c->id2view.end()) return fail(LM_ERR_INVALID, "unknown image id " + std::to_string(img_id));
+  const int sv = it->second;
+  if (c->image_added[sv]) return fail(LM_ERR_STATE, "image " + std::to_string(img_id) + " was already triangulated");
+  if (c->any_matches) return fail(LM_ERR_STATE, "cannot mix exhaustive and match-based triangulation in one run");
+  const int64_t nl = c->line_off[sv + 1] - c->line_off[sv];
+  for (int g = 0; g < n_ng; ++g) {
+    auto f = c->id2view.find(ng_ids[g]);
+    if (f == c->id2view.end()) return fail(LM_ERR_INVALID, "unknown neighbor image id " + std::to_string(ng_ids[g]));
+    MatchBlock b;
+    b.src_view = sv;
+    b.ng_view = f->second;
+    b.n_rows = nl * (c->line_off[b.ng_view + 1] - c->line_off[b.ng_view]);
+    b.pair_off = -1;
+    b.order = g; // neighbours are visited in the given order (base_line_triangulator.cc:116-117)
+    c->blocks.push_back(b);
+  }
+  c->image_added[sv] = 1;
+  c->any_exhaustive = true;
+  c->ran = false;
+  return LM_OK;
+}
+
+int lm_tri_run(lm_ctx *c) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  if (!c->have_scene) return fail(LM_ERR_STATE, "no scene uploaded");
+  if (!c->have_cfg) return fail(LM_ERR_STATE, "lm_tri_configure must precede lm_tri_run");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const int vb = std::max(0, c->shard_begin), ve = (c->shard_end < 0) ? c->V : std::min(c->V, c->shard_end);
+  // blocks of this shard in flat order: (source view, neighbour order)
+  std::vector<MatchBlock> blk;
+  for (const MatchBlock &b : c->blocks)
+    if (b.src_view >= vb && b.src_view < ve) blk.push_back(b);
+  const bool exhaustive = c->any_exhaustive;
+  std::stable_sort(blk.begin(), blk.end(), [exhaustive](const MatchBlock &a, const MatchBlock &b) {
+    if (a.src_view != b.src_view) return a.src_view < b.src_view;
+    if (exhaustive) return a.order < b.order;
+    return a.ng_view < b.ng_view;
+  });
+  const int nb = (int)blk.size();
+  std::vector<int64_t> row_off(nb + 1, 0), pair_off(nb);
+  std::vector<int32_t> bsrc(nb), bng(nb);
+  for (int i = 0; i < nb; ++i) {
+    row_off[i + 1] = row_off[i] + blk[i].n_rows;
+    pair_off[i] = blk[i].pair_off;
+    bsrc[i] = blk[i].src_view;
+    bng[i] = blk[i].ng_view;
+  }
+  const int64_t n_rows = row_off[nb];
+  if (n_rows >= ((int64_t)1 << 32) - 64) return fail(LM_ERR_INVALID, "more than 2^32 match rows in one run");
+  c->n_rows = n_rows;
+  c->node_begin = c->line_off[vb];
+  c->node_end = c->line_off[ve];
+  c->h_nodes_valid = c->h_rows_valid = false;
+  c->edges_collected = false;
+  c->tracks.clear();
+
+  CU(c->d_blk_row_off.ensure(8 * (nb + 1)));
+  CU(c->d_blk_src.ensure(4 * std::max(nb, 1)));
+  CU(c->d_blk_ng.ensure(4 * std::max(nb, 1)));
+  CU(c->d_blk_pair_off.ensure(8 * std::max(nb, 1)));
+  CU(c->d_key.ensure(4 * std::max<int64_t>(n_rows, 1)));
+  CU(c->d_key2.ensure(4 * std::max<int64_t>(n_rows, 1)));
+  CU(c->d_val.ensure(4 * std::max<int64_t>(n_rows, 1)));
+  CU(c->d_val2.ensure(4 * std::max<int64_t>(n_rows, 1)));
+  CU(c->d_node_row_off.ensure(4 * (c->n_nodes + 2)));
+  CU(c->d_scalars.ensure(64));
+  CU(c->d_nodes.ensure(sizeof(lm::NodeRecord) * std::max<int64_t>(c->n_nodes, 1)));
+  CU(c->d_row_state.ensure(std::max<int64_t>(n_rows, 1)));
+  if (c->cfg.debug_mode) CU(c->d_row_cand.ensure(80 * std::max<int64_t>(n_rows, 1)));
+
+  CU(cudaEventRecord(c->ev0, s));
+  CU(cudaMemsetAsync(c->d_scalars.p, 0, 64, s));
+  CU(cudaMemcpyAsync(c->d_blk_row_off.p, row_off.data(), 8 * (nb + 1), cudaMemcpyHostToDevice, s));
+  if (nb) {
+    CU(cudaMemcpyAsync(c->d_blk_src.p, bsrc.data(), 4 * nb, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->d_blk_ng.p, bng.data(), 4 * nb, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->d_blk_pair_off.p, pair_off.data(), 8 * nb, cudaMemcpyHostToDevice, s));
+  }
+  unsigned int *d_max_rows = c->d_scalars.as<unsigned int>();
+  int *d_err = c->d_scalars.as<int>() + 1;
+  unsigned long long *d_counters = reinterpret_cast<unsigned long long *>(c->d_scalars.as<char>() + 16);
+  int launches = 0;
+  if (n_rows) {
+    if (exhaustive)
+      lm::launch_expand_exhaustive(c->d_blk_row_off.as<int64_t>(), c->d_blk_src.as<int32_t>(), c->d_blk_ng.as<int32_t>(),
+                                   nb, c->d_line_off.as<int64_t>(), n_rows, c->d_key.as<uint32_t>(),
+                                   c->d_val.as<uint32_t>(), s);
+    else
+      lm::launch_expand_rows(c->d_pairs.as<int32_t>(), c->d_blk_row_off.as<int64_t>(), c->d_blk_src.as<int32_t>(),
+                             c->d_blk_ng.as<int32_t>(), c->d_blk_pair_off.as<int64_t>(), nb,
+                             c->d_line_off.as<int64_t>(), n_rows, c->d_key.as<uint32_t>(), c->d_val.as<uint32_t>(),
+                             d_err, s);
+    ++launches;
+    // stable LSD radix sort by node id keeps (neighbour, row) order inside every node
+    int nbits = 1;
+    while (((int64_t)1 << nbits) < c->n_nodes) ++nbits;
+    cub::DoubleBuffer<uint32_t> dk(c->d_key.as<uint32_t>(), c->d_key2.as<uint32_t>());
+    cub::DoubleBuffer<uint32_t> dv(c->d_val.as<uint32_t>(), c->d_val2.as<uint32_t>());
+    size_t tmp = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)n_rows, 0, nbits, s));
+    CU(c->d_sort_tmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, tmp, dk, dv, (int)n_rows, 0, nbits, s));
+    launches += (nbits + 7) / 8 + 1;
+    c->sorted_key = dk.Current();
+    c->sorted_val = dv.Current();
+  } else {
+    c->sorted_key = c->d_key.as<uint32_t>();
+    c->sorted_val = c->d_val.as<uint32_t>();
+  }
+  lm::launch_node_offsets(c->sorted_key, n_rows, c->n_nodes, c->d_node_row_off.as<uint32_t>(), d_max_rows, s);
+  ++launches;
+  // the shared-memory staging area is sized from the largest node (one 8-byte read-back)
+  unsigned int hs[2] = {0, 0};
+  CU(cudaMemcpyAsync(hs, c->d_scalars.p, 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (hs[1] == 1)
+    return fail(LM_ERR_INVALID, "IndexError! Out-of-index matches exist (line_id >= number of lines of the image). "
+                                "Please make sure you are reusing the correct descriptors and matches.");
+  if (hs[1] == 2) return fail(LM_ERR_INVALID, "IndexError! Out-of-index neighbor line id in matches.");
+  const int max_rows = (int)hs[0];
+  c->stats.max_rows_per_node = max_rows;
+
+  lm::TriParams p;
+  memset(&p, 0, sizeof(p));
+  p.views = c->d_views.as<lm::ViewD>();
+  p.segs = c->d_segs.as<double4>();
+  p.node_view = c->d_node_view.as<uint16_t>();
+  p.line_off = c->d_line_off.as<int64_t>();
+  p.row_ng = c->sorted_val;
+  p.node_row_off = c->d_node_row_off.as<uint32_t>();
+  p.nodes = c->d_nodes.as<lm::NodeRecord>();
+  p.row_state = c->d_row_state.as<uint8_t>();
+  p.row_cand = c->cfg.debug_mode ? c->d_row_cand.as<double>() : nullptr;
+  p.counters = d_counters;
+  p.node_begin = c->node_begin;
+  p.node_end = c->node_end;
+  const lm_tri_config &g = c->cfg;
+  p.min_length_2d = g.min_length_2d; p.line_tri_angle_threshold = g.line_tri_angle_threshold;
+  p.IoU_threshold = g.IoU_threshold; p.sensitivity_threshold = g.sensitivity_threshold; p.var2d = g.var2d;
+  p.fullscore_th = g.fullscore_th; p.max_valid_conns = g.max_valid_conns;
+  p.use_endpoints_triangulation = g.use_endpoints_triangulation; p.disable_algebraic = g.disable_algebraic_triangulation;
+  p.use_vp = g.use_vp; p.disable_vp = g.disable_vp_triangulation;
+  p.ranges_flag = c->ranges_flag;
+  for (int i = 0; i < 3; ++i) { p.rlo[i] = c->rlo[i]; p.rhi[i] = c->rhi[i]; }
+  p.l2d = to_dev<double>(g.linker2d);
+  {
+    lm_linker_config l3 = g.linker3d; // set_to_shared_parent_scoring (line_linker.h:115-121)
+    l3.use_angle = 1; l3.use_overlap = 0; l3.use_perp = 0; l3.use_innerseg = 0; l3.use_scaleinv = 1;
+    p.l3d = to_dev<double>(l3);
+  }
+  int cap = 32;
+  while (cap < max_rows) cap += 32;
+  size_t smem = lm::tri_smem_bytes(cap);
+  const int64_t n_shard_nodes = c->node_end - c->node_begin;
+  int grid;
+  const size_t smem_limit = (size_t)std::max(0, c->max_smem_optin - 1024);
+  if (smem <= smem_limit) {
+    p.use_slab = 0;
+    p.cap = cap;
+    grid = (int)std::min<int64_t>(n_shard_nodes, (int64_t)1 << 30);
+  } else {
+    // nodes larger than shared memory (exhaustive matching): persistent CTAs with a global staging slab
+    p.use_slab = 1;
+    p.cap = cap;
+    grid = (int)std::min<int64_t>(n_shard_nodes, (int64_t)c->sm_count * 4);
+    p.slab_stride = (int64_t)((smem + 255) / 256 * 256);
+    CU(c->d_slab.ensure((size_t)p.slab_stride * grid));
+    p.slab = c->d_slab.as<char>();
+    smem = 0;
+  }
+  if (n_shard_nodes > 0) {
+    lm::launch_tri_node_kernel(p, grid, 128, smem, s);
+    ++launches;
+  }
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev1, s));
+  CU(cudaStreamSynchronize(s));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  unsigned long long cnt[4];
+  CU(cudaMemcpy(cnt, d_counters, 32, cudaMemcpyDeviceToHost));
+  c->stats.n_rows = n_rows;
+  c->stats.n_candidates = (int64_t)cnt[0];
+  c->stats.n_valid_edges = (int64_t)cnt[1];
+  c->stats.n_fp64_pair_fallbacks = (int64_t)cnt[2];
+  c->stats.n_kernel_launches += launches;
+  c->stats.last_run_ms = ms;
+  c->ran = true;
+  return LM_OK;
+}
+
+int lm_tri_get_stats(lm_ctx *c, lm_tri_stats *out) {
+  if (!c || !out) return fail(LM_ERR_INVALID, "NULL argument");
+  *out = c->stats;
+  return LM_OK;
+}
+
+int lm_tri_get_best(lm_ctx *c, int32_t img_id, double *out_line, int32_t *out_ng, int32_t *out_ncand) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  int rc = ensure_ran(c);
+  if (rc) return rc;
+  if ((rc = fetch_nodes(c))) return rc;
+  auto it = c->id2view.find(img_id);
+  if (it == c->id2view.end()) return fail(LM_ERR_INVALID, "unknown image id");
+  const int v = it->second;
+  for (int64_t n = c->line_off[v]; n < c->line_off[v + 1]; ++n) {
+    const lm::NodeRecord &r = c->h_nodes[n];
+    const int64_t l = n - c->line_off[v];
+    for (int k = 0; k < 9; ++k) out_line[10 * l + k] = r.line[k];
+    out_line[10 * l + 9] = r.score;
+    out_ng[2 * l] = r.n_cand ? c->img_ids[r.ng_view] : 0;
+    out_ng[2 * l + 1] = r.ng_line;
+    if (out_ncand) out_ncand[l] = r.n_cand;
+  }
+  return LM_OK;
+}
+
+int64_t lm_tri_get_valid_edges(lm_ctx *c, int32_t img_id, int64_t *off, int32_t *edges) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  int rc = ensure_ran(c);
+  if (rc) return rc;
+  if ((rc = fetch_rows(c))) return rc;
+  auto it = c->id2view.find(img_id);
+  if (it == c->id2view.end()) return fail(LM_ERR_INVALID, "unknown image id");
+  const int v = it->second;
+  int64_t n_out = 0;
+  for (int64_t n = c->line_off[v]; n < c->line_off[v + 1]; ++n) {
+    if (off) off[n - c->line_off[v]] = n_out;
+    for (uint32_t r = c->h_node_row_off[n]; r < c->h_node_row_off[n + 1]; ++r) {
+      if (c->h_row_state[r] != 2) continue;
+      if (edges) {
+        edges[2 * n_out] = c->img_ids[c->h_row_ng[r] >> 16];
+        edges[2 * n_out + 1] = (int32_t)(c->h_row_ng[r] & 0xffffu);
+      }
+      ++n_out;
+    }
+  }
+  if (off) off[c->line_off[v + 1] - c->line_off[v]] = n_out;
+  return n_out;
+}
+
+int lm_tri_get_cands_node(lm_ctx *c, int32_t img_id, int32_t line_id, int32_t cap, double *out_line, int32_t *out_ng) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  if (!c->have_cfg || !c->cfg.debug_mode) return fail(LM_ERR_STATE, "GetScoredTrisNode needs debug_mode");
+  int rc = ensure_ran(c);
+  if (rc) return rc;
+  if ((rc = fetch_rows(c))) return rc;
+  auto it = c->id2view.find(img_id);
+  if (it == c->id2view.end()) return fail(LM_ERR_INVALID, "unknown image id");
+  const int64_t n = c->line_off[it->second] + line_id;
+  if (line_id < 0 || n >= c->line_off[it->second + 1]) return fail(LM_ERR_INVALID, "line id out of range");
+  int k = 0;
+  for (uint32_t r = c->h_node_row_off[n]; r < c->h_node_row_off[n + 1]; ++r) {
+    if (c->h_row_state[r] == 0) continue;
+    if (k < cap) {
+      for (int q = 0; q < 10; ++q) out_line[10 * k + q] = c->h_row_cand[(size_t)r * 10 + q];
+      out_ng[2 * k] = c->img_ids[c->h_row_ng[r] >> 16];
+      out_ng[2 * k + 1] = (int32_t)(c->h_row_ng[r] & 0xffffu);
+    }
+    ++k;
+  }
+  return k;
+}
+
+int64_t lm_tri_num_nodes(lm_ctx *c) { return c ? c->n_nodes : 0; }
+int64_t lm_scene_node_offset(lm_ctx *c, int32_t v) {
+  if (!c || v < 0 || v > c->V) return -1;
+  return c->line_off[v];
+}
+int lm_tri_export_nodes(lm_ctx *c, int64_t b, int64_t e, void *d_out) {
+  if (!c || !d_out || b < 0 || e > c->n_nodes || b > e) return fail(LM_ERR_INVALID, "bad node range");
+  int rc = ensure_ran(c);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(d_out, c->d_nodes.as<lm::NodeRecord>() + b, sizeof(lm::NodeRecord) * (e - b),
+                     cudaMemcpyDeviceToDevice, c->stream));
+  return LM_OK;
+}
+int lm_tri_import_nodes(lm_ctx *c, int64_t b, int64_t e, const void *d_in) {
+  if (!c || !d_in || b < 0 || e > c->n_nodes || b > e) return fail(LM_ERR_INVALID, "bad node range");
+  CU(c->d_nodes.ensure(sizeof(lm::NodeRecord) * std::max<int64_t>(c->n_nodes, 1)));
+  CU(cudaMemcpyAsync(c->d_nodes.as<lm::NodeRecord>() + b, d_in, sizeof(lm::NodeRecord) * (e - b),
+                     cudaMemcpyDeviceToDevice, c->stream));
+  c->h_nodes_valid = false;
+  return LM_OK;
+}
+
+static int collect_edges(lm_ctx *c) {
+  if (c->edges_collected) return LM_OK;
+  const int64_t cap = std::max<int64_t>(c->stats.n_valid_edges, 1);
+  CU(c->d_edges.ensure(16 * cap));
+  CU(c->d_edge_cnt.ensure(8));
+  CU(cudaMemsetAsync(c->d_edge_cnt.p, 0, 8, c->stream));
+  lm::launch_collect_edges(c->d_row_state.as<uint8_t>(), c->sorted_val, c->d_node_row_off.as<uint32_t>(),
+                           c->d_line_off.as<int64_t>(), c->node_begin, c->node_end, c->d_edges.as<int64_t>(),
+                           c->d_edge_cnt.as<unsigned long long>(), c->stream);
+  c->stats.n_kernel_launches += 1;
+  unsigned long long n = 0;
+  CU(cudaMemcpyAsync(&n, c->d_edge_cnt.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->n_edges_dev = (int64_t)n;
+  c->edges_collected = true;
+  return LM_OK;
+}
+int64_t lm_tri_num_valid_edges(lm_ctx *c) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  int rc = ensure_ran(c);
+  if (rc) return rc;
+  if ((rc = collect_edges(c))) return rc;
+  return c->n_edges_dev;
+}
+int lm_tri_export_edges(lm_ctx *c, void *d_out) {
+  if (!c || !d_out) return fail(LM_ERR_INVALID, "NULL argument");
+  int rc = ensure_ran(c);
+  if (rc) return rc;
+  if ((rc = collect_edges(c))) return rc;
+  if (c->n_edges_dev)
+    CU(cudaMemcpyAsync(d_out, c->d_edges.p, 16 * c->n_edges_dev, cudaMemcpyDeviceToDevice, c->stream));
+  return LM_OK;
+}
+int lm_tri_import_edges(lm_ctx *c, int64_t n, const void *d_in, int32_t append) {
+  if (!c || (n && !d_in)) return fail(LM_ERR_INVALID, "NULL argument");
+  const int64_t base = append ? c->n_edges_dev : 0;
+  if ((size_t)(base + n) * 16 > c->d_edges.cap) {
+    DevBuf nb;
+    CU(nb.ensure((size_t)(base + n) * 16));
+    if (base) CU(cudaMemcpyAsync(nb.p, c->d_edges.p, 16 * base, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->d_edges.release();
+    c->d_edges = nb;
+  }
+  if (n) CU(cudaMemcpyAsync(c->d_edges.as<char>() + 16 * base, d_in, 16 * n, cudaMemcpyDeviceToDevice, c->stream));
+  c->n_edges_dev = base + n;
+  c->edges_collected = true;
+  return LM_OK;
+}
+
+// ---- ComputeLineTracks ---------------------------------------------------------------------------
+namespace {
+
+// Symmetric 3x3 Jacobi eigen-solver (dominant eigenvector) for the total-least-squares direction of
+// Aggregator::aggregate_line3d_list (merging/aggregator.cc:63-78; JacobiSVD V.col(0) up to sign).
+void dominant_eigvec(const double Ain[3][3], double out[3]) {
+  double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  memcpy(A, Ain, sizeof(A));
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+    double diag = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+    if (off == 0 || off <= 1e-32 * diag) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (A[p][q] == 0) continue;
+        double theta = (A[q][q] - A[p][p]) / (2 * A[p][q]);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+        double cs = 1 / std::sqrt(t * t + 1), sn = t * cs;
+        for (int k = 0; k < 3; ++k) { double a = A[k][p], b = A[k][q]; A[k][p] = cs * a - sn * b; A[k][q] = sn * a + cs * b; }
+        for (int k = 0; k < 3; ++k) { double a = A[p][k], b = A[q][k]; A[p][k] = cs * a - sn * b; A[q][k] = sn * a + cs * b; }
+        for (int k = 0; k < 3; ++k) { double a = V[k][p], b = V[k][q]; V[k][p] = cs * a - sn * b; V[k][q] = sn * a + cs * b; }
+      }
+  }
+  int best = 0;
+  if (A[1][1] > A[best][best]) best = 1;
+  if (A[2][2] > A[best][best]) best = 2;
+  for (int k = 0; k < 3; ++k) out[k] = V[k][best];
+}
+
+void aggregate(const std::vector<const lm::NodeRecord *> &recs, int num_outliers, double out[7]) {
+  const int n = (int)recs.size();
+  double min_unc = 1.7976931348623157e308;
+  for (auto *r : recs) if (r->line[8] < min_unc) min_unc = r->line[8];
+  if (n < 4) { // aggregate_line3d_list_takebest (aggregator.cc:9-29); index 0 when no score > 0
+    double best_score = 0.0;
+    int best = -1;
+    for (int i = 0; i < n; ++i) if (recs[i]->score > best_score) { best_score = recs[i]->score; best = i; }
+    if (best < 0) best = 0;
+    for (int k = 0; k < 6; ++k) out[k] = recs[best]->line[k];
+    out[6] = min_unc;
+    return;
+  }
+  double ctr[3] = {0, 0, 0};
+  for (auto *r : recs) for (int k = 0; k < 3; ++k) { ctr[k] += r->line[k]; ctr[k] += r->line[3 + k]; }
+  for (int k = 0; k < 3; ++k) ctr[k] = ctr[k] / (2 * n);
+  double S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (auto *r : recs)
+    for (int e = 0; e < 2; ++e) {
+      double p[3] = {r->line[3 * e] - ctr[0], r->line[3 * e + 1] - ctr[1], r->line[3 * e + 2] - ctr[2]};
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) S[a][b] += p[a] * p[b];
+    }
+  double d[3];
+  dominant_eigvec(S, d);
+  double dn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  for (int k = 0; k < 3; ++k) d[k] /= dn;
+  std::vector<double> proj;
+  for (auto *r : recs)
+    for (int e = 0; e < 2; ++e)
+      proj.push_back((r->line[3 * e] - ctr[0]) * d[0] + (r->line[3 * e + 1] - ctr[1]) * d[1] +
+                     (r->line[3 * e + 2] - ctr[2]) * d[2]);
+  std::sort(proj.begin(), proj.end());
+  const double a = proj[num_outliers], b = proj[2 * n - 1 - num_outliers];
+  for (int k = 0; k < 3; ++k) { out[k] = ctr[k] + d[k] * a; out[3 + k] = ctr[k] + d[k] * b; }
+  out[6] = min_unc;
+}
+
+size_t uf_root(size_t i, std::vector<int> &parent) { // base/graph.cc:157-166
+  size_t r = i;
+  while (parent[r] != -1) r = parent[r];
+  while (parent[i] != -1) { size_t nx = parent[i]; parent[i] = (int)r; i = nx; } // full compression to the root
+  return r;
+}
+
+} // namespace
+
+int64_t lm_tri_build_tracks(lm_ctx *c, int64_t *n_support_total) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  int rc = ensure_ran(c);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  if ((rc = collect_edges(c))) return rc;
+  if ((rc = fetch_nodes(c))) return rc;
+  cudaStream_t s = c->stream;
+  const int64_t ne = c->n_edges_dev;
+  c->tracks.clear();
+  c->graph_nodes.clear();
+  if (n_support_total) *n_support_total = 0;
+  if (ne == 0) return 0;
+  std::vector<int64_t> h_edges(2 * ne);
+  CU(cudaMemcpyAsync(h_edges.data(), c->d_edges.p, 16 * ne, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+
+  // filterNodeByNumOuterEdges (global_line_triangulator.cc:168-232)
+  std::vector<char> flag(c->n_nodes, 1);
+  const int min_outer = c->cfg.min_num_outer_edges;
+  if (min_outer > 0) {
+    std::vector<int> counter(c->n_nodes, 0);
+    std::vector<int64_t> pstart(c->n_nodes + 1, 0);
+    for (int64_t e = 0; e < ne; ++e) { counter[h_edges[2 * e]]++; pstart[h_edges[2 * e + 1] + 1]++; }
+    for (int64_t n = 0; n < c->n_nodes; ++n) pstart[n + 1] += pstart[n];
+    std::vector<int64_t> parents(ne), fill(pstart.begin(), pstart.end() - 1);
+    for (int64_t e = 0; e < ne; ++e) parents[fill[h_edges[2 * e + 1]]++] = h_edges[2 * e];
+    std::queue<int64_t> q;
+    for (int64_t n = 0; n < c->n_nodes; ++n)
+      if (counter[n] < min_outer) { flag[n] = 0; q.push(n); }
+    while (!q.empty()) {
+      int64_t n = q.front(); q.pop();
+      for (int64_t k = pstart[n]; k < pstart[n + 1]; ++k) {
+        int64_t pn = parents[k];
+        if (!flag[pn]) continue;
+        if (--counter[pn] < min_outer) { flag[pn] = 0; q.push(pn); }
+      }
+    }
+  }
+  // undirected edge set ordered like std::set<pair<LineNode,LineNode>> (:243-261): sort + unique on device
+  std::vector<uint64_t> keys;
+  keys.reserve(ne);
+  for (int64_t e = 0; e < ne; ++e) {
+    int64_t a = h_edges[2 * e], b = h_edges[2 * e + 1];
+    if (!flag[a] || !flag[b]) continue;
+    if (a > b) std::swap(a, b);
+    keys.push_back(((uint64_t)a << 32) | (uint64_t)b);
+  }
+  const int64_t nk = (int64_t)keys.size();
+  if (nk == 0) return 0;
+  CU(c->d_edge_keys.ensure(8 * nk));
+  CU(c->d_edge_keys2.ensure(8 * nk + 8));
+  CU(cudaMemcpyAsync(c->d_edge_keys.p, keys.data(), 8 * nk, cudaMemcpyHostToDevice, s));
+  {
+    cub::DoubleBuffer<uint64_t> dk(c->d_edge_keys.as<uint64_t>(), c->d_edge_keys2.as<uint64_t>());
+    size_t tmp = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, dk, (int)nk, 0, 64, s));
+    CU(c->d_sort_tmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortKeys(c->d_sort_tmp.p, tmp, dk, (int)nk, 0, 64, s));
+    uint64_t *sorted = dk.Current();
+    uint64_t *other = dk.Alternate();
+    size_t tmp2 = 0;
+    CU(c->d_edge_cnt.ensure(8));
+    CU(cub::DeviceSelect::Unique(nullptr, tmp2, sorted, other, c->d_edge_cnt.as<int64_t>(), (int)nk, s));
+    CU(c->d_sort_tmp.ensure(tmp2));
+    CU(cub::DeviceSelect::Unique(c->d_sort_tmp.p, tmp2, sorted, other, c->d_edge_cnt.as<int64_t>(), (int)nk, s));
+    int64_t nu = 0;
+    CU(cudaMemcpyAsync(&nu, c->d_edge_cnt.p, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    keys.resize(nu);
+    CU(cudaMemcpyAsync(keys.data(), other, 8 * nu, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    c->stats.n_kernel_launches += 12;
+  }
+  const int64_t nu = (int64_t)keys.size();
+  // 3d score of every undirected edge on the device (:263-288)
+  std::vector<int64_t> ue(2 * nu);
+  for (int64_t e = 0; e < nu; ++e) { ue[2 * e] = (int64_t)(keys[e] >> 32); ue[2 * e + 1] = (int64_t)(keys[e] & 0xffffffffull); }
+  CU(c->d_edges2.ensure(16 * nu));
+  CU(c->d_edge_w.ensure(8 * nu));
+  CU(cudaMemcpyAsync(c->d_edges2.p, ue.data(), 16 * nu, cudaMemcpyHostToDevice, s));
+  lm::EdgeParams ep;
+  ep.nodes = c->d_nodes.as<lm::NodeRecord>();
+  ep.edges = c->d_edges2.as<int64_t>();
+  ep.weight = c->d_edge_w.as<double>();
+  ep.n = nu;
+  {
+    lm_linker_config l3 = c->cfg.linker3d; // set_to_spatial_merging (line_linker.h:123-129)
+    l3.use_angle = 1; l3.use_overlap = 1; l3.use_perp = 0; l3.use_innerseg = 1; l3.use_scaleinv = 0;
+    ep.l3d = to_dev<double>(l3);
+  }
+  lm::launch_edge_weights(ep, s);
+  c->stats.n_kernel_launches += 1;
+  std::vector<double> w(nu);
+  CU(cudaMemcpyAsync(w.data(), c->d_edge_w.p, 8 * nu, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+
+  // Graph::FindOrCreateNode in edge order (base/graph.cc:57-70), zero-score edges dropped first (:284-285)
+  std::unordered_map<int64_t, int> node_map;
+  std::vector<int64_t> gnode;
+  typedef std::tuple<double, size_t, size_t> edge_tuple;
+  std::vector<edge_tuple> edges;
+  for (int64_t e = 0; e < nu; ++e) {
+    if (w[e] == 0) continue;
+    size_t idx[2];
+    for (int k = 0; k < 2; ++k) {
+      auto f = node_map.find(ue[2 * e + k]);
+      if (f == node_map.end()) {
+        gnode.push_back(ue[2 * e + k]);
+        idx[k] = gnode.size() - 1;
+        node_map.emplace(ue[2 * e + k], (int)idx[k]);
+      } else
+        idx[k] = f->second;
+    }
+    edges.push_back(std::make_tuple(w[e], idx[0], idx[1]));
+  }
+  const size_t n_gn = gnode.size();
+  // ComputeLineTrackLabelsGreedy (merging/merging.cc:18-103)
+  std::sort(edges.begin(), edges.end());
+  std::reverse(edges.begin(), edges.end());
+  std::vector<int> parent(n_gn, -1);
+  std::vector<std::vector<int>> images(n_gn); // sorted distinct image ids of each root's track
+  for (size_t i = 0; i < n_gn; ++i) images[i].push_back(0);
+  {
+    // view index of a node id: binary search in line_off
+    for (size_t i = 0; i < n_gn; ++i) {
+      int v = (int)(std::upper_bound(c->line_off.begin(), c->line_off.end(), gnode[i]) - c->line_off.begin()) - 1;
+      images[i][0] = v;
+    }
+  }
+  // The reference's union_find_get_root compresses recursively (every node on the path points to the
+  // root afterwards); uf_root does the same iteratively.
+  for (const edge_tuple &e : edges) {
+    size_t r1 = uf_root(std::get<1>(e), parent), r2 = uf_root(std::get<2>(e), parent);
+    if (r1 == r2) continue;
+    size_t dst, srcn;
+    if (images[r1].size() < images[r2].size()) { parent[r1] = (int)r2; dst = r2; srcn = r1; }
+    else { parent[r2] = (int)r1; dst = r1; srcn = r2; }
+    std::vector<int> merged;
+    std::set_union(images[dst].begin(), images[dst].end(), images[srcn].begin(), images[srcn].end(),
+                   std::back_inserter(merged));
+    images[dst].swap(merged);
+    std::vector<int>().swap(images[srcn]);
+  }
+  std::vector<int> label(n_gn, -1);
+  int n_tracks = 0;
+  for (size_t i = 0; i < n_gn; ++i) {
+    if (parent[i] == -1) continue;
+    size_t pi = parent[i];
+    if (parent[pi] == -1 && label[pi] == -1) label[pi] = n_tracks++;
+  }
+  for (size_t i = 0; i < n_gn; ++i) {
+    if (parent[i] == -1) continue;
+    label[i] = label[uf_root(i, parent)];
+  }
+  // build_tracks_from_clusters (global_line_triangulator.cc:293-351)
+  c->tracks.assign(n_tracks, Track());
+  int64_t support = 0;
+  for (size_t i = 0; i < n_gn; ++i) {
+    if (label[i] < 0) continue;
+    Track &t = c->tracks[label[i]];
+    const int v = (int)(std::upper_bound(c->line_off.begin(), c->line_off.end(), gnode[i]) - c->line_off.begin()) - 1;
+    t.img.push_back(c->img_ids[v]);
+    t.line.push_back((int)(gnode[i] - c->line_off[v]));
+    t.node.push_back((int)i);
+    t.gid.push_back(gnode[i]);
+    ++support;
+  }
+  for (Track &t : c->tracks) {
+    std::vector<const lm::NodeRecord *> recs;
+    for (int64_t g : t.gid) recs.push_back(&c->h_nodes[g]);
+    aggregate(recs, c->cfg.num_outliers_aggregator, t.agg);
+  }
+  c->graph_nodes.clear();
+  if (n_support_total) *n_support_total = support;
+  return n_tracks;
+}
+
+int lm_tri_get_tracks(lm_ctx *c, int64_t *track_off, int32_t *img_ids, int32_t *line_ids, int32_t *node_ids,
+                      double *node_line3d, double *track_line) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  int64_t n = 0;
+  for (size_t t = 0; t < c->tracks.size(); ++t) {
+    const Track &tr = c->tracks[t];
+    track_off[t] = n;
+    for (size_t k = 0; k < tr.img.size(); ++k, ++n) {
+      img_ids[n] = tr.img[k];
+      line_ids[n] = tr.line[k];
+      node_ids[n] = tr.node[k];
+      const lm::NodeRecord &r = c->h_nodes[tr.gid[k]];
+      for (int q = 0; q < 9; ++q) node_line3d[10 * n + q] = r.line[q];
+      node_line3d[10 * n + 9] = r.score;
+    }
+    for (int q = 0; q < 7; ++q) track_line[7 * t + q] = tr.agg[q];
+  }
+  track_off[c->tracks.size()] = n;
+  return LM_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,82 @@
+// tri_kernels.cuh — device-side data layout and kernel declarations of the triangulation path.
+#pragma once
+#include "lm_math.cuh"
+
+namespace lm {
+
+// Per-view constants, precomputed once in fp64 at lm_scene_upload and resident in HBM
+// (replaces the per-call CameraView::R()/K_inv() recomputation of base/camera.h:72-73,106-110).
+//   M = R^T K^-1   (ray(p) = normalize(M [p;1]), base/camera_view.cc:67-69)
+//   C = -R^T T     (base/camera.h:109)
+//   P = K [R|T]    (projection, base/camera_view.cc:61-65; row 2 = [R row 2 | T.z] gives projdepth)
+//   fbar = f or (fx+fy)/2 (base/camera.cc:228-242; uncertainty = var2d * depth / fbar)
+template <typename T> struct ViewT {
+  T M[9];
+  T C[3];
+  T P[12];
+  T fbar;
+  T pad;
+};
+typedef ViewT<double> ViewD;
+typedef ViewT<float> ViewF;
+
+struct NodeRecord { // == lm_node_record
+  double line[9];   // start3, end3, depths2, uncertainty
+  double score;
+  int32_t ng_view, ng_line, n_cand, n_valid;
+};
+
+// Kernel parameters of the fused generate+score+select kernel.
+struct TriParams {
+  const ViewD *views;          // [V]
+  const double4 *segs;         // [sum L] x1,y1,x2,y2 (after add_halfpix)
+  const uint16_t *node_view;   // [sum L] view index of each node
+  const int64_t *line_off;     // [V+1] node offset of each view
+  const uint32_t *row_ng;      // [rows] sorted by node: (ng_view << 16) | ng_line
+  const uint32_t *node_row_off; // [nodes+1] row range of each node in row_ng
+  const int32_t *vp_label;     // [sum L] VP label per line or NULL
+  const int64_t *vp_off;       // [V+1]
+  const double *vps;           // [sum n_vp][3]
+  NodeRecord *nodes;           // [nodes] out
+  uint8_t *row_state;          // [rows] out: 0 rejected, 1 candidate, 2 valid connection
+  double *row_cand;            // [rows][10] out (debug_mode only, else NULL)
+  unsigned long long *counters; // [4] n_candidates, n_valid, n_fp64_fallback, spare
+  char *slab;                  // global scratch for nodes whose rows exceed the smem capacity (or NULL)
+  int64_t slab_stride;         // bytes per CTA
+  int64_t node_begin, node_end;
+  int cap;                     // candidate capacity of the staging area
+  int use_slab;
+  // config (triangulation/base_line_triangulator.h:22-43, global_line_triangulator.h:11-25)
+  double min_length_2d, line_tri_angle_threshold, IoU_threshold, sensitivity_threshold, var2d, fullscore_th;
+  int max_valid_conns, use_endpoints_triangulation, disable_algebraic, use_vp, disable_vp;
+  int ranges_flag;
+  double rlo[3], rhi[3];
+  LinkerDev<double> l2d;  // user linker2d_config
+  LinkerDev<double> l3d;  // linker3d_config after set_to_shared_parent_scoring()
+};
+
+struct EdgeParams {
+  const NodeRecord *nodes;
+  const int64_t *edges; // [n][2] (a<b) node ids
+  double *weight;       // [n] out
+  int64_t n;
+  LinkerDev<double> l3d; // linker3d_config after set_to_spatial_merging()
+};
+
+size_t tri_smem_bytes(int cap);
+void launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem, cudaStream_t s);
+void launch_expand_rows(const int32_t *d_pairs, const int64_t *d_blk_row_off, const int32_t *d_blk_src_view,
+                        const int32_t *d_blk_ng_view, const int64_t *d_blk_pair_off, int n_blocks,
+                        const int64_t *d_line_off, int64_t n_rows, uint32_t *d_key, uint32_t *d_val,
+                        int *d_err, cudaStream_t s);
+void launch_expand_exhaustive(const int64_t *d_blk_row_off, const int32_t *d_blk_src_view,
+                              const int32_t *d_blk_ng_view, int n_blocks, const int64_t *d_line_off,
+                              int64_t n_rows, uint32_t *d_key, uint32_t *d_val, cudaStream_t s);
+void launch_node_offsets(const uint32_t *d_sorted_key, int64_t n_rows, int64_t n_nodes, uint32_t *d_node_row_off,
+                         unsigned int *d_max_rows, cudaStream_t s);
+void launch_collect_edges(const uint8_t *row_state, const uint32_t *row_ng, const uint32_t *node_row_off,
+                          const int64_t *line_off, int64_t node_begin, int64_t node_end, int64_t *edges,
+                          unsigned long long *count, cudaStream_t s);
+void launch_edge_weights(const EdgeParams &p, cudaStream_t s);
+
+} // namespace lm

@@ -1,0 +1,145 @@
+"""Array-level Python face of the CUDA engine (one lm_ctx). The limap-style classes in
+limap_b200.triangulation wrap this; bench.py and the parity tests call it directly."""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from .config import make_tri_config
+from ._cabi import Context, check, lib, ptr
+
+
+class TriEngine:
+    """GlobalLineTriangulator on flat arrays (src/limap/triangulation/global_line_triangulator.h:27-93)."""
+
+    def __init__(self, cfg=None, device=0):
+        self.ctx = Context(device)
+        self.cfg = make_tri_config(cfg) if not hasattr(cfg, "_fields_") else cfg
+        check(lib().lm_tri_configure(self.ctx.handle, C.byref(self.cfg)))
+        self.img_ids = None
+        self.line_off = None
+
+    # ---- scene ---------------------------------------------------------------------------------
+    def upload_scene(self, img_ids, model_ids, kvec, qvec, tvec, line_off, segs):
+        img_ids = np.ascontiguousarray(img_ids, np.int32)
+        model_ids = np.ascontiguousarray(model_ids, np.int32)
+        kvec = np.ascontiguousarray(kvec, np.float64)
+        qvec = np.ascontiguousarray(qvec, np.float64)
+        tvec = np.ascontiguousarray(tvec, np.float64)
+        line_off = np.ascontiguousarray(line_off, np.int64)
+        segs = np.ascontiguousarray(segs, np.float64)
+        check(lib().lm_scene_upload(self.ctx.handle, len(img_ids), ptr(img_ids), ptr(model_ids),
+                                    ptr(kvec), ptr(qvec), ptr(tvec), ptr(line_off), ptr(segs)))
+        self.img_ids = img_ids
+        self.line_off = line_off
+        self._view = {int(i): v for v, i in enumerate(img_ids)}
+
+    def upload(self, scene):
+        self.upload_scene(scene.img_ids, scene.model_ids, scene.kvec, scene.qvec, scene.tvec,
+                          scene.line_off, scene.segs)
+
+    def n_lines(self, img_id):
+        v = self._view[int(img_id)]
+        return int(self.line_off[v + 1] - self.line_off[v])
+
+    def set_ranges(self, lo, hi):
+        lo = np.ascontiguousarray(lo, np.float64)
+        hi = np.ascontiguousarray(hi, np.float64)
+        check(lib().lm_tri_set_ranges(self.ctx.handle, ptr(lo), ptr(hi)))
+
+    def unset_ranges(self):
+        check(lib().lm_tri_unset_ranges(self.ctx.handle))
+
+    # ---- TriangulateImage ----------------------------------------------------------------------
+    def add_image_matches(self, img_id, ng_ids, row_off, pairs):
+        ng_ids = np.ascontiguousarray(ng_ids, np.int32)
+        row_off = np.ascontiguousarray(row_off, np.int64)
+        pairs = np.ascontiguousarray(pairs, np.int32)
+        self.ctx._keep.append(pairs)  # the H2D copy is asynchronous when `pairs` is pinned
+        check(lib().lm_tri_add_image_matches(self.ctx.handle, int(img_id), len(ng_ids), ptr(ng_ids),
+                                             ptr(row_off), ptr(pairs)))
+
+    def add_image_matches_device(self, img_id, ng_ids, row_off, d_pairs_ptr):
+        ng_ids = np.ascontiguousarray(ng_ids, np.int32)
+        row_off = np.ascontiguousarray(row_off, np.int64)
+        check(lib().lm_tri_add_image_matches_device(self.ctx.handle, int(img_id), len(ng_ids),
+                                                    ptr(ng_ids), ptr(row_off), C.c_void_p(int(d_pairs_ptr))))
+
+    def add_image_matches_dict(self, img_id, matches):
+        """matches: {ng_img_id: (M,2) int array}; neighbours are visited in ascending id order
+        (std::map iteration, base_line_triangulator.cc:74)."""
+        ngs = sorted(matches.keys())
+        row_off = np.zeros(len(ngs) + 1, np.int64)
+        parts = []
+        for i, g in enumerate(ngs):
+            m = np.asarray(matches[g])
+            if m.size and (m.ndim != 2 or m.shape[1] != 2):
+                raise RuntimeError("match_info.cols() must be 2")  # THROW_CHECK_EQ(cols, 2)
+            m = m.reshape(-1, 2)
+            parts.append(m.astype(np.int32, copy=False))
+            row_off[i + 1] = row_off[i] + len(m)
+        pairs = np.concatenate(parts, 0) if parts else np.zeros((0, 2), np.int32)
+        self.add_image_matches(img_id, np.asarray(ngs, np.int32), row_off, pairs)
+
+    def add_image_exhaustive(self, img_id, neighbors):
+        ng = np.ascontiguousarray(neighbors, np.int32)
+        check(lib().lm_tri_add_image_exhaustive(self.ctx.handle, int(img_id), len(ng), ptr(ng)))
+
+    def clear(self):
+        check(lib().lm_tri_clear(self.ctx.handle))
+        self.ctx._keep.clear()
+
+    def set_shard(self, view_begin, view_end):
+        check(lib().lm_tri_set_shard(self.ctx.handle, int(view_begin), int(view_end)))
+
+    def run(self):
+        check(lib().lm_tri_run(self.ctx.handle))
+        self.ctx._keep.clear()
+        return self.ctx.stats()
+
+    # ---- results -------------------------------------------------------------------------------
+    def get_best(self, img_id):
+        L = self.n_lines(img_id)
+        line = np.zeros((L, 10), np.float64)
+        ng = np.zeros((L, 2), np.int32)
+        ncand = np.zeros(L, np.int32)
+        check(lib().lm_tri_get_best(self.ctx.handle, int(img_id), ptr(line), ptr(ng), ptr(ncand)))
+        return line, ng, ncand
+
+    def get_valid_edges(self, img_id):
+        L = self.n_lines(img_id)
+        off = np.zeros(L + 1, np.int64)
+        n = check(lib().lm_tri_get_valid_edges(self.ctx.handle, int(img_id), ptr(off), None))
+        edges = np.zeros((max(n, 1), 2), np.int32)
+        check(lib().lm_tri_get_valid_edges(self.ctx.handle, int(img_id), ptr(off), ptr(edges)))
+        return off, edges[:n]
+
+    def get_cands_node(self, img_id, line_id, cap=4096):
+        line = np.zeros((cap, 10), np.float64)
+        ng = np.zeros((cap, 2), np.int32)
+        n = check(lib().lm_tri_get_cands_node(self.ctx.handle, int(img_id), int(line_id), cap,
+                                              ptr(line), ptr(ng)))
+        if n > cap:
+            return self.get_cands_node(img_id, line_id, cap=n)
+        return line[:n], ng[:n]
+
+    def build_tracks(self):
+        tot = C.c_int64(0)
+        T = check(lib().lm_tri_build_tracks(self.ctx.handle, C.byref(tot)))
+        n = tot.value
+        track_off = np.zeros(T + 1, np.int64)
+        img = np.zeros(max(n, 1), np.int32)
+        line = np.zeros(max(n, 1), np.int32)
+        node = np.zeros(max(n, 1), np.int32)
+        l3d = np.zeros((max(n, 1), 10), np.float64)
+        tl = np.zeros((max(T, 1), 7), np.float64)
+        check(lib().lm_tri_get_tracks(self.ctx.handle, ptr(track_off), ptr(img), ptr(line), ptr(node),
+                                      ptr(l3d), ptr(tl)))
+        return dict(track_off=track_off, img_ids=img[:n], line_ids=line[:n], node_ids=node[:n],
+                    line3d=l3d[:n], track_line=tl[:T])
+
+    def stats(self):
+        return self.ctx.stats()
+
+    def close(self):
+        self.ctx.close()

@@ -1,0 +1,197 @@
+"""Seeded synthetic scenes of the shapes in BASELINE.json `configs`.
+
+Scene box [-5,5]^3 * scale with G ground-truth 3D segments, cameras on a radius-12*scale band looking
+at the origin (SIMPLE_PINHOLE f=692.82, cx=400, cy=300, 800x600 -- Hypersim after max_image_dim 800),
+per view L segments = projections of visible GT lines with N(0, noise_px) endpoint noise, random
+truncation and random start/end flips, padded with clutter; neighbours = N nearest cameras; matches
+per (line, neighbour) = the true correspondent (when visible) + nearest-midpoint decoys, K per line
+(mimics the top-k NN matcher, src/limap/line2d/endpoints/matcher.py:71-112).
+No dataset or network access is needed; everything derives from the seed.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class Scene:
+    img_ids: np.ndarray        # [V] int32, ascending
+    model_ids: np.ndarray      # [V] int32 (0 SIMPLE_PINHOLE)
+    kvec: np.ndarray           # [V,4] fx,fy,cx,cy
+    qvec: np.ndarray           # [V,4] wxyz
+    tvec: np.ndarray           # [V,3]
+    line_off: np.ndarray       # [V+1] int64
+    segs: np.ndarray           # [sum L,4] float64
+    gt_id: np.ndarray          # [sum L] int32 GT line of each segment (-1 clutter)
+    neighbors: dict            # img_id -> list of img ids
+    matches: dict              # img_id -> {ng_img_id: (M,2) int32}
+    ranges: tuple              # (lo[3], hi[3])
+    gt_lines: np.ndarray = field(default=None)  # [G,6]
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n_views(self):
+        return len(self.img_ids)
+
+    def n_rows(self, img_ids=None):
+        ids = self.matches.keys() if img_ids is None else img_ids
+        return int(sum(len(m) for i in ids for m in self.matches[i].values()))
+
+    def lines_of(self, view):
+        return self.segs[self.line_off[view]:self.line_off[view + 1]]
+
+    def flat_matches(self, img_id):
+        """(ng_ids[n], row_off[n+1], pairs[rows,2]) of one image, neighbours ascending (std::map order)."""
+        m = self.matches[img_id]
+        ngs = sorted(m.keys())
+        row_off = np.zeros(len(ngs) + 1, np.int64)
+        for i, g in enumerate(ngs):
+            row_off[i + 1] = row_off[i] + len(m[g])
+        pairs = (np.concatenate([m[g] for g in ngs], axis=0) if ngs else np.zeros((0, 2), np.int32))
+        return np.asarray(ngs, np.int32), row_off, np.ascontiguousarray(pairs, dtype=np.int32)
+
+
+def _rot_to_quat(R):
+    """Eigen-style (Shepperd) rotation matrix -> quaternion wxyz."""
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0)
+        w = 0.5 * s
+        s = 0.5 / s
+        return np.array([w, (R[2, 1] - R[1, 2]) * s, (R[0, 2] - R[2, 0]) * s, (R[1, 0] - R[0, 1]) * s])
+    i = int(np.argmax(np.diag(R)))
+    j, k = (i + 1) % 3, (i + 2) % 3
+    s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0)
+    q = np.zeros(4)
+    q[1 + i] = 0.5 * s
+    s = 0.5 / s
+    q[0] = (R[k, j] - R[j, k]) * s
+    q[1 + j] = (R[j, i] + R[i, j]) * s
+    q[1 + k] = (R[k, i] + R[i, k]) * s
+    return q
+
+
+def make_scene(V=10, L=100, N=5, K=4, seed=1234, scale=1.0, noise_px=0.5, G=None, id_stride=1,
+               width=800, height=600, focal=692.82, shuffle_rows=False):
+    rng = np.random.default_rng(seed)
+    G = int(L * 1.3) if G is None else G
+    # ground-truth 3D segments
+    mid = rng.uniform(-5, 5, (G, 3))
+    d = rng.normal(size=(G, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    half = rng.uniform(0.25, 1.5, (G, 1))
+    P0 = np.clip(mid - d * half, -5, 5) * scale
+    P1 = np.clip(mid + d * half, -5, 5) * scale
+    gt_lines = np.concatenate([P0, P1], axis=1)
+    # cameras on a band of a sphere looking at the origin
+    az = rng.uniform(0, 2 * np.pi, V)
+    el = rng.uniform(-0.5, 0.5, V)
+    rad = 12.0 * scale * rng.uniform(0.95, 1.05, V)
+    Cs = np.stack([rad * np.cos(el) * np.cos(az), rad * np.cos(el) * np.sin(az), rad * np.sin(el)], 1)
+    kvec = np.tile(np.array([focal, focal, width / 2.0, height / 2.0]), (V, 1))
+    qvec = np.zeros((V, 4))
+    tvec = np.zeros((V, 3))
+    Rs = np.zeros((V, 3, 3))
+    for v in range(V):
+        z = -Cs[v] / np.linalg.norm(Cs[v])
+        up = np.array([0.0, 0.0, 1.0]) + rng.normal(scale=0.05, size=3)
+        x = np.cross(z, up)
+        x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        R = np.stack([x, y, z], 0)
+        Rs[v] = R
+        qvec[v] = _rot_to_quat(R)
+        tvec[v] = -R @ Cs[v]
+    img_ids = (np.arange(V) * id_stride + (3 if id_stride > 1 else 0)).astype(np.int32)
+
+    segs_all, gt_all, line_off = [], [], [0]
+    line_of_gt = -np.ones((V, G), np.int64)
+    for v in range(V):
+        R, t = Rs[v], tvec[v]
+        Xc0 = P0 @ R.T + t
+        Xc1 = P1 @ R.T + t
+        ok = (Xc0[:, 2] > 0.5 * scale) & (Xc1[:, 2] > 0.5 * scale)
+        p0 = Xc0[:, :2] / Xc0[:, 2:3] * focal + kvec[v, 2:4]
+        p1 = Xc1[:, :2] / Xc1[:, 2:3] * focal + kvec[v, 2:4]
+        inside = lambda p: (p[:, 0] >= 0) & (p[:, 0] <= width) & (p[:, 1] >= 0) & (p[:, 1] <= height)
+        ok &= inside(p0) & inside(p1) & (np.linalg.norm(p1 - p0, axis=1) > 8.0)
+        vis = np.flatnonzero(ok)
+        rng.shuffle(vis)
+        vis = vis[:L]
+        a, b = p0[vis].copy(), p1[vis].copy()
+        # random truncation along the line, noise, random flips
+        ta = rng.uniform(0.0, 0.2, (len(vis), 1))
+        tb = rng.uniform(0.0, 0.2, (len(vis), 1))
+        a2 = a + (b - a) * ta
+        b2 = b - (b - a) * tb
+        a2 += rng.normal(scale=noise_px, size=a2.shape)
+        b2 += rng.normal(scale=noise_px, size=b2.shape)
+        flip = rng.random(len(vis)) < 0.5
+        s = np.where(flip[:, None], b2, a2)
+        e = np.where(flip[:, None], a2, b2)
+        seg = np.concatenate([s, e], 1)
+        gt = vis.astype(np.int32)
+        n_clutter = L - len(vis)
+        if n_clutter > 0:
+            c0 = rng.uniform([0, 0], [width, height], (n_clutter, 2))
+            ang = rng.uniform(0, np.pi, n_clutter)
+            ln = rng.uniform(10, 120, n_clutter)
+            c1 = c0 + np.stack([np.cos(ang), np.sin(ang)], 1) * ln[:, None]
+            seg = np.concatenate([seg, np.concatenate([c0, c1], 1)], 0)
+            gt = np.concatenate([gt, -np.ones(n_clutter, np.int32)])
+        perm = rng.permutation(len(seg))
+        seg, gt = seg[perm], gt[perm]
+        line_of_gt[v, gt[gt >= 0]] = np.flatnonzero(gt >= 0)
+        segs_all.append(seg)
+        gt_all.append(gt)
+        line_off.append(line_off[-1] + len(seg))
+    segs = np.ascontiguousarray(np.concatenate(segs_all, 0), dtype=np.float64)
+    gt_id = np.concatenate(gt_all)
+    line_off = np.asarray(line_off, np.int64)
+
+    # neighbours: N nearest camera centres
+    D = np.linalg.norm(Cs[:, None, :] - Cs[None, :, :], axis=2)
+    np.fill_diagonal(D, np.inf)
+    Nn = min(N, V - 1)
+    nb_idx = np.argsort(D, axis=1)[:, :Nn]
+    neighbors = {int(img_ids[v]): [int(img_ids[u]) for u in nb_idx[v]] for v in range(V)}
+
+    # matches with decoys
+    from scipy.spatial import cKDTree
+    mids = [(s[:, :2] + s[:, 2:]) * 0.5 for s in segs_all]
+    trees = [cKDTree(m) for m in mids]
+    matches = {}
+    for v in range(V):
+        mv = {}
+        Lv = len(segs_all[v])
+        for u in nb_idx[v]:
+            Lu = len(segs_all[u])
+            kk = min(K, Lu)
+            g = gt_all[v]
+            tgt = np.where(g >= 0, line_of_gt[u, np.maximum(g, 0)], -1)
+            qpts = np.where((tgt >= 0)[:, None], mids[u][np.maximum(tgt, 0)], mids[v])
+            _, nn = trees[u].query(qpts, k=kk)
+            nn = nn.reshape(Lv, kk)
+            # make sure the true correspondent is the first candidate when it exists
+            has = tgt >= 0
+            nn[has, 0] = tgt[has]
+            rows = np.stack([np.repeat(np.arange(Lv), kk), nn.reshape(-1)], 1).astype(np.int32)
+            if shuffle_rows:
+                rows = rows[rng.permutation(len(rows))]
+            mv[int(img_ids[u])] = np.ascontiguousarray(rows)
+        matches[int(img_ids[v])] = mv
+    lo = np.array([-5.0, -5.0, -5.0]) * scale * 1.25
+    hi = np.array([5.0, 5.0, 5.0]) * scale * 1.25
+    return Scene(img_ids=img_ids, model_ids=np.zeros(V, np.int32), kvec=np.ascontiguousarray(kvec),
+                 qvec=np.ascontiguousarray(qvec), tvec=np.ascontiguousarray(tvec), line_off=line_off,
+                 segs=segs, gt_id=gt_id, neighbors=neighbors, matches=matches, ranges=(lo, hi),
+                 gt_lines=gt_lines, meta=dict(V=V, L=L, N=N, K=K, seed=seed, scale=scale,
+                                              noise_px=noise_px))
+
+
+# BASELINE.json `configs` -> generator arguments
+CONFIGS = {
+    "hypersim10": dict(V=10, L=800, N=9, K=10, seed=1234),              # configs[0] stand-in
+    "hypersim100": dict(V=100, L=1000, N=20, K=10, seed=1235),          # configs[1] (the metric's config)
+    "sweep500": dict(V=500, L=400, N=40, K=10, seed=1236),              # configs[2]
+}

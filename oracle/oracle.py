@@ -1,0 +1,172 @@
+"""ctypes wrapper of the CPU oracle (oracle/_build/liblimap_oracle.so). TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+PARITY UNPINNED -- see oracle/orc_geom.h."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "liblimap_oracle.so")
+_lib = None
+_P = C.c_void_p
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    if force or not os.path.exists(LIB_PATH) or any(
+            os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
+        env = dict(os.environ)
+        env.pop("CXX", None)
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, env=env,
+                       stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_tri_create.restype = _P
+        L.orc_tri_create.argtypes = [_P]
+        L.orc_tri_destroy.argtypes = [_P]
+        L.orc_tri_init.argtypes = [_P, C.c_int] + [_P] * 7
+        L.orc_tri_set_ranges.argtypes = [_P, _P, _P]
+        L.orc_tri_unset_ranges.argtypes = [_P]
+        L.orc_tri_triangulate_image.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P]
+        L.orc_tri_triangulate_image_exhaustive.argtypes = [_P, C.c_int, C.c_int, _P]
+        L.orc_tri_rows_tested.restype = C.c_longlong
+        L.orc_tri_rows_tested.argtypes = [_P]
+        L.orc_tri_get_best.argtypes = [_P, C.c_int, _P, _P, _P]
+        L.orc_tri_get_valid_edges.restype = C.c_longlong
+        L.orc_tri_get_valid_edges.argtypes = [_P, C.c_int, _P, _P]
+        L.orc_tri_get_tris_node.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, _P]
+        L.orc_tri_compute_tracks.argtypes = [_P, _P]
+        L.orc_tri_get_tracks.argtypes = [_P] * 7
+        L.orc_tri_get_graph.restype = C.c_longlong
+        L.orc_tri_get_graph.argtypes = [_P] * 5
+        L.orc_line2d_length.restype = C.c_double
+        L.orc_line2d_length.argtypes = [_P]
+        L.orc_line2d_direction.argtypes = [_P, _P]
+        L.orc_compute_epipolar_IoU.restype = C.c_double
+        L.orc_compute_epipolar_IoU.argtypes = [_P] * 4
+        L.orc_triangulate_line.argtypes = [_P, _P, _P, _P, C.c_int, _P]
+        L.orc_project_point.argtypes = [_P, _P, _P]
+        L.orc_score_3d.restype = C.c_double
+        L.orc_score_3d.argtypes = [_P, _P, _P]
+        L.orc_score_2d.restype = C.c_double
+        L.orc_score_2d.argtypes = [_P, _P, _P]
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_P)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+class OracleTri:
+    """fp64 CPU restatement of GlobalLineTriangulator, same array-level interface as
+    limap_b200.engine.TriEngine."""
+
+    def __init__(self, cfg=None, threads=None):
+        from limap_b200.config import make_tri_config
+        self.cfg = make_tri_config(cfg) if not hasattr(cfg, "_fields_") else cfg
+        L = lib()
+        if threads:
+            L.orc_set_num_threads(int(threads))
+        self._h = L.orc_tri_create(C.byref(self.cfg))
+        if not self._h:
+            raise RuntimeError(L.orc_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_tri_destroy(self._h)
+            self._h = None
+
+    def upload_scene(self, img_ids, model_ids, kvec, qvec, tvec, line_off, segs):
+        self.img_ids = np.ascontiguousarray(img_ids, np.int32)
+        self.line_off = np.ascontiguousarray(line_off, np.int64)
+        self._view = {int(i): v for v, i in enumerate(self.img_ids)}
+        a = [self.img_ids, np.ascontiguousarray(model_ids, np.int32), _f64(kvec), _f64(qvec), _f64(tvec),
+             self.line_off, _f64(segs)]
+        lib().orc_tri_init(self._h, len(self.img_ids), *[_p(x) for x in a])
+
+    def upload(self, scene):
+        self.upload_scene(scene.img_ids, scene.model_ids, scene.kvec, scene.qvec, scene.tvec,
+                          scene.line_off, scene.segs)
+
+    def n_lines(self, img_id):
+        v = self._view[int(img_id)]
+        return int(self.line_off[v + 1] - self.line_off[v])
+
+    def set_ranges(self, lo, hi):
+        lib().orc_tri_set_ranges(self._h, _p(_f64(lo)), _p(_f64(hi)))
+
+    def add_image_matches(self, img_id, ng_ids, row_off, pairs):
+        ng_ids = np.ascontiguousarray(ng_ids, np.int32)
+        row_off = np.ascontiguousarray(row_off, np.int64)
+        pairs = np.ascontiguousarray(pairs, np.int32)
+        rc = lib().orc_tri_triangulate_image(self._h, int(img_id), len(ng_ids), _p(ng_ids), _p(row_off),
+                                             _p(pairs))
+        if rc:
+            raise RuntimeError(lib().orc_last_error().decode())
+
+    def add_image_exhaustive(self, img_id, neighbors):
+        ng = np.ascontiguousarray(neighbors, np.int32)
+        rc = lib().orc_tri_triangulate_image_exhaustive(self._h, int(img_id), len(ng), _p(ng))
+        if rc:
+            raise RuntimeError(lib().orc_last_error().decode())
+
+    def rows_tested(self):
+        return int(lib().orc_tri_rows_tested(self._h))
+
+    def get_best(self, img_id):
+        L = self.n_lines(img_id)
+        line = np.zeros((L, 10))
+        ng = np.zeros((L, 2), np.int32)
+        nc = np.zeros(L, np.int32)
+        lib().orc_tri_get_best(self._h, int(img_id), _p(line), _p(ng), _p(nc))
+        return line, ng, nc
+
+    def get_valid_edges(self, img_id):
+        L = self.n_lines(img_id)
+        off = np.zeros(L + 1, np.int64)
+        n = lib().orc_tri_get_valid_edges(self._h, int(img_id), _p(off), None)
+        edges = np.zeros((max(n, 1), 2), np.int32)
+        lib().orc_tri_get_valid_edges(self._h, int(img_id), _p(off), _p(edges))
+        return off, edges[:n]
+
+    def get_cands_node(self, img_id, line_id, cap=4096):
+        line = np.zeros((cap, 10))
+        ng = np.zeros((cap, 2), np.int32)
+        n = lib().orc_tri_get_tris_node(self._h, int(img_id), int(line_id), cap, _p(line), _p(ng))
+        if n > cap:
+            return self.get_cands_node(img_id, line_id, n)
+        return line[:n], ng[:n]
+
+    def build_tracks(self):
+        tot = C.c_int64(0)
+        T = lib().orc_tri_compute_tracks(self._h, C.byref(tot))
+        n = tot.value
+        track_off = np.zeros(T + 1, np.int64)
+        img = np.zeros(max(n, 1), np.int32)
+        line = np.zeros(max(n, 1), np.int32)
+        node = np.zeros(max(n, 1), np.int32)
+        l3d = np.zeros((max(n, 1), 10))
+        tl = np.zeros((max(T, 1), 7))
+        lib().orc_tri_get_tracks(self._h, _p(track_off), _p(img), _p(line), _p(node), _p(l3d), _p(tl))
+        return dict(track_off=track_off, img_ids=img[:n], line_ids=line[:n], node_ids=node[:n],
+                    line3d=l3d[:n], track_line=tl[:T])
+
+
+def cam_array(model, kvec, qvec, tvec):
+    return _f64([model, *kvec, *qvec, *tvec])

@@ -1,0 +1,132 @@
+"""GPU parity: CUDA engine through the C ABI vs the fp64 CPU oracle on the same seeded scenes."""
+import numpy as np
+import pytest
+
+from limap_b200.config import DEFAULT_YAML_TRIANGULATION
+from limap_b200.synth import make_scene
+
+from parity_utils import compare_nodes, compare_tracks, run_both
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(**kw):
+    c = dict(DEFAULT_YAML_TRIANGULATION)
+    c.update(kw)
+    return c
+
+
+def test_small_scene_debug_candidates():
+    sc = make_scene(V=6, L=80, N=4, K=4, seed=11)
+    eng, orc = run_both(sc, _cfg(debug_mode=True))
+    st = compare_nodes(sc, eng, orc, debug=True)
+    assert st["candidates"] > 500 and st["valid_edges"] > 100
+    assert eng.stats()["n_candidates"] == st["candidates"]
+    assert eng.stats()["n_rows"] == sc.n_rows()
+    tr = compare_tracks(eng, orc)
+    assert tr["tracks"] > 20
+
+
+def test_medium_scene_default_yaml():
+    sc = make_scene(V=12, L=300, N=8, K=10, seed=12)
+    eng, orc = run_both(sc, _cfg())
+    st = compare_nodes(sc, eng, orc)
+    assert st["valid_edges"] > 1000
+    tr = compare_tracks(eng, orc)
+    assert tr["tracks"] > 100
+
+
+def test_cpp_defaults_and_outer_edge_filter():
+    # C++ defaults differ from the yaml (min_length_2d 20, angle 5, min_num_outer_edges 1, linker thresholds)
+    sc = make_scene(V=8, L=120, N=5, K=5, seed=13)
+    eng, orc = run_both(sc, {})
+    compare_nodes(sc, eng, orc)
+    compare_tracks(eng, orc)
+
+
+def test_asset_unit_scale_non_contiguous_ids_shuffled_rows():
+    # Hypersim asset units (|X| ~ 1e3), image ids with gaps, match rows not sorted by line id
+    sc = make_scene(V=8, L=100, N=5, K=4, seed=14, scale=100.0, id_stride=7, shuffle_rows=True)
+    eng, orc = run_both(sc, _cfg(debug_mode=True))
+    compare_nodes(sc, eng, orc, debug=True)
+    compare_tracks(eng, orc)
+
+
+def test_endpoints_triangulation_and_halfpix_no_ranges():
+    sc = make_scene(V=6, L=80, N=4, K=4, seed=15)
+    eng, orc = run_both(sc, _cfg(use_endpoints_triangulation=True, add_halfpix=True), use_ranges=False)
+    compare_nodes(sc, eng, orc)
+    compare_tracks(eng, orc)
+
+
+def test_max_valid_conns_cap():
+    sc = make_scene(V=6, L=60, N=5, K=8, seed=16)
+    eng, orc = run_both(sc, _cfg(max_valid_conns=3))
+    compare_nodes(sc, eng, orc)
+    compare_tracks(eng, orc)
+
+
+def test_exhaustive_matcher():
+    # TriangulateImageExhaustiveMatch: every line of every neighbour (CI E2E mode of the reference)
+    sc = make_scene(V=5, L=40, N=3, K=2, seed=17)
+    eng, orc = run_both(sc, _cfg(), exhaustive=True)
+    compare_nodes(sc, eng, orc)
+    compare_tracks(eng, orc)
+
+
+def test_empty_and_ragged_inputs():
+    sc = make_scene(V=5, L=30, N=3, K=3, seed=18)
+    # image 0 has no matches at all, image 1 has an empty table for one neighbour
+    i0, i1 = int(sc.img_ids[0]), int(sc.img_ids[1])
+    sc.matches[i0] = {}
+    g = sorted(sc.matches[i1].keys())[0]
+    sc.matches[i1][g] = np.zeros((0, 2), np.int32)
+    eng, orc = run_both(sc, _cfg())
+    compare_nodes(sc, eng, orc)
+    compare_tracks(eng, orc)
+
+
+def test_out_of_range_match_raises():
+    from limap_b200._cabi import LimapB200Error
+    from limap_b200.engine import TriEngine
+    sc = make_scene(V=4, L=20, N=2, K=2, seed=19)
+    eng = TriEngine(_cfg())
+    eng.upload(sc)
+    i = int(sc.img_ids[0])
+    ng, off, pairs = sc.flat_matches(i)
+    pairs = pairs.copy()
+    pairs[0, 0] = 10_000
+    eng.add_image_matches(i, ng, off, pairs)
+    with pytest.raises(LimapB200Error, match="IndexError"):
+        eng.run()
+
+
+def test_full_size_properties_hypersim100_shape():
+    """BASELINE.json configs[1] shape (V=100 scaled down in L to keep the test short): size-independent
+    properties -- every valid connection's candidate exists, scores are >= fullscore_th, best is the
+    arg-max, rerun is idempotent, sharded runs agree with the full run."""
+    sc = make_scene(V=40, L=400, N=10, K=10, seed=20)
+    from limap_b200.engine import TriEngine
+    eng = TriEngine(_cfg())
+    eng.upload(sc)
+    eng.set_ranges(*sc.ranges)
+    for i in sc.img_ids:
+        eng.add_image_matches(int(i), *sc.flat_matches(int(i)))
+    s1 = eng.run()
+    best1 = [eng.get_best(int(i)) for i in sc.img_ids]
+    s2 = eng.run()
+    assert s1["n_candidates"] == s2["n_candidates"] and s1["n_valid_edges"] == s2["n_valid_edges"]
+    for (a, b, c), i in zip(best1, sc.img_ids):
+        a2, b2, c2 = eng.get_best(int(i))
+        assert np.array_equal(a, a2) and np.array_equal(b, b2) and np.array_equal(c, c2)
+    assert s1["n_rows"] == sc.n_rows()
+    # shard [0,20) + [20,40) == full
+    tot = 0
+    for lo, hi in ((0, 20), (20, 40)):
+        eng.set_shard(lo, hi)
+        st = eng.run()
+        tot += st["n_candidates"]
+        for v in range(lo, hi):
+            a2, b2, c2 = eng.get_best(int(sc.img_ids[v]))
+            assert np.array_equal(best1[v][0], a2) and np.array_equal(best1[v][2], c2)
+    assert tot == s1["n_candidates"]
