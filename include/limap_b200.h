@@ -60,6 +60,7 @@ typedef struct lm_tri_stats {
   int64_t n_fp64_pair_fallbacks; /* pair scores re-evaluated in fp64 by the guard band */
   int64_t max_rows_per_node;
   double last_run_ms;    /* device time of the last lm_tri_run (CUDA events on the ctx stream) */
+  double last_node_kernel_ms; /* device time of its fused generate+score kernel alone */
 } lm_tri_stats;
 
 const char *lm_last_error(void);
@@ -153,6 +154,43 @@ int64_t lm_tri_build_tracks(lm_ctx *ctx, int64_t *n_support_total);
  * depths2,uncertainty,score); per track: line[7] = start3,end3,uncertainty. */
 int lm_tri_get_tracks(lm_ctx *ctx, int64_t *track_off, int32_t *img_ids, int32_t *line_ids,
                       int32_t *node_ids, double *node_line3d, double *track_line);
+
+/* ---- line refinement / line bundle adjustment (cameras constant) ---------------------------------
+ * Replaces HybridBAEngine::{InitLineTracks,SetUp,Solve,GetOutputLineTracks}
+ * (optimize/hybrid_bundle_adjustment/hybrid_bundle_adjustment.cc:39-59,156-264,298-310) as called by
+ * solve_line_bundle_adjustment (optimize/hybrid_bundle_adjustment/solve.py:31-39), and
+ * RefinementEngine::{Initialize,SetUp,Solve,GetLine3d} (optimize/line_refinement/refine.cc:19-198):
+ * every track is an independent 4-dof Levenberg-Marquardt problem solved by one warp.
+ * config: HybridBAConfig / RefinementConfig fields used on this path
+ * (optimize/line_refinement/refinement_config.h:18-92). */
+typedef struct lm_ba_config {
+  double geometric_alpha;   /* 10.0 */
+  double cauchy_scale;      /* CauchyLoss(0.25) */
+  int32_t max_num_iterations; /* 100 (runners pass 200) */
+  int32_t min_num_images;     /* 4: tracks seen in fewer distinct images stay constant */
+  int32_t num_outliers;       /* num_outliers_aggregate = 2 */
+  int32_t max_num_consecutive_invalid_steps; /* 10 */
+} lm_ba_config;
+
+typedef struct lm_ba_stats {
+  int64_t n_tracks, n_blocks;
+  int64_t total_iterations;  /* sum over tracks of LM iterations executed (the M2 numerator) */
+  int64_t total_successful;
+  double solve_ms;           /* device time of the LM kernel (CUDA events on the ctx stream) */
+  double prepare_ms;         /* device time of the block-digest kernel */
+} lm_ba_stats;
+
+/* Cameras: kvec[n_views][4], qvec[n_views][4], tvec[n_views][3]. Tracks: sup_off[T+1]; per supporting
+ * 2D line k: sup_view[k] (index into the camera arrays; also the image identity for count_images),
+ * segs[k][4], line3d[k][6] (track.line3d_list, used only to cut the output segment,
+ * base/infinite_line.cc:265-287); line_init[T][6] = track.line. Outputs: out_line[T][6] refined segment,
+ * out_minimal[T][6] = (uvec, wvec), out_iters[T][2] = (iterations, successful), out_cost[T][2] =
+ * (initial, final) cost. Any output may be NULL. */
+int lm_ba_solve(lm_ctx *ctx, int32_t n_views, const double *kvec, const double *qvec, const double *tvec,
+                int64_t n_tracks, const int64_t *sup_off, const int32_t *sup_view, const double *segs,
+                const double *line3d, const double *line_init, const lm_ba_config *cfg, double *out_line,
+                double *out_minimal, int32_t *out_iters, double *out_cost);
+int lm_ba_get_stats(lm_ctx *ctx, lm_ba_stats *out);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,18 @@ class TriStats(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("n_candidates", C.c_int64), ("n_valid_edges", C.c_int64),
                 ("n_nodes", C.c_int64), ("n_kernel_launches", C.c_int64),
                 ("n_fp64_pair_fallbacks", C.c_int64), ("max_rows_per_node", C.c_int64),
-                ("last_run_ms", C.c_double)]
+                ("last_run_ms", C.c_double), ("last_node_kernel_ms", C.c_double)]
+
+
+class BAConfig(C.Structure):
+    _fields_ = [("geometric_alpha", C.c_double), ("cauchy_scale", C.c_double),
+                ("max_num_iterations", C.c_int32), ("min_num_images", C.c_int32),
+                ("num_outliers", C.c_int32), ("max_num_consecutive_invalid_steps", C.c_int32)]
+
+
+class BAStats(C.Structure):
+    _fields_ = [("n_tracks", C.c_int64), ("n_blocks", C.c_int64), ("total_iterations", C.c_int64),
+                ("total_successful", C.c_int64), ("solve_ms", C.c_double), ("prepare_ms", C.c_double)]
 
 
 NODE_RECORD_DTYPE = np.dtype([("line", np.float64, 9), ("score", np.float64), ("ng_view", np.int32),
@@ -58,6 +69,8 @@ _SIGS = {
     "lm_scene_node_offset": (C.c_int64, [_P, C.c_int32]),
     "lm_tri_build_tracks": (C.c_int64, [_P, C.POINTER(C.c_int64)]),
     "lm_tri_get_tracks": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "lm_ba_solve": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "lm_ba_get_stats": (C.c_int, [_P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

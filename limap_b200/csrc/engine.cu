@@ -11,10 +11,12 @@
 // There is no CPU fallback: without a CUDA device lm_ctx_create fails with LM_ERR_NOGPU.
 #include "../../include/limap_b200.h"
 #include "tri_kernels.cuh"
+#include "lm_kernels.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <map>
 #include <queue>
@@ -108,7 +110,7 @@ struct lm_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   int sm_count = 148;
   int max_smem_optin = 0;
   // scene
@@ -140,6 +142,7 @@ struct lm_ctx {
   DevBuf d_node_row_off, d_scalars; // scalars: [0] max_rows(uint) [1] err(int) ; counters at +16
   DevBuf d_nodes, d_row_state, d_row_cand, d_slab;
   DevBuf d_edges, d_edges2, d_edge_keys, d_edge_keys2, d_edge_w, d_edge_cnt;
+  DevBuf d_nvalid, d_edge_off, d_edge_ng; // compact valid_edges_ of the shard (node-major, candidate order)
   uint32_t *sorted_val = nullptr;
   uint32_t *sorted_key = nullptr;
   int64_t n_rows = 0;
@@ -153,8 +156,13 @@ struct lm_ctx {
   std::vector<uint32_t> h_node_row_off, h_row_ng;
   std::vector<uint8_t> h_row_state;
   std::vector<double> h_row_cand;
+  bool h_edges_valid = false;
+  std::vector<uint32_t> h_edge_off, h_edge_ng;
   int64_t n_edges_dev = 0; // directed valid edges collected on device
   bool edges_collected = false;
+  // line BA
+  DevBuf d_ba_in, d_ba_blocks, d_ba_out;
+  lm_ba_stats ba_stats;
   // tracks
   std::vector<Track> tracks;
   std::vector<std::pair<int, int>> graph_nodes;
@@ -196,6 +204,22 @@ int fetch_rows(lm_ctx *c) {
   return LM_OK;
 }
 
+int fetch_edges(lm_ctx *c) {
+  if (c->h_edges_valid) return LM_OK;
+  const int64_t n = c->node_end - c->node_begin;
+  c->h_edge_off.assign(n + 1, 0);
+  c->h_edge_ng.resize(c->stats.n_valid_edges);
+  if (n > 0) {
+    CU(cudaMemcpyAsync(c->h_edge_off.data(), c->d_edge_off.p, 4 * (n + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (c->stats.n_valid_edges)
+      CU(cudaMemcpyAsync(c->h_edge_ng.data(), c->d_edge_ng.p, 4 * c->stats.n_valid_edges, cudaMemcpyDeviceToHost,
+                         c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  c->h_edges_valid = true;
+  return LM_OK;
+}
+
 int ensure_ran(lm_ctx *c) {
   if (c->ran) return LM_OK;
   return lm_tri_run(c);
@@ -223,9 +247,12 @@ int lm_ctx_create(int device, lm_ctx **out) {
   c->own_stream = true;
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
+  CU(cudaEventCreate(&c->evk0));
+  CU(cudaEventCreate(&c->evk1));
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   memset(&c->stats, 0, sizeof(c->stats));
+  memset(&c->ba_stats, 0, sizeof(c->ba_stats));
   *out = c;
   return LM_OK;
 }
@@ -238,10 +265,12 @@ void lm_ctx_destroy(lm_ctx *c) {
                     &c->d_blk_src, &c->d_blk_ng, &c->d_blk_pair_off, &c->d_key, &c->d_key2, &c->d_val, &c->d_val2,
                     &c->d_sort_tmp, &c->d_node_row_off, &c->d_scalars, &c->d_nodes, &c->d_row_state, &c->d_row_cand,
                     &c->d_slab, &c->d_edges, &c->d_edges2, &c->d_edge_keys, &c->d_edge_keys2, &c->d_edge_w,
-                    &c->d_edge_cnt};
+                    &c->d_edge_cnt, &c->d_nvalid, &c->d_edge_off, &c->d_edge_ng, &c->d_ba_in, &c->d_ba_blocks, &c->d_ba_out};
   for (DevBuf *b : bufs) b->release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->evk0) cudaEventDestroy(c->evk0);
+  if (c->evk1) cudaEventDestroy(c->evk1);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -371,7 +400,7 @@ int lm_tri_clear(lm_ctx *c) {
   c->pairs_rows = 0;
   c->any_exhaustive = c->any_matches = false;
   c->ran = false;
-  c->h_nodes_valid = c->h_rows_valid = false;
+  c->h_nodes_valid = c->h_rows_valid = c->h_edges_valid = false;
   c->edges_collected = false;
   c->tracks.clear();
   c->graph_nodes.clear();
@@ -495,7 +524,7 @@ int lm_tri_run(lm_ctx *c) {
   c->n_rows = n_rows;
   c->node_begin = c->line_off[vb];
   c->node_end = c->line_off[ve];
-  c->h_nodes_valid = c->h_rows_valid = false;
+  c->h_nodes_valid = c->h_rows_valid = c->h_edges_valid = false;
   c->edges_collected = false;
   c->tracks.clear();
 
@@ -613,15 +642,36 @@ int lm_tri_run(lm_ctx *c) {
     p.slab = c->d_slab.as<char>();
     smem = 0;
   }
+  CU(cudaEventRecord(c->evk0, s));
   if (n_shard_nodes > 0) {
     lm::launch_tri_node_kernel(p, grid, 128, smem, s);
     ++launches;
+  }
+  CU(cudaEventRecord(c->evk1, s));
+  // valid_edges_ in compact form: per-node counts -> exclusive scan -> ordered scatter
+  if (n_shard_nodes > 0) {
+    CU(c->d_nvalid.ensure(4 * (n_shard_nodes + 1)));
+    CU(c->d_edge_off.ensure(4 * (n_shard_nodes + 1)));
+    CU(c->d_edge_ng.ensure(4 * std::max<int64_t>(n_rows, 1)));
+    lm::launch_extract_nvalid(p.nodes, c->node_begin, n_shard_nodes, c->d_nvalid.as<uint32_t>(), s);
+    size_t tmp = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_nvalid.as<uint32_t>(), c->d_edge_off.as<uint32_t>(),
+                                     (int)(n_shard_nodes + 1), s));
+    CU(c->d_sort_tmp.ensure(tmp));
+    CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp, c->d_nvalid.as<uint32_t>(), c->d_edge_off.as<uint32_t>(),
+                                     (int)(n_shard_nodes + 1), s));
+    lm::launch_compact_edges_only(p.row_state, p.row_ng, p.node_row_off, c->d_edge_off.as<uint32_t>(), c->node_begin,
+                                  n_shard_nodes, c->d_edge_ng.as<uint32_t>(), s);
+    launches += 4;
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev1, s));
   CU(cudaStreamSynchronize(s));
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  float msk = 0;
+  CU(cudaEventElapsedTime(&msk, c->evk0, c->evk1));
+  c->stats.last_node_kernel_ms = msk;
   unsigned long long cnt[4];
   CU(cudaMemcpy(cnt, d_counters, 32, cudaMemcpyDeviceToHost));
   c->stats.n_rows = n_rows;
@@ -664,23 +714,26 @@ int64_t lm_tri_get_valid_edges(lm_ctx *c, int32_t img_id, int64_t *off, int32_t 
   if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
   int rc = ensure_ran(c);
   if (rc) return rc;
-  if ((rc = fetch_rows(c))) return rc;
+  if ((rc = fetch_edges(c))) return rc;
   auto it = c->id2view.find(img_id);
   if (it == c->id2view.end()) return fail(LM_ERR_INVALID, "unknown image id");
   const int v = it->second;
+  const int64_t L = c->line_off[v + 1] - c->line_off[v];
+  const bool in_shard = c->line_off[v] >= c->node_begin && c->line_off[v + 1] <= c->node_end;
   int64_t n_out = 0;
-  for (int64_t n = c->line_off[v]; n < c->line_off[v + 1]; ++n) {
-    if (off) off[n - c->line_off[v]] = n_out;
-    for (uint32_t r = c->h_node_row_off[n]; r < c->h_node_row_off[n + 1]; ++r) {
-      if (c->h_row_state[r] != 2) continue;
+  for (int64_t l = 0; l < L; ++l) {
+    if (off) off[l] = n_out;
+    if (!in_shard) continue;
+    const int64_t i = c->line_off[v] + l - c->node_begin;
+    for (uint32_t e = c->h_edge_off[i]; e < c->h_edge_off[i + 1]; ++e) {
       if (edges) {
-        edges[2 * n_out] = c->img_ids[c->h_row_ng[r] >> 16];
-        edges[2 * n_out + 1] = (int32_t)(c->h_row_ng[r] & 0xffffu);
+        edges[2 * n_out] = c->img_ids[c->h_edge_ng[e] >> 16];
+        edges[2 * n_out + 1] = (int32_t)(c->h_edge_ng[e] & 0xffffu);
       }
       ++n_out;
     }
   }
-  if (off) off[c->line_off[v + 1] - c->line_off[v]] = n_out;
+  if (off) off[L] = n_out;
   return n_out;
 }
 
@@ -731,18 +784,12 @@ int lm_tri_import_nodes(lm_ctx *c, int64_t b, int64_t e, const void *d_in) {
 
 static int collect_edges(lm_ctx *c) {
   if (c->edges_collected) return LM_OK;
-  const int64_t cap = std::max<int64_t>(c->stats.n_valid_edges, 1);
-  CU(c->d_edges.ensure(16 * cap));
-  CU(c->d_edge_cnt.ensure(8));
-  CU(cudaMemsetAsync(c->d_edge_cnt.p, 0, 8, c->stream));
-  lm::launch_collect_edges(c->d_row_state.as<uint8_t>(), c->sorted_val, c->d_node_row_off.as<uint32_t>(),
-                           c->d_line_off.as<int64_t>(), c->node_begin, c->node_end, c->d_edges.as<int64_t>(),
-                           c->d_edge_cnt.as<unsigned long long>(), c->stream);
+  const int64_t ne = c->stats.n_valid_edges;
+  CU(c->d_edges.ensure(16 * std::max<int64_t>(ne, 1)));
+  lm::launch_edge_pairs(c->d_edge_off.as<uint32_t>(), c->d_edge_ng.as<uint32_t>(), c->d_line_off.as<int64_t>(),
+                        c->node_begin, c->node_end - c->node_begin, ne, c->d_edges.as<int64_t>(), c->stream);
   c->stats.n_kernel_launches += 1;
-  unsigned long long n = 0;
-  CU(cudaMemcpyAsync(&n, c->d_edge_cnt.p, 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  c->n_edges_dev = (int64_t)n;
+  c->n_edges_dev = ne;
   c->edges_collected = true;
   return LM_OK;
 }
@@ -1050,6 +1097,212 @@ int lm_tri_get_tracks(lm_ctx *c, int64_t *track_off, int32_t *img_ids, int32_t *
     for (int q = 0; q < 7; ++q) track_line[7 * t + q] = tr.agg[q];
   }
   track_off[c->tracks.size()] = n;
+  return LM_OK;
+}
+
+} // extern "C"
+
+// ---- line refinement ------------------------------------------------------------------------------
+namespace {
+
+struct V3h { double x, y, z; };
+inline V3h v3(double x, double y, double z) { return V3h{x, y, z}; }
+inline V3h crossh(V3h a, V3h b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+inline double normh(V3h a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+inline V3h scaleh(V3h a, double s) { return v3(a.x * s, a.y * s, a.z * s); }
+
+// MinimalInfiniteLine3d(InfiniteLine3d(Line3d)) (base/infinite_line.cc:67-71,180-218): orthonormal
+// representation, Q -> quaternion with Eigen's Quaterniond(Matrix3d) (Shepperd).
+void minimal_from_line(const double *l, double out[6]) {
+  V3h s = v3(l[0], l[1], l[2]), e = v3(l[3], l[4], l[5]);
+  V3h a = v3(e.x - s.x, e.y - s.y, e.z - s.z);
+  double an2 = a.x * a.x + a.y * a.y + a.z * a.z;
+  if (an2 > 0) a = scaleh(a, 1.0 / std::sqrt(an2)); // direction() = normalized()
+  V3h b = crossh(s, a);
+  const double bn = normh(b);
+  const double w1 = 1.0, w2 = bn, den = std::sqrt(w1 * w1 + w2 * w2);
+  out[4] = w1 / den;
+  out[5] = w2 / den;
+  V3h q0 = scaleh(a, 1.0 / normh(a)), q1, q2;
+  if (bn > 1e-12) {
+    q1 = scaleh(b, 1.0 / bn);
+    V3h axb = crossh(a, b);
+    q2 = scaleh(axb, 1.0 / normh(axb));
+  } else {
+    const double av[3] = {a.x, a.y, a.z};
+    int best = 0;
+    if (std::fabs(av[1]) > std::fabs(av[0])) best = 1;
+    if (std::fabs(av[2]) > std::fabs(av[best])) best = 2;
+    const int i1 = (best + 1) % 3, i2 = (best + 2) % 3;
+    double bp[3];
+    bp[i1] = 1.0; bp[i2] = 1.0; bp[best] = -(av[i1] * bp[i1] + av[i2] * bp[i2]) / av[best];
+    V3h bprime = v3(bp[0], bp[1], bp[2]);
+    q1 = scaleh(bprime, 1.0 / normh(bprime));
+    V3h axb = crossh(a, bprime);
+    q2 = scaleh(axb, 1.0 / normh(axb));
+  }
+  const double R[3][3] = {{q0.x, q1.x, q2.x}, {q0.y, q1.y, q2.y}, {q0.z, q1.z, q2.z}};
+  double t = R[0][0] + R[1][1] + R[2][2];
+  double q[4];
+  if (t > 0) {
+    t = std::sqrt(t + 1.0);
+    q[0] = 0.5 * t;
+    t = 0.5 / t;
+    q[1] = (R[2][1] - R[1][2]) * t; q[2] = (R[0][2] - R[2][0]) * t; q[3] = (R[1][0] - R[0][1]) * t;
+  } else {
+    int i = 0;
+    if (R[1][1] > R[0][0]) i = 1;
+    if (R[2][2] > R[i][i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(R[i][i] - R[j][j] - R[k][k] + 1.0);
+    double v[3];
+    v[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (R[k][j] - R[j][k]) * t;
+    v[j] = (R[j][i] + R[i][j]) * t;
+    v[k] = (R[k][i] + R[i][k]) * t;
+    q[1] = v[0]; q[2] = v[1]; q[3] = v[2];
+  }
+  for (int i = 0; i < 4; ++i) out[i] = q[i];
+}
+
+// MinimalInfiniteLine3d::GetInfiniteLine (:220-231) + GetLineSegmentFromInfiniteLine3d (:265-287)
+void segment_from_minimal(const double x[6], const double *l3d, int64_t n, int num_outliers, double out[6]) {
+  M3h Q = quat_to_R(x);
+  const V3h d = v3(Q.m[0], Q.m[3], Q.m[6]);
+  const double f = std::fabs(x[5]) / std::fabs(x[4]);
+  const V3h m = v3(Q.m[1] * f, Q.m[4] * f, Q.m[7] * f);
+  auto point_projection = [&](V3h q) { // InfiniteLine3d::point_projection (:73-78)
+    V3h dq = crossh(d, q);
+    V3h mq = v3(m.x + dq.x, m.y + dq.y, m.z + dq.z);
+    V3h c = crossh(d, mq);
+    return v3(q.x + c.x, q.y + c.y, q.z + c.z);
+  };
+  const V3h pref = point_projection(v3(l3d[0], l3d[1], l3d[2]));
+  std::vector<double> vals;
+  vals.reserve(2 * n);
+  for (int64_t k = 0; k < n; ++k)
+    for (int e = 0; e < 2; ++e) {
+      const double *p = l3d + 6 * k + 3 * e;
+      vals.push_back((p[0] - pref.x) * d.x + (p[1] - pref.y) * d.y + (p[2] - pref.z) * d.z);
+    }
+  std::sort(vals.begin(), vals.end());
+  const double a = vals[num_outliers], b = vals[2 * n - 1 - num_outliers];
+  out[0] = pref.x + d.x * a; out[1] = pref.y + d.y * a; out[2] = pref.z + d.z * a;
+  out[3] = pref.x + d.x * b; out[4] = pref.y + d.y * b; out[5] = pref.z + d.z * b;
+}
+
+} // namespace
+
+extern "C" {
+
+int lm_ba_solve(lm_ctx *c, int32_t n_views, const double *kvec, const double *qvec, const double *tvec, int64_t T,
+                const int64_t *sup_off, const int32_t *sup_view, const double *segs, const double *line3d,
+                const double *line_init, const lm_ba_config *cfg, double *out_line, double *out_minimal,
+                int32_t *out_iters, double *out_cost) {
+  if (!c || !cfg || !sup_off) return fail(LM_ERR_INVALID, "NULL argument");
+  if (T < 0 || n_views <= 0) return fail(LM_ERR_INVALID, "bad sizes");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const int64_t n = sup_off[T];
+  for (int64_t k = 0; k < n; ++k)
+    if (sup_view[k] < 0 || sup_view[k] >= n_views) return fail(LM_ERR_INVALID, "support view index out of range");
+  // host prologue: minimal parameterisation of every start line, constant-track flags
+  std::vector<double> x0(6 * std::max<int64_t>(T, 1));
+  std::vector<uint8_t> active(std::max<int64_t>(T, 1));
+  std::vector<int32_t> tmp;
+  for (int64_t t = 0; t < T; ++t) {
+    if (sup_off[t + 1] > sup_off[t]) {
+      const double *l = line_init + 6 * t;
+      const double len2 = (l[0] - l[3]) * (l[0] - l[3]) + (l[1] - l[4]) * (l[1] - l[4]) + (l[2] - l[5]) * (l[2] - l[5]);
+      if (!(len2 > 0)) return fail(LM_ERR_INVALID, "track with a zero-length 3D line (CHECK_GT(line.length(), 0))");
+    }
+    minimal_from_line(line_init + 6 * t, &x0[6 * t]);
+    tmp.assign(sup_view + sup_off[t], sup_view + sup_off[t + 1]);
+    std::sort(tmp.begin(), tmp.end());
+    const int n_img = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+    active[t] = n_img >= cfg->min_num_images; // ParameterizeLines (hybrid_bundle_adjustment.cc:106-123)
+  }
+  // device input arena: [kvec | qvec | tvec | segs | x0 | sup_off | sup_view | active]
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_k = take(32 * n_views), o_q = take(32 * n_views), o_t = take(24 * n_views), o_s = take(32 * n),
+               o_x = take(48 * T), o_so = take(8 * (T + 1)), o_sv = take(4 * n), o_a = take(T);
+  CU(c->d_ba_in.ensure(off + 256));
+  char *in = c->d_ba_in.as<char>();
+  CU(cudaMemcpyAsync(in + o_k, kvec, 32 * n_views, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(in + o_q, qvec, 32 * n_views, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(in + o_t, tvec, 24 * n_views, cudaMemcpyHostToDevice, s));
+  if (n) CU(cudaMemcpyAsync(in + o_s, segs, 32 * n, cudaMemcpyHostToDevice, s));
+  if (T) CU(cudaMemcpyAsync(in + o_x, x0.data(), 48 * T, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(in + o_so, sup_off, 8 * (T + 1), cudaMemcpyHostToDevice, s));
+  if (n) CU(cudaMemcpyAsync(in + o_sv, sup_view, 4 * n, cudaMemcpyHostToDevice, s));
+  if (T) CU(cudaMemcpyAsync(in + o_a, active.data(), T, cudaMemcpyHostToDevice, s));
+  CU(c->d_ba_blocks.ensure(sizeof(lm::LMBlockDev) * std::max<int64_t>(n, 1)));
+  size_t oo = 0;
+  auto take_o = [&](size_t bytes) { size_t o = oo; oo += (bytes + 255) / 256 * 256; return o; };
+  const size_t oo_x = take_o(48 * T), oo_i = take_o(8 * T), oo_c = take_o(16 * T), oo_t = take_o(4 * T);
+  CU(c->d_ba_out.ensure(oo + 256));
+  char *out = c->d_ba_out.as<char>();
+  CU(cudaEventRecord(c->ev0, s));
+  lm::launch_lm_prepare(reinterpret_cast<const double *>(in + o_s), reinterpret_cast<const int32_t *>(in + o_sv),
+                        reinterpret_cast<const double *>(in + o_k), reinterpret_cast<const double *>(in + o_q),
+                        reinterpret_cast<const double *>(in + o_t), n, c->d_ba_blocks.as<lm::LMBlockDev>(), s);
+  CU(cudaEventRecord(c->evk0, s));
+  lm::LMParams p;
+  p.blocks = c->d_ba_blocks.as<lm::LMBlockDev>();
+  p.sup_off = reinterpret_cast<const int64_t *>(in + o_so);
+  p.x0 = reinterpret_cast<const double *>(in + o_x);
+  p.active = reinterpret_cast<const uint8_t *>(in + o_a);
+  p.x_out = reinterpret_cast<double *>(out + oo_x);
+  p.iters = reinterpret_cast<int32_t *>(out + oo_i);
+  p.cost = reinterpret_cast<double *>(out + oo_c);
+  p.term = reinterpret_cast<int32_t *>(out + oo_t);
+  p.T = T;
+  p.geometric_alpha = cfg->geometric_alpha;
+  p.cauchy_scale = cfg->cauchy_scale;
+  p.max_num_iterations = cfg->max_num_iterations;
+  p.max_invalid = cfg->max_num_consecutive_invalid_steps;
+  lm::launch_lm_refine(p, s);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->evk1, s));
+  std::vector<double> xf(6 * std::max<int64_t>(T, 1)), cost(2 * std::max<int64_t>(T, 1));
+  std::vector<int32_t> iters(2 * std::max<int64_t>(T, 1));
+  if (T) {
+    CU(cudaMemcpyAsync(xf.data(), out + oo_x, 48 * T, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(iters.data(), out + oo_i, 8 * T, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(cost.data(), out + oo_c, 16 * T, cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaStreamSynchronize(s));
+  float ms0 = 0, ms1 = 0;
+  CU(cudaEventElapsedTime(&ms0, c->ev0, c->evk0));
+  CU(cudaEventElapsedTime(&ms1, c->evk0, c->evk1));
+  c->stats.n_kernel_launches += 2;
+  c->ba_stats.n_tracks = T;
+  c->ba_stats.n_blocks = n;
+  c->ba_stats.prepare_ms = ms0;
+  c->ba_stats.solve_ms = ms1;
+  c->ba_stats.total_iterations = c->ba_stats.total_successful = 0;
+  for (int64_t t = 0; t < T; ++t) {
+    c->ba_stats.total_iterations += iters[2 * t];
+    c->ba_stats.total_successful += iters[2 * t + 1];
+    if (out_minimal) memcpy(out_minimal + 6 * t, &xf[6 * t], 48);
+    if (out_iters) { out_iters[2 * t] = iters[2 * t]; out_iters[2 * t + 1] = iters[2 * t + 1]; }
+    if (out_cost) { out_cost[2 * t] = cost[2 * t]; out_cost[2 * t + 1] = cost[2 * t + 1]; }
+    if (out_line) {
+      const int64_t a = sup_off[t], b = sup_off[t + 1];
+      if (b > a && 2 * (b - a) - 1 - cfg->num_outliers >= 0 && cfg->num_outliers < 2 * (b - a))
+        segment_from_minimal(&xf[6 * t], line3d + 6 * a, b - a, cfg->num_outliers, out_line + 6 * t);
+      else
+        memcpy(out_line + 6 * t, line_init + 6 * t, 48);
+    }
+  }
+  return LM_OK;
+}
+
+int lm_ba_get_stats(lm_ctx *c, lm_ba_stats *out) {
+  if (!c || !out) return fail(LM_ERR_INVALID, "NULL argument");
+  *out = c->ba_stats;
   return LM_OK;
 }
 

@@ -1,0 +1,445 @@
+// lm_kernels.cu — batched per-track Levenberg-Marquardt line refinement for sm_100a.
+//
+// Replaces the Ceres problems of
+//   RefinementEngine::{SetUp,Solve}        (optimize/line_refinement/refine.cc:129-178)
+//   HybridBAEngine::{SetUp,Solve}          (optimize/hybrid_bundle_adjustment/hybrid_bundle_adjustment.cc:199-264)
+// for the line-only, constant-camera case: the cost is block-separable per track, so every track is an
+// independent 4-dof problem (Quaternion manifold on uvec, Sphere<2> on wvec).
+//
+// One warp owns one track for the whole solve (all iterations in one launch): the track's supporting
+// blocks are pre-digested once into 21 doubles each (2D endpoints, K, R, t, loss weight) that stay in
+// L1/L2, lanes evaluate residual blocks, and the 4x4 normal equations are accumulated with warp-shuffle
+// all-reductions so that every lane holds J^T J / J^T r and the trust-region logic stays warp-uniform.
+//
+// Residual: GeometricRefinementFunctor (optimize/line_refinement/cost_functions.h:129-194) =
+//   MinimalPluckerToPlucker (ceresbase/line_transforms.h:9-29) -> Line_WorldToPixel
+//   (ceresbase/line_projection.h:51-80) -> Ceres_CosineWeightedPerpendicularDist2D_1D (:107-127),
+// loss ScaledLoss(CauchyLoss(0.25), |seg|/30) (refine.cc:77-78, base/linetrack.cc:315-322).
+// Derivatives: the reference differentiates with 6-wide Ceres Jets through the whole chain; here the chain
+// is split at the camera-frame Pluecker moment m_c = R m + t x (R d): d(m, d)/d(local) is computed once
+// per evaluation per track with 4-wide duals, and each lane carries 3-wide duals from m_c to the residual.
+// The solver restates Ceres' trust-region LM (DESIGN.md "LM recipe" lists the steps and their provenance).
+#include "lm_kernels.cuh"
+#include <cfloat>
+
+namespace lm {
+
+template <int N> struct Dual {
+  double a;
+  double v[N];
+};
+template <int N> LM_D Dual<N> dconst(double x) { Dual<N> r; r.a = x;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.v[i] = 0; return r; }
+template <int N> LM_D Dual<N> operator+(const Dual<N> &f, const Dual<N> &g) { Dual<N> h; h.a = f.a + g.a;
+#pragma unroll
+  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] + g.v[i]; return h; }
+template <int N> LM_D Dual<N> operator-(const Dual<N> &f, const Dual<N> &g) { Dual<N> h; h.a = f.a - g.a;
+#pragma unroll
+  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] - g.v[i]; return h; }
+template <int N> LM_D Dual<N> operator-(const Dual<N> &f) { Dual<N> h; h.a = -f.a;
+#pragma unroll
+  for (int i = 0; i < N; ++i) h.v[i] = -f.v[i]; return h; }
+template <int N> LM_D Dual<N> operator*(const Dual<N> &f, const Dual<N> &g) { Dual<N> h; h.a = f.a * g.a;
+#pragma unroll
+  for (int i = 0; i < N; ++i) h.v[i] = f.a * g.v[i] + f.v[i] * g.a; return h; }
+template <int N> LM_D Dual<N> operator*(const Dual<N> &f, double s) { Dual<N> h; h.a = f.a * s;
+#pragma unroll
+  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * s; return h; }
+template <int N> LM_D Dual<N> operator/(const Dual<N> &f, const Dual<N> &g) { Dual<N> h; const double gi = 1.0 / g.a, q = f.a * gi; h.a = q;
+#pragma unroll
+  for (int i = 0; i < N; ++i) h.v[i] = (f.v[i] - q * g.v[i]) * gi; return h; }
+template <int N> LM_D Dual<N> dsqrt(const Dual<N> &f) { Dual<N> h; h.a = sqrt(f.a); const double t = 1.0 / (2.0 * h.a);
+#pragma unroll
+  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * t; return h; }
+template <int N> LM_D Dual<N> dexp(const Dual<N> &f) { Dual<N> h; h.a = exp(f.a);
+#pragma unroll
+  for (int i = 0; i < N; ++i) h.v[i] = h.a * f.v[i]; return h; }
+template <int N> LM_D Dual<N> dabs(const Dual<N> &f) { return f.a < 0 ? -f : f; }
+
+LM_D double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// ceres QuaternionManifold / SphereManifold<2> (DESIGN.md "LM recipe")
+LM_D void quat_plus(const double x[4], const double d[3], double out[4]) {
+  const double sq = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  if (sq == 0.0) { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3]; return; }
+  const double nd = sqrt(sq), sbd = sin(nd) / nd;
+  const double z0 = cos(nd), z1 = sbd * d[0], z2 = sbd * d[1], z3 = sbd * d[2];
+  out[0] = z0 * x[0] - z1 * x[1] - z2 * x[2] - z3 * x[3];
+  out[1] = z0 * x[1] + z1 * x[0] + z2 * x[3] - z3 * x[2];
+  out[2] = z0 * x[2] - z1 * x[3] + z2 * x[0] + z3 * x[1];
+  out[3] = z0 * x[3] + z1 * x[2] - z2 * x[1] + z3 * x[0];
+}
+LM_D void householder2(const double x[2], double v[2], double &beta) {
+  const double sigma = x[0] * x[0];
+  v[0] = x[0]; v[1] = 1.0; beta = 0.0;
+  const double xp = x[1];
+  if (sigma <= DBL_EPSILON) { if (xp < 0.0) beta = 2.0; return; }
+  const double mu = sqrt(xp * xp + sigma);
+  const double vp = (xp <= 0.0) ? (xp - mu) : (-sigma / (xp + mu));
+  beta = 2.0 * vp * vp / (sigma + vp * vp);
+  v[0] /= vp;
+}
+LM_D void sphere2_plus(const double x[2], double delta, double out[2]) {
+  const double nd = fabs(delta);
+  if (nd == 0.0) { out[0] = x[0]; out[1] = x[1]; return; }
+  double v[2], beta;
+  householder2(x, v, beta);
+  const double y0 = sin(nd) / nd * delta, y1 = cos(nd);
+  const double vty = v[0] * y0 + v[1] * y1;
+  const double nx = sqrt(x[0] * x[0] + x[1] * x[1]);
+  out[0] = nx * (y0 - v[0] * (beta * vty));
+  out[1] = nx * (y1 - v[1] * (beta * vty));
+}
+
+// d and m (world-frame Pluecker line) with derivatives w.r.t. the 4 local (tangent) coordinates.
+// MinimalPluckerToPlucker with ceres::QuaternionToRotation (normalised by |u|^2), composed with the plus
+// Jacobians of the two manifolds.
+struct LineLocal {
+  Dual<4> d[3], m[3];
+};
+LM_D void line_from_minimal(const double x[6], bool want_jac, LineLocal &L) {
+  // ambient duals (6-wide) would be wasteful: seed the 4 local directions directly through the plus Jacobians
+  Dual<4> u[4], w[2];
+  // QuaternionPlusJacobian (4x3)
+  const double Pq[12] = {-x[1], -x[2], -x[3], x[0], x[3], -x[2], -x[3], x[0], x[1], x[2], -x[1], x[0]};
+  double v2[2], beta;
+  householder2(x + 4, v2, beta);
+  const double nx = sqrt(x[4] * x[4] + x[5] * x[5]);
+  const double Ps[2] = {(-beta * v2[0] * v2[0] + 1.0) * nx, (-beta * v2[0] * v2[1]) * nx};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    u[i].a = x[i];
+    u[i].v[0] = want_jac ? Pq[3 * i] : 0; u[i].v[1] = want_jac ? Pq[3 * i + 1] : 0; u[i].v[2] = want_jac ? Pq[3 * i + 2] : 0;
+    u[i].v[3] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    w[i].a = x[4 + i];
+    w[i].v[0] = w[i].v[1] = w[i].v[2] = 0;
+    w[i].v[3] = want_jac ? Ps[i] : 0;
+  }
+  const Dual<4> a = u[0], b = u[1], c = u[2], dd = u[3];
+  const Dual<4> aa = a * a, ab = a * b, ac = a * c, ad = a * dd, bb = b * b, bc = b * c, bd = b * dd, cc = c * c,
+                cd = c * dd, d2 = dd * dd;
+  const Dual<4> nrm = dconst<4>(1.0) / (aa + bb + cc + d2);
+  // column 0 of R: (R00, R10, R20); column 1: (R01, R11, R21)
+  L.d[0] = (aa + bb - cc - d2) * nrm;
+  L.d[1] = ((ad + bc) * 2.0) * nrm;
+  L.d[2] = ((bd - ac) * 2.0) * nrm;
+  const Dual<4> w1 = dabs(w[0]), w2 = dabs(w[1]);
+  const Dual<4> bn = w2 / (w1 + dconst<4>(consts<double>::eps()));
+  L.m[0] = (((bc - ad) * 2.0) * nrm) * bn;
+  L.m[1] = ((aa - bb + cc - d2) * nrm) * bn;
+  L.m[2] = (((ab + cd) * 2.0) * nrm) * bn;
+}
+
+struct BlockEval {
+  double r[2];     // raw residuals
+  double J[8];     // 2x4 local Jacobian (raw)
+};
+
+// One residual block: from (d, m) to the two cosine-weighted point-line distances.
+LM_D void eval_block(const LMBlockDev &B, const LineLocal &L, double alpha, bool want_jac, BlockEval &o) {
+  // m_c = R m + t x (R d)   (Line_WorldToPixel, matrix form R [m]x R^T - t (Rd)^T + (Rd) t^T)
+  double Rd[3], Rm[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Rd[i] = B.R[3 * i] * L.d[0].a + B.R[3 * i + 1] * L.d[1].a + B.R[3 * i + 2] * L.d[2].a;
+    Rm[i] = B.R[3 * i] * L.m[0].a + B.R[3 * i + 1] * L.m[1].a + B.R[3 * i + 2] * L.m[2].a;
+  }
+  const double mc[3] = {Rm[0] + (B.t[1] * Rd[2] - B.t[2] * Rd[1]), Rm[1] + (B.t[2] * Rd[0] - B.t[0] * Rd[2]),
+                        Rm[2] + (B.t[0] * Rd[1] - B.t[1] * Rd[0])};
+  // 3-wide duals seeded on m_c
+  Dual<3> q[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { q[i].a = mc[i]; q[i].v[0] = (i == 0); q[i].v[1] = (i == 1); q[i].v[2] = (i == 2); }
+  // Line_ImgFromCam: coor = cof(K) m_c = (fy mx, fx my, fx fy mz - fy cx mx - fx cy my), then normalised (+EPS)
+  const double fx = B.k[0], fy = B.k[1], cx = B.k[2], cy = B.k[3];
+  Dual<3> c0 = q[0] * fy, c1 = q[1] * fx, c2 = q[2] * (fx * fy) - q[0] * (fy * cx) - q[1] * (fx * cy);
+  const Dual<3> eps = dconst<3>(consts<double>::eps());
+  const Dual<3> cn = dsqrt(c0 * c0 + c1 * c1 + c2 * c2 + eps);
+  c0 = c0 / cn; c1 = c1 / cn; c2 = c2 / cn;
+  // Ceres_CosineWeightedPerpendicularDist2D_1D
+  const Dual<3> dn = dsqrt(c0 * c0 + c1 * c1 + eps);
+  const Dual<3> dir0 = -c1 / dn, dir1 = c0 / dn;
+  const double sx = B.p[2] - B.p[0], sy = B.p[3] - B.p[1];
+  const Dual<3> n1 = dsqrt(dir0 * dir0 + dir1 * dir1 + eps);
+  const double n2 = sqrt(sx * sx + sy * sy + consts<double>::eps());
+  Dual<3> cosine = dabs((dir0 * sx + dir1 * sy) / (n1 * n2));
+  if (cosine.a > 1.0) cosine = dconst<3>(1.0);
+  const Dual<3> weight = dexp((dconst<3>(1.0) - cosine) * alpha);
+  const Dual<3> r0 = ((c0 * B.p[0] + c1 * B.p[1] + c2) / dn) * weight;
+  const Dual<3> r1 = ((c0 * B.p[2] + c1 * B.p[3] + c2) / dn) * weight;
+  o.r[0] = r0.a;
+  o.r[1] = r1.a;
+  if (!want_jac) return;
+  // G = d m_c / d local (3x4) = R Dm + t x (R Dd)
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    double rd[3], rm[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      rd[i] = B.R[3 * i] * L.d[0].v[c] + B.R[3 * i + 1] * L.d[1].v[c] + B.R[3 * i + 2] * L.d[2].v[c];
+      rm[i] = B.R[3 * i] * L.m[0].v[c] + B.R[3 * i + 1] * L.m[1].v[c] + B.R[3 * i + 2] * L.m[2].v[c];
+    }
+    const double g0 = rm[0] + (B.t[1] * rd[2] - B.t[2] * rd[1]);
+    const double g1 = rm[1] + (B.t[2] * rd[0] - B.t[0] * rd[2]);
+    const double g2 = rm[2] + (B.t[0] * rd[1] - B.t[1] * rd[0]);
+    o.J[c] = r0.v[0] * g0 + r0.v[1] * g1 + r0.v[2] * g2;
+    o.J[4 + c] = r1.v[0] * g0 + r1.v[1] * g1 + r1.v[2] * g2;
+  }
+}
+
+struct Normal {
+  double A[10]; // upper triangle of J^T J (scaled columns): 00 01 02 03 11 12 13 22 23 33
+  double g[4];  // J^T r
+  double cost;
+};
+
+// Evaluate the whole track at x: cost (always) and, if want_jac, the loss-corrected normal equations with the
+// Jacobi column scaling applied (scale may be NULL -> unscaled, used to initialise the scaling).
+LM_D void eval_track(const LMBlockDev *blocks, int S, const double x[6], double alpha, double bq, bool want_jac,
+                     const double *scale, Normal &N, double colnorm2[4]) {
+  LineLocal L;
+  line_from_minimal(x, want_jac, L);
+  const int lane = threadIdx.x & 31;
+  double A[10], g[4], cost = 0, cn2[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 10; ++i) A[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) g[i] = 0;
+  const double cq = 1.0 / bq;
+  for (int k = lane; k < S; k += 32) {
+    const LMBlockDev B = blocks[k];
+    BlockEval e;
+    eval_block(B, L, alpha, want_jac, e);
+    // ScaledLoss(CauchyLoss, w) + ceres Corrector
+    const double s = e.r[0] * e.r[0] + e.r[1] * e.r[1];
+    const double sum = 1.0 + s * cq, inv = 1.0 / sum;
+    const double rho0 = B.w * bq * log(sum), rho1 = B.w * fmax(DBL_MIN, inv), rho2 = B.w * (-cq * (inv * inv));
+    cost += 0.5 * rho0;
+    if (!want_jac) continue;
+    const double sqrt_rho1 = sqrt(rho1);
+    double residual_scaling = sqrt_rho1, alpha_sq_norm = 0.0;
+    if (!(s == 0.0 || rho2 <= 0.0)) {
+      const double D = 1.0 + 2.0 * s * rho2 / rho1;
+      const double al = 1.0 - sqrt(D);
+      residual_scaling = sqrt_rho1 / (1 - al);
+      alpha_sq_norm = al / s;
+    }
+    double J0[4], J1[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (alpha_sq_norm == 0.0) { J0[c] = sqrt_rho1 * e.J[c]; J1[c] = sqrt_rho1 * e.J[4 + c]; }
+      else {
+        const double rtj = e.r[0] * e.J[c] + e.r[1] * e.J[4 + c];
+        J0[c] = sqrt_rho1 * (e.J[c] - alpha_sq_norm * e.r[0] * rtj);
+        J1[c] = sqrt_rho1 * (e.J[4 + c] - alpha_sq_norm * e.r[1] * rtj);
+      }
+      cn2[c] += J0[c] * J0[c] + J1[c] * J1[c];
+      if (scale) { J0[c] *= scale[c]; J1[c] *= scale[c]; }
+    }
+    const double r0 = e.r[0] * residual_scaling, r1 = e.r[1] * residual_scaling;
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      g[a] += J0[a] * r0 + J1[a] * r1;
+#pragma unroll
+      for (int b = a; b < 4; ++b) A[idx++] += J0[a] * J0[b] + J1[a] * J1[b];
+    }
+  }
+  N.cost = warp_sum(cost);
+  if (want_jac) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) N.A[i] = warp_sum(A[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { N.g[i] = warp_sum(g[i]); if (colnorm2) colnorm2[i] = warp_sum(cn2[i]); }
+  }
+}
+
+LM_D bool chol_solve4(const double Au[10], const double dg[4], const double b[4], double x[4]) {
+  // A = upper-triangle storage + dg on the diagonal
+  double A[4][4];
+  int idx = 0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = a; c < 4; ++c) { A[a][c] = Au[idx]; A[c][a] = Au[idx]; ++idx; }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) A[a][a] += dg[a];
+  double Lm[4][4] = {{0}};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      double s = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= Lm[i][k] * Lm[j][k];
+      if (i == j) { if (!(s > 0)) return false; Lm[i][i] = sqrt(s); }
+      else Lm[i][j] = s / Lm[j][j];
+    }
+  double y[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { double s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= Lm[i][k] * y[k]; y[i] = s / Lm[i][i]; }
+#pragma unroll
+  for (int i = 3; i >= 0; --i) { double s = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 4; ++k) s -= Lm[k][i] * x[k]; x[i] = s / Lm[i][i]; }
+  return true;
+}
+
+__global__ void __launch_bounds__(128) lm_refine_kernel(const __grid_constant__ LMParams p) {
+  const int warp_in_block = threadIdx.x >> 5;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+  if (t >= p.T) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t s0 = p.sup_off[t];
+  const int S = (int)(p.sup_off[t + 1] - s0);
+  const LMBlockDev *blocks = p.blocks + s0;
+  double x[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = p.x0[6 * t + i];
+  const double bq = p.cauchy_scale * p.cauchy_scale;
+  Normal N;
+  double cn2[4];
+  int it = 0, successful = 0, term = 0;
+  double cost0, cost;
+  if (S == 0 || !p.active[t]) {
+    eval_track(blocks, S, x, p.geometric_alpha, bq, false, nullptr, N, nullptr);
+    cost0 = cost = N.cost;
+  } else {
+    // iteration 0: evaluate, fix the Jacobi scaling 1/(1+||J_col||)
+    eval_track(blocks, S, x, p.geometric_alpha, bq, true, nullptr, N, cn2);
+    double scale[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) scale[c] = 1.0 / (1.0 + sqrt(cn2[c]));
+    {
+      int idx = 0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { N.g[a] *= scale[a];
+#pragma unroll
+        for (int b = a; b < 4; ++b) N.A[idx++] *= scale[a] * scale[b]; }
+    }
+    cost0 = cost = N.cost;
+    double radius = 1e4, decrease_factor = 2.0, diag[4] = {0, 0, 0, 0};
+    bool reuse_diagonal = false;
+    int invalid = 0;
+    while (true) {
+      if (it >= p.max_num_iterations) { term = 1; break; }
+      if (radius <= 1e-32) { term = 2; break; }
+      {
+        double gmax = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gmax = fmax(gmax, fabs(N.g[c] / scale[c]));
+        if (gmax <= 0.0) { term = 3; break; }
+      }
+      ++it;
+      const double dgi[4] = {N.A[0], N.A[4], N.A[7], N.A[9]};
+      if (!reuse_diagonal)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) diag[c] = fmin(fmax(dgi[c], 1e-6), 1e32);
+      reuse_diagonal = true;
+      double dg[4], step[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dg[c] = diag[c] / radius;
+      bool ok = chol_solve4(N.A, dg, N.g, step);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { step[c] = -step[c]; if (!isfinite(step[c])) ok = false; }
+      double mcc = 0;
+      if (ok) {
+        // model_cost_change = -(step . g + step^T (J^T J) step / 2)
+        double sg = 0, sAs = 0;
+        int idx = 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          sg += step[a] * N.g[a];
+#pragma unroll
+          for (int b = a; b < 4; ++b) { sAs += ((a == b) ? 1.0 : 2.0) * step[a] * step[b] * N.A[idx]; ++idx; }
+        }
+        mcc = -(sg + 0.5 * sAs);
+      }
+      if (!ok || !(mcc > 0.0)) {
+        if (++invalid >= p.max_invalid) { term = 4; break; }
+        radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+        continue;
+      }
+      invalid = 0;
+      double delta[4], cand[6];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) delta[c] = step[c] * scale[c];
+      quat_plus(x, delta, cand);
+      sphere2_plus(x + 4, delta[3], cand + 4);
+      Normal Nc;
+      eval_track(blocks, S, cand, p.geometric_alpha, bq, false, nullptr, Nc, nullptr);
+      double sn = 0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) sn += (x[c] - cand[c]) * (x[c] - cand[c]);
+      if (!(sqrt(sn) > 0.0)) { term = 5; break; }
+      if (!(fabs(cost - Nc.cost) > 0.0)) { term = 6; break; }
+      const double rel = (cost - Nc.cost) / mcc;
+      if (rel > 1e-3) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) x[c] = cand[c];
+        eval_track(blocks, S, x, p.geometric_alpha, bq, true, scale, N, nullptr);
+        cost = N.cost;
+        const double tq = 2.0 * rel - 1.0;
+        radius = radius / fmax(1.0 / 3.0, 1.0 - tq * tq * tq);
+        radius = fmin(1e16, radius);
+        decrease_factor = 2.0; reuse_diagonal = false;
+        ++successful;
+      } else {
+        radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      }
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) p.x_out[6 * t + i] = x[i];
+    p.iters[2 * t] = it; p.iters[2 * t + 1] = successful;
+    p.cost[2 * t] = cost0; p.cost[2 * t + 1] = cost;
+    p.term[t] = term;
+  }
+}
+
+// supports -> digested blocks: R from qvec via ceres::QuaternionToRotation (normalising), loss weight |seg|/30
+__global__ void lm_prepare_blocks_kernel(const double *__restrict__ segs, const int32_t *__restrict__ sup_view,
+                                         const double *__restrict__ kvec, const double *__restrict__ qvec,
+                                         const double *__restrict__ tvec, int64_t n, LMBlockDev *__restrict__ out) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int v = sup_view[k];
+  LMBlockDev B;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { B.p[i] = segs[4 * k + i]; B.k[i] = kvec[4 * v + i]; }
+  const double a = qvec[4 * v], b = qvec[4 * v + 1], c = qvec[4 * v + 2], d = qvec[4 * v + 3];
+  const double aa = a * a, ab = a * b, ac = a * c, ad = a * d, bb = b * b, bc = b * c, bd = b * d, cc = c * c, cd = c * d, dd = d * d;
+  const double nr = 1.0 / (aa + bb + cc + dd);
+  B.R[0] = (aa + bb - cc - dd) * nr; B.R[1] = 2 * (bc - ad) * nr; B.R[2] = 2 * (ac + bd) * nr;
+  B.R[3] = 2 * (ad + bc) * nr; B.R[4] = (aa - bb + cc - dd) * nr; B.R[5] = 2 * (cd - ab) * nr;
+  B.R[6] = 2 * (bd - ac) * nr; B.R[7] = 2 * (ab + cd) * nr; B.R[8] = (aa - bb - cc + dd) * nr;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) B.t[i] = tvec[3 * v + i];
+  const double dx = B.p[0] - B.p[2], dy = B.p[1] - B.p[3];
+  B.w = sqrt(dx * dx + dy * dy) / 30.0; // ComputeLineWeights (base/linetrack.cc:315-322)
+  out[k] = B;
+}
+
+void launch_lm_prepare(const double *segs, const int32_t *sup_view, const double *kvec, const double *qvec,
+                       const double *tvec, int64_t n, LMBlockDev *out, cudaStream_t s) {
+  if (n <= 0) return;
+  lm_prepare_blocks_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(segs, sup_view, kvec, qvec, tvec, n, out);
+}
+void launch_lm_refine(const LMParams &p, cudaStream_t s) {
+  if (p.T <= 0) return;
+  const int warps = 4;
+  lm_refine_kernel<<<(int)((p.T + warps - 1) / warps), warps * 32, 0, s>>>(p);
+}
+
+} // namespace lm

@@ -489,40 +489,60 @@ void launch_node_offsets(const uint32_t *d_sorted_key, int64_t n_rows, int64_t n
   node_offsets_kernel<<<grid, 256, 0, s>>>(d_sorted_key, n_rows, n_nodes, d_node_row_off, d_max_rows);
 }
 
-// valid connections -> (min node, max node) pairs, unordered (sorted afterwards).
-__global__ void collect_edges_kernel(const uint8_t *__restrict__ row_state, const uint32_t *__restrict__ row_ng,
-                                     const uint32_t *__restrict__ node_row_off, const int64_t *__restrict__ line_off,
-                                     int64_t node_begin, int64_t node_end, int64_t *__restrict__ edges,
-                                     unsigned long long *count) {
+// valid_edges_ (global_line_triangulator.cc:130-142) in compact, node-major, candidate-ordered form.
+__global__ void extract_nvalid_kernel(const NodeRecord *__restrict__ nodes, int64_t node_begin, int64_t n,
+                                      uint32_t *__restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)nodes[node_begin + i].n_valid;
+  if (i == n) out[i] = 0;
+}
+__global__ void compact_edges_kernel(const uint8_t *__restrict__ row_state, const uint32_t *__restrict__ row_ng,
+                                     const uint32_t *__restrict__ node_row_off, const uint32_t *__restrict__ edge_off,
+                                     int64_t node_begin, int64_t n, uint32_t *__restrict__ edge_ng) {
   const int lane = threadIdx.x & 31;
-  const int64_t node = node_begin + (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
-  if (node >= node_end) return;
-  const uint32_t r0 = node_row_off[node], r1 = node_row_off[node + 1];
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+  if (i >= n) return;
+  const uint32_t r0 = node_row_off[node_begin + i], r1 = node_row_off[node_begin + i + 1];
+  uint32_t base = edge_off[i];
+  if (edge_off[i + 1] == base) return;
   for (uint32_t rb = r0; rb < r1; rb += 32) {
     const uint32_t r = rb + lane;
     const bool v = (r < r1) && row_state[r] == 2;
     const unsigned m = __ballot_sync(0xffffffffu, v);
-    if (!m) continue;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (v) {
-      const uint32_t ng = row_ng[r];
-      const int64_t dst = line_off[ng >> 16] + (ng & 0xffffu);
-      const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
-      edges[2 * idx] = node;
-      edges[2 * idx + 1] = dst;
-    }
+    if (v) edge_ng[base + __popc(m & ((1u << lane) - 1u))] = row_ng[r];
+    base += __popc(m);
   }
 }
-void launch_collect_edges(const uint8_t *row_state, const uint32_t *row_ng, const uint32_t *node_row_off,
-                          const int64_t *line_off, int64_t node_begin, int64_t node_end, int64_t *edges,
-                          unsigned long long *count, cudaStream_t s) {
-  const int64_t n = node_end - node_begin;
+// directed (src node, dst node) pairs of the compact edge list
+__global__ void edge_pairs_kernel(const uint32_t *__restrict__ edge_off, const uint32_t *__restrict__ edge_ng,
+                                  const int64_t *__restrict__ line_off, int64_t node_begin, int64_t n_nodes,
+                                  int64_t n_edges, int64_t *__restrict__ out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  int64_t lo = 0, hi = n_nodes; // largest i with edge_off[i] <= e
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (edge_off[mid] <= (uint32_t)e) lo = mid; else hi = mid;
+  }
+  const uint32_t ng = edge_ng[e];
+  out[2 * e] = node_begin + lo;
+  out[2 * e + 1] = line_off[ng >> 16] + (ng & 0xffffu);
+}
+void launch_edge_pairs(const uint32_t *edge_off, const uint32_t *edge_ng, const int64_t *line_off,
+                       int64_t node_begin, int64_t n_nodes, int64_t n_edges, int64_t *out, cudaStream_t s) {
+  if (n_edges <= 0) return;
+  edge_pairs_kernel<<<(int)((n_edges + 255) / 256), 256, 0, s>>>(edge_off, edge_ng, line_off, node_begin, n_nodes,
+                                                                 n_edges, out);
+}
+void launch_extract_nvalid(const NodeRecord *nodes, int64_t node_begin, int64_t n, uint32_t *out, cudaStream_t s) {
+  extract_nvalid_kernel<<<(int)((n + 1 + 255) / 256), 256, 0, s>>>(nodes, node_begin, n, out);
+}
+void launch_compact_edges_only(const uint8_t *row_state, const uint32_t *row_ng, const uint32_t *node_row_off,
+                               const uint32_t *edge_off, int64_t node_begin, int64_t n, uint32_t *edge_ng,
+                               cudaStream_t s) {
   if (n <= 0) return;
-  const int grid = (int)((n * 32 + 255) / 256);
-  collect_edges_kernel<<<grid, 256, 0, s>>>(row_state, row_ng, node_row_off, line_off, node_begin, node_end, edges,
-                                            count);
+  compact_edges_kernel<<<(int)((n * 32 + 255) / 256), 256, 0, s>>>(row_state, row_ng, node_row_off, edge_off,
+                                                                   node_begin, n, edge_ng);
 }
 
 // run_clustering edge weight (global_line_triangulator.cc:263-288): LineLinker3d::compute_score of the

@@ -74,9 +74,12 @@ void launch_expand_exhaustive(const int64_t *d_blk_row_off, const int32_t *d_blk
                               int64_t n_rows, uint32_t *d_key, uint32_t *d_val, cudaStream_t s);
 void launch_node_offsets(const uint32_t *d_sorted_key, int64_t n_rows, int64_t n_nodes, uint32_t *d_node_row_off,
                          unsigned int *d_max_rows, cudaStream_t s);
-void launch_collect_edges(const uint8_t *row_state, const uint32_t *row_ng, const uint32_t *node_row_off,
-                          const int64_t *line_off, int64_t node_begin, int64_t node_end, int64_t *edges,
-                          unsigned long long *count, cudaStream_t s);
+void launch_extract_nvalid(const NodeRecord *nodes, int64_t node_begin, int64_t n, uint32_t *out, cudaStream_t s);
+void launch_compact_edges_only(const uint8_t *row_state, const uint32_t *row_ng, const uint32_t *node_row_off,
+                               const uint32_t *edge_off, int64_t node_begin, int64_t n, uint32_t *edge_ng,
+                               cudaStream_t s);
+void launch_edge_pairs(const uint32_t *edge_off, const uint32_t *edge_ng, const int64_t *line_off,
+                       int64_t node_begin, int64_t n_nodes, int64_t n_edges, int64_t *out, cudaStream_t s);
 void launch_edge_weights(const EdgeParams &p, cudaStream_t s);
 
 } // namespace lm

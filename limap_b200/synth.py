@@ -34,6 +34,7 @@ class Scene:
         return len(self.img_ids)
 
     def n_rows(self, img_ids=None):
+        """Match rows (the M1 unit) of the given source images (default: all that have matches)."""
         ids = self.matches.keys() if img_ids is None else img_ids
         return int(sum(len(m) for i in ids for m in self.matches[i].values()))
 
@@ -72,7 +73,7 @@ def _rot_to_quat(R):
 
 
 def make_scene(V=10, L=100, N=5, K=4, seed=1234, scale=1.0, noise_px=0.5, G=None, id_stride=1,
-               width=800, height=600, focal=692.82, shuffle_rows=False):
+               width=800, height=600, focal=692.82, shuffle_rows=False, match_views=None):
     rng = np.random.default_rng(seed)
     G = int(L * 1.3) if G is None else G
     # ground-truth 3D segments
@@ -161,7 +162,7 @@ def make_scene(V=10, L=100, N=5, K=4, seed=1234, scale=1.0, noise_px=0.5, G=None
     mids = [(s[:, :2] + s[:, 2:]) * 0.5 for s in segs_all]
     trees = [cKDTree(m) for m in mids]
     matches = {}
-    for v in range(V):
+    for v in (range(V) if match_views is None else match_views):
         mv = {}
         Lv = len(segs_all[v])
         for u in nb_idx[v]:
@@ -195,3 +196,71 @@ CONFIGS = {
     "hypersim100": dict(V=100, L=1000, N=20, K=10, seed=1235),          # configs[1] (the metric's config)
     "sweep500": dict(V=500, L=400, N=40, K=10, seed=1236),              # configs[2]
 }
+
+
+@dataclass
+class TrackSet:
+    """Flat line tracks for the refinement path (BASELINE.json configs[3]): sup_off[T+1]; per support:
+    2D segment, camera (kvec,qvec,tvec), image id and the per-node 3D line (track.line3d_list)."""
+    sup_off: np.ndarray
+    segs: np.ndarray      # [n,4]
+    kvec: np.ndarray      # [n,4]
+    qvec: np.ndarray      # [n,4]
+    tvec: np.ndarray      # [n,3]
+    img_ids: np.ndarray   # [n] int32
+    line3d: np.ndarray    # [n,6]
+    line_init: np.ndarray  # [T,6]
+    gt: np.ndarray        # [T,6]
+
+    @property
+    def n_tracks(self):
+        return len(self.sup_off) - 1
+
+
+def make_tracks(T=100, S=30, V=300, seed=1237, noise_px=0.5, perturb=0.05, scale=1.0, width=800,
+                height=600, focal=692.82):
+    """T ground-truth 3D segments, each observed in S of V ring cameras (one 2D segment per view, noisy
+    endpoints, random truncation); the start line is the GT perturbed by N(0, perturb) on its endpoints
+    (cf. src/limap/optimize/functions.py:6-13); line3d_list = noisy copies of the GT segment."""
+    rng = np.random.default_rng(seed)
+    az = rng.uniform(0, 2 * np.pi, V)
+    el = rng.uniform(-0.5, 0.5, V)
+    rad = 12.0 * scale * rng.uniform(0.95, 1.05, V)
+    Cs = np.stack([rad * np.cos(el) * np.cos(az), rad * np.cos(el) * np.sin(az), rad * np.sin(el)], 1)
+    Rs, qs, ts = np.zeros((V, 3, 3)), np.zeros((V, 4)), np.zeros((V, 3))
+    for v in range(V):
+        z = -Cs[v] / np.linalg.norm(Cs[v])
+        x = np.cross(z, np.array([0.0, 0.0, 1.0]) + rng.normal(scale=0.05, size=3))
+        x /= np.linalg.norm(x)
+        R = np.stack([x, np.cross(z, x), z], 0)
+        Rs[v], qs[v], ts[v] = R, _rot_to_quat(R), -R @ Cs[v]
+    mid = rng.uniform(-4, 4, (T, 3))
+    d = rng.normal(size=(T, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    half = rng.uniform(0.25, 1.5, (T, 1))
+    gt = np.concatenate([(mid - d * half), (mid + d * half)], 1) * scale
+    K = np.array([focal, focal, width / 2.0, height / 2.0])
+    sup_off = np.arange(T + 1, dtype=np.int64) * S
+    n = T * S
+    views = np.stack([rng.choice(V, S, replace=False) for _ in range(T)]).reshape(-1)
+    R = Rs[views]
+    t = ts[views]
+    P0 = np.repeat(gt[:, :3], S, 0)
+    P1 = np.repeat(gt[:, 3:], S, 0)
+    ta = rng.uniform(0.0, 0.2, (n, 1))
+    tb = rng.uniform(0.0, 0.2, (n, 1))
+    A = P0 + (P1 - P0) * ta
+    B = P1 - (P1 - P0) * tb
+    def proj(X):
+        Xc = np.einsum("nij,nj->ni", R, X) + t
+        return Xc[:, :2] / Xc[:, 2:3] * focal + K[2:4]
+    a = proj(A) + rng.normal(scale=noise_px, size=(n, 2))
+    b = proj(B) + rng.normal(scale=noise_px, size=(n, 2))
+    flip = rng.random(n) < 0.5
+    segs = np.where(flip[:, None], np.concatenate([b, a], 1), np.concatenate([a, b], 1))
+    line3d = np.concatenate([A, B], 1) + rng.normal(scale=0.02 * scale, size=(n, 6))
+    line_init = gt + rng.normal(scale=perturb * scale, size=gt.shape)
+    return TrackSet(sup_off=sup_off, segs=np.ascontiguousarray(segs), kvec=np.tile(K, (n, 1)),
+                    qvec=np.ascontiguousarray(qs[views]), tvec=np.ascontiguousarray(ts[views]),
+                    img_ids=views.astype(np.int32), line3d=np.ascontiguousarray(line3d),
+                    line_init=np.ascontiguousarray(line_init), gt=gt)

@@ -13,6 +13,20 @@ _lib = None
 _P = C.c_void_p
 
 
+def usable_cpus():
+    """CPUs this process may really use: affinity mask capped by the cgroup quota. OpenMP's default
+    (every core the machine has) oversubscribes badly inside a CPU-limited container."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, p = f.read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(p))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def build(force=False):
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
     if force or not os.path.exists(LIB_PATH) or any(
@@ -81,8 +95,8 @@ class OracleTri:
         from limap_b200.config import make_tri_config
         self.cfg = make_tri_config(cfg) if not hasattr(cfg, "_fields_") else cfg
         L = lib()
-        if threads:
-            L.orc_set_num_threads(int(threads))
+        # parity runs do not need many threads; the reference's OpenMP regions are tiny (one node each)
+        L.orc_set_num_threads(int(threads) if threads else min(8, usable_cpus()))
         self._h = L.orc_tri_create(C.byref(self.cfg))
         if not self._h:
             raise RuntimeError(L.orc_last_error().decode())
@@ -170,3 +184,29 @@ class OracleTri:
 
 def cam_array(model, kvec, qvec, tvec):
     return _f64([model, *kvec, *qvec, *tvec])
+
+
+class LMCfg(C.Structure):
+    _fields_ = [("geometric_alpha", C.c_double), ("cauchy_scale", C.c_double),
+                ("max_num_iterations", C.c_int32), ("min_num_images", C.c_int32),
+                ("num_outliers", C.c_int32), ("mode", C.c_int32), ("parallel_tracks", C.c_int32),
+                ("pad", C.c_int32)]
+
+
+def refine_tracks(ts, max_num_iterations=100, min_num_images=4, num_outliers=2, geometric_alpha=10.0,
+                  cauchy_scale=0.25, mode=0, parallel_tracks=True, threads=None):
+    """CPU restatement of solve_line_bundle_adjustment / per-track RefinementEngine on a TrackSet."""
+    L = lib()
+    L.orc_set_num_threads(int(threads) if threads else min(8, usable_cpus()))
+    L.orc_refine_tracks.argtypes = [C.c_int] + [_P] * 13
+    T = ts.n_tracks
+    cfg = LMCfg(geometric_alpha, cauchy_scale, max_num_iterations, min_num_images, num_outliers, mode,
+                int(parallel_tracks), 0)
+    out_line = np.zeros((T, 6))
+    out_min = np.zeros((T, 6))
+    iters = np.zeros((T, 2), np.int32)
+    cost = np.zeros((T, 2))
+    a = [np.ascontiguousarray(ts.sup_off, np.int64), _f64(ts.segs), _f64(ts.kvec), _f64(ts.qvec), _f64(ts.tvec),
+         np.ascontiguousarray(ts.img_ids, np.int32), _f64(ts.line3d), _f64(ts.line_init)]
+    L.orc_refine_tracks(T, *[_p(x) for x in a], C.byref(cfg), _p(out_line), _p(out_min), _p(iters), _p(cost))
+    return dict(line=out_line, minimal=out_min, iters=iters, cost=cost)
