@@ -76,10 +76,25 @@ def compare_tracks(eng, orc):
     # endpoints (the TLS direction sign is arbitrary: compare up to a start/end swap)
     om = {frozenset(s): k for k, s in enumerate(os_)}
     worst = 0.0
+    n_ties = 0
     for k, s in enumerate(gs):
-        a, b = gt["track_line"][k], ot["track_line"][om[frozenset(s)]]
+        j = om[frozenset(s)]
+        a, b = gt["track_line"][k], ot["track_line"][j]
         d = min(np.abs(a[:6] - b[:6]).max(), np.abs(a[:6] - np.concatenate([b[3:6], b[:3]])).max())
+        if d > ENDPOINT_TOL and len(s) < 4:
+            # aggregate_line3d_list_takebest (merging/aggregator.cc:9-29) keeps the first strict maximum of the
+            # node scores. Two nodes of a track that triangulate each other carry the SAME infinite line, so
+            # their scores agree to the last few bits and which one wins depends on rounding (compiler / libm),
+            # in the reference as well. Accept any member whose score ties with the maximum within 1e-9.
+            oa, ob = ot["track_off"][j], ot["track_off"][j + 1]
+            sc = ot["line3d"][oa:ob, 9]
+            tied = [m for m in range(ob - oa) if sc[m] >= sc.max() * (1 - 1e-9)]
+            cand = [ot["line3d"][oa + m, :6] for m in tied]
+            dd = min(np.abs(a[:6] - c).max() for c in cand)
+            if len(tied) > 1 and dd <= ENDPOINT_TOL:
+                n_ties += 1
+                d = dd
         worst = max(worst, d)
         assert abs(a[6] - b[6]) <= ENDPOINT_TOL
     assert worst <= ENDPOINT_TOL, f"track endpoints differ by {worst}"
-    return dict(tracks=len(gs), exact_order=exact_order, worst=worst)
+    return dict(tracks=len(gs), exact_order=exact_order, worst=worst, score_ties=n_ties)
