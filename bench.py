@@ -350,6 +350,7 @@ def main():
                 "config": {"workload": WORKLOAD, "V": 100 * world, "L": 1000, "N": 20, "K": 10,
                            "rows_per_step": int(rows_all), "candidates_per_step_rank0": int(st["n_candidates"]),
                            "valid_connections_rank0": int(st["n_valid_edges"]),
+                           "pairs": {"past_3d_gates": int(st["n_pairs_gated"]), "scored_exact_fp64": int(st["n_pairs_exact"])},
                            "parallelism": f"source-image shards x{world}",
                            "l2": "inputs larger than L2 (match rows + sort buffers > 126 MB per step)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

@@ -57,7 +57,8 @@ typedef struct lm_tri_stats {
   int64_t n_valid_edges; /* candidates kept as valid connections */
   int64_t n_nodes;       /* 2D lines in the scene */
   int64_t n_kernel_launches; /* kernels this library launched since ctx creation */
-  int64_t n_fp64_pair_fallbacks; /* pair scores re-evaluated in fp64 by the guard band */
+  int64_t n_pairs_gated; /* candidate pairs that passed the fp32 3d pruning gates */
+  int64_t n_pairs_exact; /* candidate pairs scored with the exact fp64 reference formulas */
   int64_t max_rows_per_node;
   double last_run_ms;    /* device time of the last lm_tri_run (CUDA events on the ctx stream) */
   double last_node_kernel_ms; /* device time of its fused generate+score kernel alone */

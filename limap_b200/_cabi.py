@@ -19,7 +19,7 @@ class LimapB200Error(RuntimeError):
 class TriStats(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("n_candidates", C.c_int64), ("n_valid_edges", C.c_int64),
                 ("n_nodes", C.c_int64), ("n_kernel_launches", C.c_int64),
-                ("n_fp64_pair_fallbacks", C.c_int64), ("max_rows_per_node", C.c_int64),
+                ("n_pairs_gated", C.c_int64), ("n_pairs_exact", C.c_int64), ("max_rows_per_node", C.c_int64),
                 ("last_run_ms", C.c_double), ("last_node_kernel_ms", C.c_double)]
 
 

@@ -622,6 +622,28 @@ int lm_tri_run(lm_ctx *c) {
     l3.use_angle = 1; l3.use_overlap = 0; l3.use_perp = 0; l3.use_innerseg = 0; l3.use_scaleinv = 1;
     p.l3d = to_dev<double>(l3);
   }
+  {
+    const double kPi = 3.14159265358979323846;
+    const double t3 = p.l3d.th_angle, t2 = p.l2d.th_angle;
+    p.cos_th3d_f = (t3 >= 90.0) ? -1.0f : (float)(std::cos(t3 * kPi / 180.0) - 4e-6);
+    const double c2 = (t2 >= 90.0) ? 0.0 : std::cos(t2 * kPi / 180.0);
+    p.cos2_th2d = c2 * c2;
+    p.th_perp2_2d = p.l2d.th_perp * p.l2d.th_perp;
+    const double ta = p.line_tri_angle_threshold, tsn = p.sensitivity_threshold;
+    p.tri_poly_ok = (ta > 0.0 && ta < 90.0);
+    p.sens_poly_ok = (tsn > 0.0 && tsn < 90.0);
+    p.sin2_tri = std::sin(ta * kPi / 180.0) * std::sin(ta * kPi / 180.0);
+    p.sin2_sens = std::sin(tsn * kPi / 180.0) * std::sin(tsn * kPi / 180.0);
+    // direction buckets of width >= th_angle * 1.001 + 0.02 deg (candidates of a node are coplanar when they
+    // come from the plane-pair intersection; endpoint triangulation does not guarantee that)
+    p.n_buckets = 1;
+    if (!g.use_endpoints_triangulation && t3 > 0.0 && t3 < 60.0) {
+      const int nb = (int)std::floor(180.0 / (t3 * 1.001 + 0.02));
+      p.n_buckets = std::max(1, std::min(32, nb));
+    }
+    p.bucket_scale = (float)(p.n_buckets / kPi);
+  }
+  if (max_rows > 65535) return fail(LM_ERR_INVALID, "more than 65535 match rows for one 2D line");
   int cap = 32;
   while (cap < max_rows) cap += 32;
   size_t smem = lm::tri_smem_bytes(cap);
@@ -677,7 +699,8 @@ int lm_tri_run(lm_ctx *c) {
   c->stats.n_rows = n_rows;
   c->stats.n_candidates = (int64_t)cnt[0];
   c->stats.n_valid_edges = (int64_t)cnt[1];
-  c->stats.n_fp64_pair_fallbacks = (int64_t)cnt[2];
+  c->stats.n_pairs_gated = (int64_t)cnt[2];
+  c->stats.n_pairs_exact = (int64_t)cnt[3];
   c->stats.n_kernel_launches += launches;
   c->stats.last_run_ms = ms;
   c->ran = true;

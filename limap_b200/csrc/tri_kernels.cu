@@ -16,23 +16,49 @@
 
 namespace lm {
 
+#ifndef LM_TRI_MIN_BLOCKS
+#define LM_TRI_MIN_BLOCKS 4
+#endif
 static constexpr int kThreads = 128;
 static constexpr int kWarps = kThreads / 32;
-static constexpr int kCandDoubles = 17; // sx..ez(6) d(3) zs ze unc q(4) score
-static constexpr int kCandBytes = kCandDoubles * 8 + 8;
+// per-candidate staging: 17 doubles (exact fp64 data + score), 11 floats (fp32 gate copies), ng + row
+// (2 x uint32); plus two survivor lists per warp
+static constexpr int kFlush = 64;      // a warp flushes its survivor list once it holds this many pairs
+static constexpr int kListExtra = kFlush + 32;
+// per-candidate staging: 17 doubles (exact fp64 data + score), one 48-byte fp32 gate record, ng + row +
+// meta (3 x uint32); plus per warp two survivor lists (uint32) and one prefilter list (uint16)
+static constexpr int kCandBytes = 17 * 8 + 48 + 12;
 
-size_t tri_smem_bytes(int cap) { return (size_t)cap * kCandBytes; }
+size_t tri_smem_bytes(int cap) {
+  return (size_t)cap * kCandBytes + (size_t)kWarps * 2 * (cap + kListExtra) * 4 + (size_t)kWarps * cap * 2;
+}
+
+// fp32 copy of a candidate for the pruning gates (three 16-byte loads, conflict-free at 48-byte stride):
+// unit direction, endpoints relative to the source camera centre, squared scale-invariance limits of the
+// candidate taken as l_i.
+struct __align__(16) GateRec {
+  float dx, dy, dz, lims2;
+  float sx, sy, sz, lime2;
+  float ex, ey, ez, pad;
+};
 
 struct Slab {
   double *sx, *sy, *sz, *ex, *ey, *ez, *dx, *dy, *dz, *zs, *ze, *unc, *q0, *q1, *q2, *q3, *score;
-  uint32_t *ng, *row;
+  GateRec *gate;
+  uint32_t *ng, *row, *meta; // meta = view << 16 | direction bucket
+  uint32_t *list;            // [kWarps][2][cap + kListExtra]: (row << 16 | j) survivor entries
+  uint16_t *list0;           // [kWarps][cap]: j of the bucket prefilter
   LM_D void carve(char *base, int cap) {
     double *d = reinterpret_cast<double *>(base);
     sx = d; sy = sx + cap; sz = sy + cap; ex = sz + cap; ey = ex + cap; ez = ey + cap;
     dx = ez + cap; dy = dx + cap; dz = dy + cap; zs = dz + cap; ze = zs + cap; unc = ze + cap;
     q0 = unc + cap; q1 = q0 + cap; q2 = q1 + cap; q3 = q2 + cap; score = q3 + cap;
-    ng = reinterpret_cast<uint32_t *>(score + cap);
+    gate = reinterpret_cast<GateRec *>(score + cap);
+    ng = reinterpret_cast<uint32_t *>(gate + cap);
     row = ng + cap;
+    meta = row + cap;
+    list = meta + cap;
+    list0 = reinterpret_cast<uint16_t *>(list + (size_t)kWarps * 2 * (cap + kListExtra));
   }
 };
 
@@ -47,15 +73,6 @@ LM_D double4 ld_seg(const double4 *p) {
   return make_double4(a.x, a.y, b.x, b.y);
 }
 LM_D double deg_from_cos_abs(double c) { return acos(fabs(c)) * consts<double>::rad2deg(); }
-
-// Line3d::sensitivity (base/linebase.cc:100-107)
-LM_D double sensitivity(const ViewD &v, vec3<double> Xs, vec3<double> Xe, vec3<double> dir) {
-  vec2<double> ps = dehom(proj_h(v.P, Xs));
-  vec2<double> pe = dehom(proj_h(v.P, Xe));
-  vec2<double> mid = (ps + pe) * 0.5;
-  vec3<double> d3 = normalized(mat3_mul_h(v.M, mid.x, mid.y));
-  return 90.0 - deg_from_cos_abs(dot(dir, d3));
-}
 
 // triangulate_point (triangulation/functions.cc:100-117): mid-point method, 2x2 LDLT.
 LM_D bool triangulate_point(const ViewD &v1, const ViewD &v2, vec3<double> n1e, vec3<double> n2e, vec3<double> C1,
@@ -84,84 +101,132 @@ struct Src {
   vec3<double> w1s, w1e;     // M1 [p;1] (unnormalised world rays)
   vec3<double> ray1s, ray1e; // normalised
   vec3<double> C1;
+  vec3<double> pu, pv;       // orthonormal basis of the back-projection plane of l1
   bool ok;
 };
 
+// Margin comparison of squared quantities: returns +1 / -1 when lhs is above / below rhs by more than
+// 1e-9 relative (far beyond fp64 rounding of these short expressions), 0 when too close to call -- the
+// caller then evaluates the reference's transcendental form for that single test.
+LM_D int cmp_margin(double lhs, double rhs) {
+  const double REL = 1e-9;
+  if (lhs > rhs * (1.0 + REL)) return 1;
+  if (lhs < rhs * (1.0 - REL)) return -1;
+  return 0;
+}
+
+// Line3d::sensitivity(view) > th  (base/linebase.cc:100-107), decided without acos when clear:
+// 90 - acos|c| > th  <=>  |c| > sin(th).
+LM_D bool sensitivity_exceeds(const TriParams &p, const ViewD &v, vec3<double> Xs, vec3<double> Xe, vec3<double> dir_raw) {
+  const vec2<double> ps = dehom(proj_h(v.P, Xs));
+  const vec2<double> pe = dehom(proj_h(v.P, Xe));
+  const vec2<double> mid = (ps + pe) * 0.5;
+  const vec3<double> d3 = mat3_mul_h(v.M, mid.x, mid.y);
+  const double t = dot(dir_raw, d3);
+  const int cm = cmp_margin(t * t, p.sin2_sens * dot(dir_raw, dir_raw) * dot(d3, d3));
+  if (cm != 0 && p.sens_poly_ok) return cm > 0;
+  return 90.0 - deg_from_cos_abs(dot(normalized(dir_raw), normalized(d3))) > p.sensitivity_threshold;
+}
+
 // One match row -> candidate. Steps follow triangulateOneNode "Step 3" (base_line_triangulator.cc:290-326).
+// Unit-vector normalisations that do not change a decision or an output beyond rounding are dropped; the
+// angle / sensitivity gates use margin forms with the reference's acos form as the tie fallback.
 LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const Src &src, uint32_t ngv, uint32_t ngl, Cand &c,
                         double4 &l2out) {
   const double4 l2 = ld_seg(&p.segs[p.line_off[ngv] + ngl]);
   l2out = l2;
-  {
-    double dx = l2.x - l2.z, dy = l2.y - l2.w;
-    if (sqrt(dx * dx + dy * dy) <= p.min_length_2d) return false; // :177
-  }
+  const vec2<double> s2 = mk2(l2.x, l2.y), e2 = mk2(l2.z, l2.w);
+  const vec2<double> v2d = e2 - s2;
+  const double len2sq = dot(v2d, v2d);
+  if (sqrt(len2sq) <= p.min_length_2d) return false; // :177
   if (p.disable_algebraic) return false;
   const ViewD &v2 = p.views[ngv];
-  vec3<double> c2s = mat3_mul_h(v2.M, l2.x, l2.y);
-  vec3<double> c2e = mat3_mul_h(v2.M, l2.z, l2.w);
-  // getNormalDirection (functions.cc:28-35) + ray-plane angle tests (:292-302)
-  vec3<double> n2 = normalized(cross(c2s, c2e));
-  double angle_start = 90.0 - deg_from_cos_abs(dot(n2, src.ray1s));
-  if (angle_start < p.line_tri_angle_threshold) return false;
-  double angle_end = 90.0 - deg_from_cos_abs(dot(n2, src.ray1e));
-  if (angle_end < p.line_tri_angle_threshold) return false;
-  vec3<double> C2 = mk3(v2.C[0], v2.C[1], v2.C[2]);
-  // compute_epipolar_IoU (functions.cc:76-98). F x1 = M2^T ((C1 - C2) x (M1 x1)) exactly
-  // (F = K2^-T [t]x R2 R1^T K1^-1 with t = R2 (C1 - C2)); see DESIGN.md.
+  const vec3<double> c2s = mat3_mul_h(v2.M, l2.x, l2.y);
+  const vec3<double> c2e = mat3_mul_h(v2.M, l2.z, l2.w);
+  // getNormalDirection (functions.cc:28-35) + ray-plane angle tests (:292-302):
+  // 90 - acos|n2.ray| < th  <=>  |n2.ray| < sin(th)
   {
-    vec3<double> base = src.C1 - C2;
-    vec3<double> coor_l2 = normalized(cross(mk3(l2.x, l2.y, 1.0), mk3(l2.z, l2.w, 1.0)));
-    vec3<double> eps_ = normalized(mat3T_mul(v2.M, cross(base, src.w1s)));
-    vec2<double> cs = dehom(cross(coor_l2, eps_));
-    vec3<double> epe_ = normalized(mat3T_mul(v2.M, cross(base, src.w1e)));
-    vec2<double> ce = dehom(cross(coor_l2, epe_));
-    vec2<double> s2 = mk2(l2.x, l2.y), e2 = mk2(l2.z, l2.w);
-    vec2<double> dir2 = normalized(e2 - s2);
-    double len2 = norm(s2 - e2);
-    double c1 = dot(cs - s2, dir2) / len2;
-    double c2 = dot(ce - s2, dir2) / len2;
+    const vec3<double> n2 = cross(c2s, c2e);
+    const double nn = dot(n2, n2);
+    const double ts = dot(n2, src.ray1s), te = dot(n2, src.ray1e);
+    int cs_ = cmp_margin(ts * ts, p.sin2_tri * nn), ce_ = cmp_margin(te * te, p.sin2_tri * nn);
+    if (!p.tri_poly_ok) cs_ = ce_ = 0;
+    if (cs_ < 0 || ce_ < 0) return false; // one endpoint ray clearly below the threshold
+    if (cs_ == 0 || ce_ == 0) {           // too close to call: the reference's acos form decides
+      const vec3<double> n2u = normalized(n2);
+      if (cs_ == 0 && 90.0 - deg_from_cos_abs(dot(n2u, src.ray1s)) < p.line_tri_angle_threshold) return false;
+      if (ce_ == 0 && 90.0 - deg_from_cos_abs(dot(n2u, src.ray1e)) < p.line_tri_angle_threshold) return false;
+    }
+  }
+  const vec3<double> C2 = mk3(v2.C[0], v2.C[1], v2.C[2]);
+  // compute_epipolar_IoU (functions.cc:76-98). F x1 = M2^T ((C1 - C2) x (M1 x1)) exactly
+  // (F = K2^-T [t]x R2 R1^T K1^-1 with t = R2 (C1 - C2)); dehomogeneous() of the cross product of two
+  // normalised line vectors == raw.xy / (raw.z + EPS |a| |b|).
+  {
+    const vec3<double> base = src.C1 - C2;
+    const vec3<double> l2h = cross(mk3(l2.x, l2.y, 1.0), mk3(l2.z, l2.w, 1.0));
+    const double nl = norm(l2h);
+    const vec3<double> eps_ = mat3T_mul(v2.M, cross(base, src.w1s));
+    const vec3<double> hs = cross(l2h, eps_);
+    const double ws = hs.z + consts<double>::eps() * nl * norm(eps_);
+    const vec3<double> epe_ = mat3T_mul(v2.M, cross(base, src.w1e));
+    const vec3<double> he = cross(l2h, epe_);
+    const double we = he.z + consts<double>::eps() * nl * norm(epe_);
+    const vec2<double> cs = mk2(hs.x / ws, hs.y / ws), ce = mk2(he.x / we, he.y / we);
+    double c1 = dot(cs - s2, v2d) / len2sq;
+    double c2 = dot(ce - s2, v2d) / len2sq;
     if (c1 > c2) { double t = c1; c1 = c2; c2 = t; }
     double IoU = (smin(c2, 1.0) - smax(c1, 0.0)) / (smax(c2, 1.0) - smin(c1, 0.0));
+    if (fabs(IoU - p.IoU_threshold) < 1e-7) {
+      // too close to the threshold: evaluate in the reference's normalised form
+      const vec3<double> coor_l2 = normalized(l2h);
+      const vec2<double> cs2 = dehom(cross(coor_l2, normalized(eps_)));
+      const vec2<double> ce2 = dehom(cross(coor_l2, normalized(epe_)));
+      const vec2<double> dir2 = normalized(v2d);
+      const double len2 = norm(s2 - e2);
+      c1 = dot(cs2 - s2, dir2) / len2;
+      c2 = dot(ce2 - s2, dir2) / len2;
+      if (c1 > c2) { double t = c1; c1 = c2; c2 = t; }
+      IoU = (smin(c2, 1.0) - smax(c1, 0.0)) / (smax(c2, 1.0) - smin(c1, 0.0));
+    }
     if (IoU < p.IoU_threshold) return false;
   }
   vec3<double> Xs, Xe;
-  vec3<double> r2s = normalized(c2s), r2e = normalized(c2e);
   const double EPS = consts<double>::eps();
   if (!p.use_endpoints_triangulation) {
-    // line_triangulation (functions.cc:194-233): plane-pair intersection
-    vec3<double> B = C2 - src.C1;
-    vec3<double> nb = mk3(-r2s.x, -r2s.y, -r2s.z), nc = mk3(-r2e.x, -r2e.y, -r2e.z);
-    vec3<double> ls = solve3_cols(src.ray1s, nb, nc, B);
+    // line_triangulation (functions.cc:194-233): plane-pair intersection. Only lambda_0 is used, which
+    // does not depend on the norms of the second and third column.
+    const vec3<double> B = C2 - src.C1;
+    const vec3<double> nb = mk3(-c2s.x, -c2s.y, -c2s.z), nc = mk3(-c2e.x, -c2e.y, -c2e.z);
+    const vec3<double> ls = solve3_cols(src.ray1s, nb, nc, B);
     Xs = src.ray1s * ls.x + src.C1;
-    vec3<double> le = solve3_cols(src.ray1e, nb, nc, B);
+    const vec3<double> le = solve3_cols(src.ray1e, nb, nc, B);
     Xe = src.ray1e * le.x + src.C1;
     c.zs = v1.P[8] * Xs.x + v1.P[9] * Xs.y + v1.P[10] * Xs.z + v1.P[11];
     c.ze = v1.P[8] * Xe.x + v1.P[9] * Xe.y + v1.P[10] * Xe.z + v1.P[11];
     if (c.zs < EPS || c.ze < EPS) return false;
-    double d21 = v2.P[8] * Xs.x + v2.P[9] * Xs.y + v2.P[10] * Xs.z + v2.P[11];
-    double d22 = v2.P[8] * Xe.x + v2.P[9] * Xe.y + v2.P[10] * Xe.z + v2.P[11];
+    const double d21 = v2.P[8] * Xs.x + v2.P[9] * Xs.y + v2.P[10] * Xs.z + v2.P[11];
+    const double d22 = v2.P[8] * Xe.x + v2.P[9] * Xe.y + v2.P[10] * Xe.z + v2.P[11];
     if (d21 < EPS || d22 < EPS) return false;
     if (isnan(Xs.x) || isnan(Xe.x)) return false;
   } else {
     // triangulate_line_by_endpoints (functions.cc:172-190)
+    const vec3<double> r2s = normalized(c2s), r2e = normalized(c2e);
     if (!triangulate_point(v1, v2, src.ray1s, r2s, src.C1, C2, Xs)) return false;
     if (!triangulate_point(v1, v2, src.ray1e, r2e, src.C1, C2, Xe)) return false;
     c.zs = v1.P[8] * Xs.x + v1.P[9] * Xs.y + v1.P[10] * Xs.z + v1.P[11];
     c.ze = v1.P[8] * Xe.x + v1.P[9] * Xe.y + v1.P[10] * Xe.z + v1.P[11];
   }
   // sensitivity in both views (:315-317)
-  vec3<double> dir = normalized(Xe - Xs);
-  if (sensitivity(v1, Xs, Xe, dir) > p.sensitivity_threshold &&
-      sensitivity(v2, Xs, Xe, dir) > p.sensitivity_threshold)
-    return false;
+  const vec3<double> dir_raw = Xe - Xs;
+  if (sensitivity_exceeds(p, v1, Xs, Xe, dir_raw) && sensitivity_exceeds(p, v2, Xs, Xe, dir_raw)) return false;
   // uncertainty = min(u1, u2) (:319-321; linebase.cc:109-116; camera.cc:228-242)
   {
-    double d1 = (c.zs + c.ze) / 2.0;
-    double u1 = p.var2d * d1 / v1.fbar;
-    double z2s = v2.P[8] * Xs.x + v2.P[9] * Xs.y + v2.P[10] * Xs.z + v2.P[11];
-    double z2e = v2.P[8] * Xe.x + v2.P[9] * Xe.y + v2.P[10] * Xe.z + v2.P[11];
-    double u2 = p.var2d * ((z2s + z2e) / 2.0) / v2.fbar;
+    const double d1 = (c.zs + c.ze) / 2.0;
+    const double u1 = p.var2d * d1 / v1.fbar;
+    const double z2s = v2.P[8] * Xs.x + v2.P[9] * Xs.y + v2.P[10] * Xs.z + v2.P[11];
+    const double z2e = v2.P[8] * Xe.x + v2.P[9] * Xe.y + v2.P[10] * Xe.z + v2.P[11];
+    const double u2 = p.var2d * ((z2s + z2e) / 2.0) / v2.fbar;
     c.unc = smin(u1, u2);
   }
   // test_line_inside_ranges (functions.cc:8-26)
@@ -207,13 +272,78 @@ LM_D double pair_score(const TriParams &p, const seg<vec3<double>> &Li, vec3<dou
   return smin(score3, score2);
 }
 
-__global__ void __launch_bounds__(kThreads) tri_node_kernel(const __grid_constant__ TriParams p) {
+// ---- pruning gates -----------------------------------------------------------------------------------
+// The reference decides every sub-test on exp(-(v/sigma)^2/2) >= score_th, i.e. v <= th. The gates below
+// only discard pairs that fail a sub-test by a margin far above the arithmetic error of the gate (fp32
+// for the 3d tests, fp64 polynomial forms for the 2d tests); every surviving pair is then scored by
+// pair_score(), which evaluates the reference formulas in fp64 and takes all decisions itself. Pruned
+// pairs would have scored exactly 0, so results do not depend on the gates.
+
+// 3d gate, fp32: angle (line_linker.cc:185-192) and scale-invariant endpoint distance (:269-277).
+LM_D bool gate3d(const GateRec &r, const GateRec *g, float cos_th) {
+  const float4 a = *reinterpret_cast<const float4 *>(&g->dx);
+  const float cs = fabsf(r.dx * a.x + r.dy * a.y + r.dz * a.z);
+  if (cs < cos_th) return false;
+  const float4 b = *reinterpret_cast<const float4 *>(&g->sx);
+  const float ax = r.sx - b.x, ay = r.sy - b.y, az = r.sz - b.z;
+  if (ax * ax + ay * ay + az * az > r.lims2) return false;
+  const float4 c = *reinterpret_cast<const float4 *>(&g->ex);
+  const float bx = r.ex - c.x, by = r.ey - c.y, bz = r.ez - c.z;
+  return !(bx * bx + by * by + bz * bz > r.lime2);
+}
+
+// 2d gate, fp64 without transcendentals: angle, overlap and perpendicular tests of
+// LineLinker2d::compute_score (line_linker.cc:139-160) in margin form.
+LM_D bool gate2d(const TriParams &p, const seg<vec3<double>> &Li, const Slab &sl, int j, uint32_t vj) {
+  const LinkerDev<double> &c = p.l2d;
+  const ViewD &v = p.views[vj];
+  const vec2<double> as = dehom(proj_h(v.P, Li.s)), ae = dehom(proj_h(v.P, Li.e));
+  const vec2<double> bs = mk2(sl.q0[j], sl.q1[j]), be = mk2(sl.q2[j], sl.q3[j]);
+  const vec2<double> va = ae - as, vb = be - bs;
+  const double na2 = dot(va, va), nb2 = dot(vb, vb);
+  const double REL = 1e-9;
+  if (c.use_angle) {
+    const double d = dot(va, vb);
+    if (d * d < p.cos2_th2d * na2 * nb2 * (1.0 - REL)) return false; // |cos| < cos(th_angle)
+  }
+  if (c.use_overlap) {
+    // compute_bioverlap (line_dists.h:190-208) with p = dot / |l2|^2 (no normalisation)
+    double p1 = dot(as - bs, vb) / nb2, p2 = dot(ae - bs, vb) / nb2;
+    if (p1 > p2) { const double t = p1; p1 = p2; p2 = t; }
+    const double o1 = smin(p2, 1.0) - smax(p1, 0.0);
+    double r1 = dot(bs - as, va) / na2, r2 = dot(be - as, va) / na2;
+    if (r1 > r2) { const double t = r1; r1 = r2; r2 = t; }
+    const double o2 = smin(r2, 1.0) - smax(r1, 0.0);
+    const double bio = smax(o1, o2);
+    if (bio < c.th_overlap - REL * (1.0 + fabs(c.th_overlap))) return false;
+  }
+  if (c.use_perp) {
+    // squared endpoint-to-infinite-line distances (line_dists.h:105-133)
+    const vec2<double> d0 = as - bs, d1 = ae - bs, d2 = bs - as, d3 = be - as;
+    const double t0 = dot(d0, vb), t1 = dot(d1, vb), t2 = dot(d2, va), t3 = dot(d3, va);
+    double m = dot(d0, d0) - t0 * t0 / nb2;
+    m = fmax(m, dot(d1, d1) - t1 * t1 / nb2);
+    m = fmax(m, dot(d2, d2) - t2 * t2 / na2);
+    m = fmax(m, dot(d3, d3) - t3 * t3 / na2);
+    if (m > p.th_perp2_2d * (1.0 + REL) + REL) return false;
+  }
+  return true;
+}
+
+template <bool SLAB>
+__global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(const __grid_constant__ TriParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_wtot[kWarps];
   __shared__ int s_nvalid;
+  __shared__ int s_next_row;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
   Slab sl;
-  sl.carve(p.use_slab ? p.slab + (int64_t)blockIdx.x * p.slab_stride : reinterpret_cast<char *>(smem_raw), p.cap);
+  if (SLAB) sl.carve(p.slab + (int64_t)blockIdx.x * p.slab_stride, p.cap);
+  else sl.carve(reinterpret_cast<char *>(smem_raw), p.cap);
+  uint32_t *list1 = sl.list + (size_t)(warp * 2) * (p.cap + kListExtra), *list2 = list1 + p.cap + kListExtra;
+  uint16_t *list0 = sl.list0 + (size_t)warp * p.cap;
+  unsigned long long n1_total = 0, n2_total = 0;
 
   for (int64_t node = p.node_begin + blockIdx.x; node < p.node_end; node += gridDim.x) {
     const uint32_t r0 = p.node_row_off[node], r1 = p.node_row_off[node + 1];
@@ -237,6 +367,8 @@ __global__ void __launch_bounds__(kThreads) tri_node_kernel(const __grid_constan
       src.ray1s = normalized(src.w1s);
       src.ray1e = normalized(src.w1e);
       src.C1 = mk3(v1.C[0], v1.C[1], v1.C[2]);
+      src.pu = src.ray1s;
+      src.pv = normalized(src.ray1e - src.ray1s * dot(src.ray1e, src.ray1s));
     }
     int count = 0;
     for (int base = 0; base < nrows; base += kThreads) {
@@ -260,8 +392,8 @@ __global__ void __launch_bounds__(kThreads) tri_node_kernel(const __grid_constan
         tot += s_wtot[w];
       }
       if (ok) {
-        const int idx = count + woff + __popc(bal & ((1u << lane) - 1u));
-        vec3<double> d = normalized(c.e - c.s);
+        const int idx = count + woff + __popc(bal & lt_mask);
+        const vec3<double> d = normalized(c.e - c.s);
         sl.sx[idx] = c.s.x; sl.sy[idx] = c.s.y; sl.sz[idx] = c.s.z;
         sl.ex[idx] = c.e.x; sl.ey[idx] = c.e.y; sl.ez[idx] = c.e.z;
         sl.dx[idx] = d.x; sl.dy[idx] = d.y; sl.dz[idx] = d.z;
@@ -269,56 +401,169 @@ __global__ void __launch_bounds__(kThreads) tri_node_kernel(const __grid_constan
         sl.q0[idx] = l2.x; sl.q1[idx] = l2.y; sl.q2[idx] = l2.z; sl.q3[idx] = l2.w;
         sl.ng[idx] = ng;
         sl.row[idx] = (uint32_t)r;
+        // fp32 gate copy, relative to the source camera centre (keeps |coord| ~ depth)
+        const vec3<double> rs = c.s - src.C1, re = c.e - src.C1;
+        // scale-invariance limit th * (z + EPS) widened by 0.5% plus 1e-5 of the coordinate magnitude
+        // (fp32 rounding of the two endpoints is < 1e-6 of it); see DESIGN.md "gates"
+        const double rad = fmax(norm(rs), norm(re));
+        const double ls = p.l3d.th_scaleinv * (c.zs + consts<double>::eps()) * 1.005 + 1e-5 * rad;
+        const double le = p.l3d.th_scaleinv * (c.ze + consts<double>::eps()) * 1.005 + 1e-5 * rad;
+        GateRec g;
+        g.dx = (float)d.x; g.dy = (float)d.y; g.dz = (float)d.z; g.lims2 = (float)(ls * ls * 1.000001);
+        g.sx = (float)rs.x; g.sy = (float)rs.y; g.sz = (float)rs.z; g.lime2 = (float)(le * le * 1.000001);
+        g.ex = (float)re.x; g.ey = (float)re.y; g.ez = (float)re.z; g.pad = 0.f;
+        sl.gate[idx] = g;
+        // direction bucket: every candidate of the node lies in the back-projection plane of l1, so its
+        // direction is an angle phi in [0, pi) within that plane; the 3d angle test can only pass for
+        // candidates whose buckets (width >= th_angle + margin) are equal or adjacent
+        uint32_t bucket = 0;
+        if (p.n_buckets > 1) {
+          float phi = atan2f((float)dot(d, src.pv), (float)dot(d, src.pu));
+          if (phi < 0.f) phi += 3.14159265358979f;
+          int b = (int)(phi * p.bucket_scale);
+          bucket = (uint32_t)min(max(b, 0), p.n_buckets - 1);
+        }
+        sl.meta[idx] = (ng & 0xffff0000u) | bucket;
+        {
+          uint32_t accept = 0xffffffffu; // own bucket and both neighbours (circular)
+          if (p.n_buckets > 3) {
+            const int b = (int)bucket, nb = p.n_buckets;
+            accept = (1u << b) | (1u << (b + 1 == nb ? 0 : b + 1)) | (1u << (b == 0 ? nb - 1 : b - 1));
+          }
+          sl.gate[idx].pad = __uint_as_float(accept);
+        }
       }
       count += tot;
       __syncthreads();
     }
     const int C = count;
-    if (tid == 0) s_nvalid = 0;
-    // ---------------- phase B: all-pairs scoring, one warp per candidate i ------------------
-    for (int i = warp; i < C; i += kWarps) {
-      seg<vec3<double>> Li;
-      Li.s = mk3(sl.sx[i], sl.sy[i], sl.sz[i]);
-      Li.e = mk3(sl.ex[i], sl.ey[i], sl.ez[i]);
-      const vec3<double> di = mk3(sl.dx[i], sl.dy[i], sl.dz[i]);
-      const double zsi = sl.zs[i], zei = sl.ze[i];
-      const uint32_t vi = sl.ng[i] >> 16;
-      double total = 0.0;
-      uint32_t carry_view = 0xffffffffu;
-      double carry_max = 0.0;
-      for (int jb = 0; jb < C; jb += 32) {
-        const int j = jb + lane;
-        double s = 0.0;
-        uint32_t vj = 0xfffffffeu;
-        if (j < C) {
-          vj = sl.ng[j] >> 16;
-          if (j != i && vj != vi) s = pair_score(p, Li, di, zsi, zei, sl, j, vj);
+    if (tid == 0) { s_nvalid = 0; s_next_row = 0; }
+    __syncthreads();
+    // ---------------- phase B: all-pairs scoring ------------------------------------------------
+    // Warps fetch rows i dynamically. B1 prunes (i, j) pairs with the fp32 3d gates and appends the
+    // survivors of several rows to a warp-private list until it holds >= kFlush entries, so that the fp64
+    // stages B2 (2d margin gates) and B3 (exact reference score) run on dense 32-lane batches.
+    for (int i = tid; i < C; i += kThreads) sl.score[i] = 0.0;
+    __syncthreads();
+    bool more = true;
+    while (more) {
+      int n1 = 0;
+      while (n1 < kFlush) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&s_next_row, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= C) { more = false; break; }
+        const GateRec rf = sl.gate[i];
+        const uint32_t vi = sl.meta[i] >> 16;
+        const uint32_t accept = __float_as_uint(rf.pad);
+        // B0: bucket / view prefilter on one packed word per candidate
+        int n0 = 0;
+        for (int jb = 0; jb < C; jb += 32) {
+          const int j = jb + lane;
+          bool pass = false;
+          if (j < C) {
+            const uint32_t mj = sl.meta[j];
+            pass = ((accept >> (mj & 31u)) & 1u) && (mj >> 16) != vi && j != i;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, pass);
+          if (pass) list0[n0 + __popc(bal & lt_mask)] = (uint16_t)j;
+          n0 += __popc(bal);
         }
-        if (vj == carry_view && carry_max > s) s = carry_max;
-        // segmented inclusive max-scan over lanes with equal view (candidates are view-sorted)
+        __syncwarp();
+        // B1: fp32 3d gates on the dense prefilter list
+        for (int kb = 0; kb < n0; kb += 32) {
+          const int k = kb + lane;
+          bool pass = false;
+          int j = 0;
+          if (k < n0) {
+            j = list0[k];
+            pass = gate3d(rf, &sl.gate[j], p.cos_th3d_f);
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, pass);
+          if (pass) list1[n1 + __popc(bal & lt_mask)] = ((uint32_t)i << 16) | (uint32_t)j;
+          n1 += __popc(bal);
+        }
+        __syncwarp();
+      }
+      __syncwarp();
+      n1_total += n1;
+      if (n1 == 0) continue;
+      // B2: fp64 margin gates of the 2d tests
+      int n2 = 0;
+      for (int kb = 0; kb < n1; kb += 32) {
+        const int k = kb + lane;
+        bool pass = false;
+        uint32_t e = 0;
+        if (k < n1) {
+          e = list1[k];
+          const int i = e >> 16, j = e & 0xffffu;
+          seg<vec3<double>> Li;
+          Li.s = mk3(sl.sx[i], sl.sy[i], sl.sz[i]);
+          Li.e = mk3(sl.ex[i], sl.ey[i], sl.ez[i]);
+          pass = gate2d(p, Li, sl, j, sl.ng[j] >> 16);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (pass) list2[n2 + __popc(bal & lt_mask)] = e;
+        n2 += __popc(bal);
+      }
+      __syncwarp();
+      n2_total += n2;
+      // B3: exact reference scores; maximum per (row, image), summed per row (:97-112). Entries are ordered
+      // by (row, image), so both reductions are segmented warp scans with a carry across batches.
+      uint32_t carry_key = 0xffffffffu, cur_row = 0xffffffffu;
+      double carry_max = 0.0, cur_sum = 0.0;
+      for (int kb = 0; kb < n2; kb += 32) {
+        const int k = kb + lane;
+        double sc = 0.0;
+        uint32_t key = 0xfffffffeu, row = 0xfffffffeu; // key = row << 16 | view
+        if (k < n2) {
+          const uint32_t e = list2[k];
+          const int i = e >> 16, j = e & 0xffffu;
+          const uint32_t vj = sl.ng[j] >> 16;
+          row = (uint32_t)i;
+          key = (row << 16) | vj;
+          seg<vec3<double>> Li;
+          Li.s = mk3(sl.sx[i], sl.sy[i], sl.sz[i]);
+          Li.e = mk3(sl.ex[i], sl.ey[i], sl.ez[i]);
+          sc = pair_score(p, Li, mk3(sl.dx[i], sl.dy[i], sl.dz[i]), sl.zs[i], sl.ze[i], sl, j, vj);
+        }
+        if (key == carry_key && carry_max > sc) sc = carry_max;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-          const double o = __shfl_up_sync(0xffffffffu, s, d);
-          const uint32_t ov = __shfl_up_sync(0xffffffffu, vj, d);
-          if (lane >= d && ov == vj && o > s) s = o;
+          const double o = __shfl_up_sync(0xffffffffu, sc, d);
+          const uint32_t ok = __shfl_up_sync(0xffffffffu, key, d);
+          if (lane >= d && ok == key && o > sc) sc = o;
         }
-        uint32_t vnext = __shfl_down_sync(0xffffffffu, vj, 1);
-        if (lane == 31) vnext = (j + 1 < C) ? (sl.ng[j + 1] >> 16) : 0xfffffffdu;
-        const bool seg_end = (j < C) && (vnext != vj);
-        // one image contributes its maximum once (:110-112); add in ascending-view order
+        uint32_t knext = __shfl_down_sync(0xffffffffu, key, 1);
+        if (lane == 31) {
+          knext = 0xfffffffdu;
+          if (k + 1 < n2) { const uint32_t e2 = list2[k + 1]; knext = (e2 & 0xffff0000u) | (sl.ng[e2 & 0xffffu] >> 16); }
+        }
+        const bool seg_end = (k < n2) && (knext != key);
+        // one image contributes its maximum once (:110-112): add the segment maxima to their row's total in
+        // list order = ascending (row, image), exactly the reference's std::map order; the running
+        // (row, sum) pair is warp-uniform, so the result does not depend on how rows were batched
         unsigned m = __ballot_sync(0xffffffffu, seg_end);
         while (m) {
           const int l = __ffs(m) - 1;
-          total += __shfl_sync(0xffffffffu, s, l);
+          const double v = __shfl_sync(0xffffffffu, sc, l);
+          const uint32_t r = __shfl_sync(0xffffffffu, row, l);
+          if (r != cur_row) {
+            if (cur_row != 0xffffffffu && lane == 0) sl.score[cur_row] = cur_sum;
+            cur_row = r;
+            cur_sum = 0.0;
+          }
+          cur_sum += v;
           m &= m - 1;
         }
-        const uint32_t v31 = __shfl_sync(0xffffffffu, vj, 31);
-        const double s31 = __shfl_sync(0xffffffffu, s, 31);
+        const uint32_t k31 = __shfl_sync(0xffffffffu, key, 31);
+        const double s31 = __shfl_sync(0xffffffffu, sc, 31);
         const bool end31 = __shfl_sync(0xffffffffu, (int)seg_end, 31);
-        if (!end31 && jb + 31 < C) { carry_view = v31; carry_max = s31; }
-        else { carry_view = 0xffffffffu; carry_max = 0.0; }
+        if (!end31 && kb + 31 < n2) { carry_key = k31; carry_max = s31; }
+        else { carry_key = 0xffffffffu; carry_max = 0.0; }
       }
-      if (lane == 0) sl.score[i] = total;
+      if (cur_row != 0xffffffffu && lane == 0) sl.score[cur_row] = cur_sum;
+      __syncwarp();
     }
     __syncthreads();
     // ---------------- phase C: valid connections + best candidate (:115-153) ----------------
@@ -382,16 +627,24 @@ __global__ void __launch_bounds__(kThreads) tri_node_kernel(const __grid_constan
     }
     __syncthreads();
   }
+  if (lane == 0 && n1_total) {
+    atomicAdd(&p.counters[2], n1_total); // pairs past the fp32 3d gates
+    atomicAdd(&p.counters[3], n2_total); // pairs scored exactly in fp64
+  }
 }
 
 void launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem, cudaStream_t s) {
   (void)block;
   static size_t configured = 0;
+  if (p.use_slab) {
+    tri_node_kernel<true><<<grid, kThreads, 0, s>>>(p);
+    return;
+  }
   if (smem > configured) {
-    cudaFuncSetAttribute(tri_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(tri_node_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  tri_node_kernel<<<grid, kThreads, smem, s>>>(p);
+  tri_node_kernel<false><<<grid, kThreads, smem, s>>>(p);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -40,7 +40,7 @@ struct TriParams {
   NodeRecord *nodes;           // [nodes] out
   uint8_t *row_state;          // [rows] out: 0 rejected, 1 candidate, 2 valid connection
   double *row_cand;            // [rows][10] out (debug_mode only, else NULL)
-  unsigned long long *counters; // [4] n_candidates, n_valid, n_fp64_fallback, spare
+  unsigned long long *counters; // [4] n_candidates, n_valid, pairs past the 3d gates, pairs scored exactly
   char *slab;                  // global scratch for nodes whose rows exceed the smem capacity (or NULL)
   int64_t slab_stride;         // bytes per CTA
   int64_t node_begin, node_end;
@@ -53,6 +53,15 @@ struct TriParams {
   double rlo[3], rhi[3];
   LinkerDev<double> l2d;  // user linker2d_config
   LinkerDev<double> l3d;  // linker3d_config after set_to_shared_parent_scoring()
+  // pruning-gate constants derived from the thresholds (see tri_kernels.cu "pruning gates")
+  float cos_th3d_f;       // cos(l3d.th_angle) - 4e-6
+  double cos2_th2d;       // cos^2(l2d.th_angle) (0 when th_angle >= 90)
+  double th_perp2_2d;     // l2d.th_perp^2
+  double sin2_tri;        // sin^2(line_tri_angle_threshold); valid when tri_poly_ok
+  double sin2_sens;       // sin^2(sensitivity_threshold); valid when sens_poly_ok
+  int tri_poly_ok, sens_poly_ok; // thresholds inside (0, 90): the polynomial forms are equivalent
+  int n_buckets;          // direction buckets over [0, pi) (1 = prefilter off)
+  float bucket_scale;     // n_buckets / pi
 };
 
 struct EdgeParams {

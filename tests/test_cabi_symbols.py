@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(LinkerConfig) == 8 * 8 + 6 * 4
     assert C.sizeof(TriConfig) == 6 * 8 + 12 * 4 + 2 * C.sizeof(LinkerConfig)
     assert _cabi.NODE_RECORD_DTYPE.itemsize == 96
-    assert C.sizeof(_cabi.TriStats) == 7 * 8 + 2 * 8
+    assert C.sizeof(_cabi.TriStats) == 8 * 8 + 2 * 8
 
 
 def test_no_cpu_fallback():
