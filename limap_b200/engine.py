@@ -50,6 +50,25 @@ class TriEngine:
     def unset_ranges(self):
         check(lib().lm_tri_unset_ranges(self.ctx.handle))
 
+    def set_vps(self, vpresults, img_ids, line_off):
+        """InitVPResults: {img_id: VPResult-like with .labels and .vps}."""
+        ids = [int(i) for i in img_ids if int(i) in vpresults]
+        label_off, vp_off, labels, vps = [0], [0], [], []
+        for i in ids:
+            r = vpresults[i]
+            lab = np.asarray(r.labels, np.int32).reshape(-1)
+            v = np.asarray(r.vps, np.float64).reshape(-1, 3)
+            labels.append(lab)
+            vps.append(v)
+            label_off.append(label_off[-1] + len(lab))
+            vp_off.append(vp_off[-1] + len(v))
+        labels = np.concatenate(labels) if labels else np.zeros(0, np.int32)
+        vps = np.concatenate(vps) if vps else np.zeros((0, 3))
+        ids_a = np.asarray(ids, np.int32)
+        lo, vo = np.asarray(label_off, np.int64), np.asarray(vp_off, np.int64)
+        check(lib().lm_tri_set_vps(self.ctx.handle, len(ids), ptr(ids_a), ptr(lo), ptr(np.ascontiguousarray(labels)),
+                                   ptr(vo), ptr(np.ascontiguousarray(vps))))
+
     # ---- TriangulateImage ----------------------------------------------------------------------
     def add_image_matches(self, img_id, ng_ids, row_off, pairs):
         ng_ids = np.ascontiguousarray(ng_ids, np.int32)

@@ -1,0 +1,88 @@
+"""The limap-style operator surface ([D] triangulation and [E] line bundle adjustment of
+src/limap/runners/line_triangulation.py:99-219) driven the way the runner drives it, checked against the
+oracle on the same scene."""
+import numpy as np
+import pytest
+
+from limap_b200.config import DEFAULT_YAML_TRIANGULATION
+from limap_b200.synth import make_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _imagecols(sc):
+    import limap.base as base
+    cams = {0: base.Camera("SIMPLE_PINHOLE", [sc.kvec[0, 0], sc.kvec[0, 2], sc.kvec[0, 3]], 0, (600, 800))}
+    imgs = {int(i): base.CameraImage(0, base.CameraPose(sc.qvec[v], sc.tvec[v]), f"img_{int(i)}.png")
+            for v, i in enumerate(sc.img_ids)}
+    return base.ImageCollection(cams, imgs)
+
+
+def test_runner_style_triangulation_and_ba():
+    import limap.base as base
+    import limap.optimize as optimize
+    import limap.triangulation as triangulation
+    from oracle import oracle as orc
+    sc = make_scene(V=10, L=150, N=6, K=6, seed=41)
+    cfg = dict(DEFAULT_YAML_TRIANGULATION)
+    imagecols = _imagecols(sc)
+    all_2d_segs = {int(i): sc.lines_of(v) for v, i in enumerate(sc.img_ids)}
+    # [D]
+    Triangulator = triangulation.GlobalLineTriangulator(cfg)
+    Triangulator.SetRanges(sc.ranges)
+    all_2d_lines = base.get_all_lines_2d(all_2d_segs)
+    Triangulator.Init(all_2d_lines, imagecols)
+    for img_id in imagecols.get_img_ids():
+        Triangulator.TriangulateImage(img_id, sc.matches[img_id])
+    linetracks = Triangulator.ComputeLineTracks()
+    assert Triangulator.CountImages() == 10 and Triangulator.CountLines(0) == 150
+    # oracle on the same data
+    o = orc.OracleTri(cfg)
+    o.upload(sc)
+    o.set_ranges(*sc.ranges)
+    for i in sc.img_ids:
+        o.add_image_matches(int(i), *sc.flat_matches(int(i)))
+    ot = o.build_tracks()
+    assert len(linetracks) == len(ot["track_off"]) - 1
+    got = {frozenset(zip(t.image_id_list, t.line_id_list)) for t in linetracks}
+    exp = {frozenset(zip(ot["img_ids"][a:b].tolist(), ot["line_ids"][a:b].tolist()))
+           for a, b in zip(ot["track_off"][:-1], ot["track_off"][1:])}
+    assert got == exp
+    t0 = linetracks[0]
+    assert len(t0.line2d_list) == len(t0.line3d_list) == len(t0.score_list) == t0.count_lines()
+    assert isinstance(t0.line2d_list[0], base.Line2d) and isinstance(t0.line, base.Line3d)
+    # [E] refinement exactly as the runner calls it
+    cfg_ref = dict(constant_intrinsics=True, constant_principal_point=True, constant_pose=True, constant_line=False,
+                   min_num_images=4, num_outliers_aggregator=2, use_geometric=True, geometric_alpha=10.0)
+    ba_engine = optimize.solve_line_bundle_adjustment(cfg_ref, imagecols, linetracks, max_num_iterations=200)
+    out = ba_engine.GetOutputLineTracks(num_outliers=2)
+    assert sorted(out) == list(range(len(linetracks)))
+    # oracle refinement on the same tracks
+    from limap_b200.optimize import _tracks_to_arrays
+    from limap_b200.synth import TrackSet
+    view_of = {int(i): v for v, i in enumerate(sc.img_ids)}
+    sup_off, sup_view, segs, l3d, init = _tracks_to_arrays(linetracks, view_of)
+    ts = TrackSet(sup_off=sup_off, segs=segs, kvec=sc.kvec[sup_view], qvec=sc.qvec[sup_view], tvec=sc.tvec[sup_view],
+                  img_ids=sup_view.astype(np.int32), line3d=l3d, line_init=init, gt=init)
+    ref = orc.refine_tracks(ts, max_num_iterations=200, min_num_images=4, num_outliers=2)
+    lines = np.array([np.concatenate([out[k].line.start, out[k].line.end]) for k in range(len(linetracks))])
+    d = np.minimum(np.abs(lines - ref["line"]).max(1), np.abs(lines - ref["line"][:, [3, 4, 5, 0, 1, 2]]).max(1))
+    assert d.max() <= 1e-4
+    moved = np.abs(lines - init).max(1) > 1e-9
+    n_img = np.array([t.count_images() for t in linetracks])
+    assert moved[n_img >= 4].mean() > 0.9
+
+
+def test_triangulate_image_index_error_and_model_check():
+    import limap.base as base
+    import limap.triangulation as triangulation
+    sc = make_scene(V=4, L=20, N=2, K=2, seed=42)
+    imagecols = _imagecols(sc)
+    tri = triangulation.GlobalLineTriangulator(dict(DEFAULT_YAML_TRIANGULATION))
+    tri.Init(base.get_all_lines_2d({int(i): sc.lines_of(v) for v, i in enumerate(sc.img_ids)}), imagecols)
+    bad = {k: v.copy() for k, v in sc.matches[0].items()}
+    next(iter(bad.values()))[0, 0] = 999
+    with pytest.raises(RuntimeError, match="IndexError"):
+        tri.TriangulateImage(0, bad)
+    with pytest.raises(RuntimeError):
+        base.Camera("OPENCV", [1, 1, 0, 0, 0, 0, 0, 0], 0, (10, 10))
