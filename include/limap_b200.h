@@ -193,6 +193,26 @@ int lm_ba_solve(lm_ctx *ctx, int32_t n_views, const double *kvec, const double *
                 double *out_minimal, int32_t *out_iters, double *out_cost);
 int lm_ba_get_stats(lm_ctx *ctx, lm_ba_stats *out);
 
+/* ---- vanishing points: JLinkage::AssociateVPs for a batch of images
+ * (vplib/JLinkage/JLinkage.cc:14-127; Python glue vplib/base_vp_detector.py:46-78 fans images out with
+ * joblib, here all images go to the GPU in one call). The clustering arithmetic of the reference lives in
+ * an external library with an unseeded RNG (B1ueber2y/JLinkage@75dadd5); it is restated with a counter-based
+ * RNG (`seed`), see DESIGN.md. config: BaseVPDetectorConfig (vplib/base_vp_detector.h:20-35); NB the
+ * reference reads th_perp_supports from the shadowed base-class config, i.e. always 3.0. */
+typedef struct lm_vp_config {
+  double min_length;        /* 40 px */
+  double inlier_threshold;  /* 1 px */
+  double th_perp_supports;  /* 3 px */
+  int32_t min_num_supports; /* 5 (yaml: 10) */
+  int32_t n_models;         /* 5000 */
+  uint64_t seed;
+} lm_vp_config;
+/* line_off[n_images+1], segs[sum L][4]. Outputs: labels[sum L] (-1 = no VP), vp_off[n_images+1],
+ * vps[vp_cap][3] (homogeneous, unit norm). Returns the total number of VPs (call again with a larger vp_cap
+ * if it exceeds vp_cap) or <0. */
+int64_t lm_vp_detect(lm_ctx *ctx, int32_t n_images, const int64_t *line_off, const double *segs,
+                     const lm_vp_config *cfg, int32_t *labels, int64_t *vp_off, double *vps, int64_t vp_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,11 @@ class BAConfig(C.Structure):
                 ("num_outliers", C.c_int32), ("max_num_consecutive_invalid_steps", C.c_int32)]
 
 
+class VPConfig(C.Structure):
+    _fields_ = [("min_length", C.c_double), ("inlier_threshold", C.c_double), ("th_perp_supports", C.c_double),
+                ("min_num_supports", C.c_int32), ("n_models", C.c_int32), ("seed", C.c_uint64)]
+
+
 class BAStats(C.Structure):
     _fields_ = [("n_tracks", C.c_int64), ("n_blocks", C.c_int64), ("total_iterations", C.c_int64),
                 ("total_successful", C.c_int64), ("solve_ms", C.c_double), ("prepare_ms", C.c_double)]
@@ -71,6 +76,7 @@ _SIGS = {
     "lm_tri_get_tracks": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "lm_ba_solve": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lm_ba_get_stats": (C.c_int, [_P, _P]),
+    "lm_vp_detect": (C.c_int64, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

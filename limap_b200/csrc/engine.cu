@@ -12,7 +12,9 @@
 #include "../../include/limap_b200.h"
 #include "tri_kernels.cuh"
 #include "lm_kernels.cuh"
+#include "vp_kernels.cuh"
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
@@ -128,6 +130,10 @@ struct lm_ctx {
   lm_tri_config cfg;
   bool ranges_flag = false;
   double rlo[3] = {0, 0, 0}, rhi[3] = {0, 0, 0};
+  // InitVPResults
+  bool have_vps = false;
+  DevBuf d_vp_label, d_vp_voff, d_vp_vps;
+  int ns = 1; // proposal slots per match row of the last run (3 with VP proposals)
   // staged matches
   std::vector<MatchBlock> blocks;
   std::vector<char> image_added;
@@ -162,6 +168,7 @@ struct lm_ctx {
   bool edges_collected = false;
   // line BA
   DevBuf d_ba_in, d_ba_blocks, d_ba_out;
+  DevBuf d_vp_pts, d_vp_off, d_vp_labels, d_vp_nc, d_vp_ps, d_vp_mat;
   lm_ba_stats ba_stats;
   // tracks
   std::vector<Track> tracks;
@@ -188,15 +195,15 @@ int fetch_rows(lm_ctx *c) {
   if (c->h_rows_valid) return LM_OK;
   c->h_node_row_off.resize(c->n_nodes + 1);
   c->h_row_ng.resize(c->n_rows);
-  c->h_row_state.resize(c->n_rows);
+  c->h_row_state.resize(c->n_rows * c->ns);
   CU(cudaMemcpyAsync(c->h_node_row_off.data(), c->d_node_row_off.p, 4 * (c->n_nodes + 1), cudaMemcpyDeviceToHost,
                      c->stream));
   if (c->n_rows) {
     CU(cudaMemcpyAsync(c->h_row_ng.data(), c->sorted_val, 4 * c->n_rows, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(c->h_row_state.data(), c->d_row_state.p, c->n_rows, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_row_state.data(), c->d_row_state.p, c->n_rows * c->ns, cudaMemcpyDeviceToHost, c->stream));
     if (c->cfg.debug_mode) {
-      c->h_row_cand.resize(c->n_rows * 10);
-      CU(cudaMemcpyAsync(c->h_row_cand.data(), c->d_row_cand.p, 80 * c->n_rows, cudaMemcpyDeviceToHost, c->stream));
+      c->h_row_cand.resize(c->n_rows * c->ns * 10);
+      CU(cudaMemcpyAsync(c->h_row_cand.data(), c->d_row_cand.p, 80 * c->n_rows * c->ns, cudaMemcpyDeviceToHost, c->stream));
     }
   }
   CU(cudaStreamSynchronize(c->stream));
@@ -265,7 +272,7 @@ void lm_ctx_destroy(lm_ctx *c) {
                     &c->d_blk_src, &c->d_blk_ng, &c->d_blk_pair_off, &c->d_key, &c->d_key2, &c->d_val, &c->d_val2,
                     &c->d_sort_tmp, &c->d_node_row_off, &c->d_scalars, &c->d_nodes, &c->d_row_state, &c->d_row_cand,
                     &c->d_slab, &c->d_edges, &c->d_edges2, &c->d_edge_keys, &c->d_edge_keys2, &c->d_edge_w,
-                    &c->d_edge_cnt, &c->d_nvalid, &c->d_edge_off, &c->d_edge_ng, &c->d_ba_in, &c->d_ba_blocks, &c->d_ba_out};
+                    &c->d_edge_cnt, &c->d_nvalid, &c->d_edge_off, &c->d_edge_ng, &c->d_ba_in, &c->d_ba_blocks, &c->d_ba_out, &c->d_vp_label, &c->d_vp_voff, &c->d_vp_vps, &c->d_vp_pts, &c->d_vp_off, &c->d_vp_labels, &c->d_vp_nc, &c->d_vp_ps, &c->d_vp_mat};
   for (DevBuf *b : bufs) b->release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -365,8 +372,6 @@ int lm_tri_configure(lm_ctx *c, const lm_tri_config *cfg) {
   if (!c || !cfg) return fail(LM_ERR_INVALID, "NULL argument");
   if (cfg->merging_strategy != 0)
     return fail(LM_ERR_INVALID, "Error!The given merging strategy is not implemented"); // global_line_triangulator.cc:318
-  if (cfg->use_vp && !cfg->disable_vp_triangulation)
-    return fail(LM_ERR_INVALID, "use_vp triangulation proposals are not built yet (SURVEY §8 a5)");
   const bool halfpix_changed = !c->have_cfg || (c->cfg.add_halfpix != cfg->add_halfpix);
   c->cfg = *cfg;
   c->have_cfg = true;
@@ -387,9 +392,44 @@ int lm_tri_unset_ranges(lm_ctx *c) {
   c->ran = false;
   return LM_OK;
 }
-int lm_tri_set_vps(lm_ctx *, int32_t, const int32_t *, const int64_t *, const int32_t *, const int64_t *,
-                   const double *) {
-  return fail(LM_ERR_INVALID, "VP proposals are not built yet (SURVEY §8 a5)");
+int lm_tri_set_vps(lm_ctx *c, int32_t n_images, const int32_t *img_ids, const int64_t *label_off, const int32_t *labels,
+                   const int64_t *vp_off, const double *vps) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  if (!c->have_scene) return fail(LM_ERR_STATE, "lm_scene_upload must precede InitVPResults");
+  CU(cudaSetDevice(c->device));
+  std::vector<int32_t> lab(std::max<int64_t>(c->n_nodes, 1), -1);
+  std::vector<int64_t> voff(c->V + 1, 0);
+  std::vector<int64_t> cnt(c->V, 0);
+  std::vector<int> src(c->V, -1);
+  for (int i = 0; i < n_images; ++i) {
+    auto it = c->id2view.find(img_ids[i]);
+    if (it == c->id2view.end()) return fail(LM_ERR_INVALID, "unknown image id in InitVPResults");
+    const int v = it->second;
+    const int64_t nl = label_off[i + 1] - label_off[i];
+    if (nl != c->line_off[v + 1] - c->line_off[v]) return fail(LM_ERR_INVALID, "VPResult.labels size != number of lines");
+    cnt[v] = vp_off[i + 1] - vp_off[i];
+    src[v] = i;
+    for (int64_t l = 0; l < nl; ++l) {
+      const int32_t x = labels[label_off[i] + l];
+      if (x >= cnt[v]) return fail(LM_ERR_INVALID, "VP label out of range");
+      lab[c->line_off[v] + l] = x;
+    }
+  }
+  for (int v = 0; v < c->V; ++v) voff[v + 1] = voff[v] + cnt[v];
+  std::vector<double> vv(3 * std::max<int64_t>(voff[c->V], 1), 0.0);
+  for (int v = 0; v < c->V; ++v)
+    if (src[v] >= 0)
+      memcpy(&vv[3 * voff[v]], vps + 3 * vp_off[src[v]], 24 * cnt[v]);
+  CU(c->d_vp_label.ensure(4 * lab.size()));
+  CU(c->d_vp_voff.ensure(8 * voff.size()));
+  CU(c->d_vp_vps.ensure(8 * vv.size()));
+  CU(cudaMemcpyAsync(c->d_vp_label.p, lab.data(), 4 * lab.size(), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_vp_voff.p, voff.data(), 8 * voff.size(), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_vp_vps.p, vv.data(), 8 * vv.size(), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->have_vps = true;
+  c->ran = false;
+  return LM_OK;
 }
 
 int lm_tri_clear(lm_ctx *c) {
@@ -539,8 +579,10 @@ int lm_tri_run(lm_ctx *c) {
   CU(c->d_node_row_off.ensure(4 * (c->n_nodes + 2)));
   CU(c->d_scalars.ensure(64));
   CU(c->d_nodes.ensure(sizeof(lm::NodeRecord) * std::max<int64_t>(c->n_nodes, 1)));
-  CU(c->d_row_state.ensure(std::max<int64_t>(n_rows, 1)));
-  if (c->cfg.debug_mode) CU(c->d_row_cand.ensure(80 * std::max<int64_t>(n_rows, 1)));
+  const int ns = (c->cfg.use_vp && !c->cfg.disable_vp_triangulation && c->have_vps) ? 3 : 1;
+  c->ns = ns;
+  CU(c->d_row_state.ensure(std::max<int64_t>(n_rows * ns, 1)));
+  if (c->cfg.debug_mode) CU(c->d_row_cand.ensure(80 * std::max<int64_t>(n_rows * ns, 1)));
 
   CU(cudaEventRecord(c->ev0, s));
   CU(cudaMemsetAsync(c->d_scalars.p, 0, 64, s));
@@ -613,7 +655,8 @@ int lm_tri_run(lm_ctx *c) {
   p.IoU_threshold = g.IoU_threshold; p.sensitivity_threshold = g.sensitivity_threshold; p.var2d = g.var2d;
   p.fullscore_th = g.fullscore_th; p.max_valid_conns = g.max_valid_conns;
   p.use_endpoints_triangulation = g.use_endpoints_triangulation; p.disable_algebraic = g.disable_algebraic_triangulation;
-  p.use_vp = g.use_vp; p.disable_vp = g.disable_vp_triangulation;
+  p.use_vp = (ns == 3); p.disable_vp = g.disable_vp_triangulation;
+  p.vp_label = c->d_vp_label.as<int32_t>(); p.vp_off = c->d_vp_voff.as<int64_t>(); p.vps = c->d_vp_vps.as<double>();
   p.ranges_flag = c->ranges_flag;
   for (int i = 0; i < 3; ++i) { p.rlo[i] = c->rlo[i]; p.rhi[i] = c->rhi[i]; }
   p.l2d = to_dev<double>(g.linker2d);
@@ -643,9 +686,9 @@ int lm_tri_run(lm_ctx *c) {
     }
     p.bucket_scale = (float)(p.n_buckets / kPi);
   }
-  if (max_rows > 65535) return fail(LM_ERR_INVALID, "more than 65535 match rows for one 2D line");
+  if ((int64_t)max_rows * ns > 65535) return fail(LM_ERR_INVALID, "more than 65535 candidates possible for one 2D line");
   int cap = 32;
-  while (cap < max_rows) cap += 32;
+  while (cap < max_rows * ns) cap += 32;
   size_t smem = lm::tri_smem_bytes(cap);
   const int64_t n_shard_nodes = c->node_end - c->node_begin;
   int grid;
@@ -674,7 +717,7 @@ int lm_tri_run(lm_ctx *c) {
   if (n_shard_nodes > 0) {
     CU(c->d_nvalid.ensure(4 * (n_shard_nodes + 1)));
     CU(c->d_edge_off.ensure(4 * (n_shard_nodes + 1)));
-    CU(c->d_edge_ng.ensure(4 * std::max<int64_t>(n_rows, 1)));
+    CU(c->d_edge_ng.ensure(4 * std::max<int64_t>(n_rows * ns, 1)));
     lm::launch_extract_nvalid(p.nodes, c->node_begin, n_shard_nodes, c->d_nvalid.as<uint32_t>(), s);
     size_t tmp = 0;
     CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_nvalid.as<uint32_t>(), c->d_edge_off.as<uint32_t>(),
@@ -683,7 +726,7 @@ int lm_tri_run(lm_ctx *c) {
     CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp, c->d_nvalid.as<uint32_t>(), c->d_edge_off.as<uint32_t>(),
                                      (int)(n_shard_nodes + 1), s));
     lm::launch_compact_edges_only(p.row_state, p.row_ng, p.node_row_off, c->d_edge_off.as<uint32_t>(), c->node_begin,
-                                  n_shard_nodes, c->d_edge_ng.as<uint32_t>(), s);
+                                  n_shard_nodes, ns, c->d_edge_ng.as<uint32_t>(), s);
     launches += 4;
   }
   CU(cudaGetLastError());
@@ -771,10 +814,11 @@ int lm_tri_get_cands_node(lm_ctx *c, int32_t img_id, int32_t line_id, int32_t ca
   const int64_t n = c->line_off[it->second] + line_id;
   if (line_id < 0 || n >= c->line_off[it->second + 1]) return fail(LM_ERR_INVALID, "line id out of range");
   int k = 0;
-  for (uint32_t r = c->h_node_row_off[n]; r < c->h_node_row_off[n + 1]; ++r) {
-    if (c->h_row_state[r] == 0) continue;
+  for (int64_t q = (int64_t)c->h_node_row_off[n] * c->ns; q < (int64_t)c->h_node_row_off[n + 1] * c->ns; ++q) {
+    if (c->h_row_state[q] == 0) continue;
+    const uint32_t r = (uint32_t)(q / c->ns);
     if (k < cap) {
-      for (int q = 0; q < 10; ++q) out_line[10 * k + q] = c->h_row_cand[(size_t)r * 10 + q];
+      for (int t = 0; t < 10; ++t) out_line[10 * k + t] = c->h_row_cand[(size_t)q * 10 + t];
       out_ng[2 * k] = c->img_ids[c->h_row_ng[r] >> 16];
       out_ng[2 * k + 1] = (int32_t)(c->h_row_ng[r] & 0xffffu);
     }
@@ -1327,6 +1371,177 @@ int lm_ba_get_stats(lm_ctx *c, lm_ba_stats *out) {
   if (!c || !out) return fail(LM_ERR_INVALID, "NULL argument");
   *out = c->ba_stats;
   return LM_OK;
+}
+
+} // extern "C"
+
+// ---- vanishing points ----------------------------------------------------------------------------
+namespace {
+
+struct L2h { double x1, y1, x2, y2; };
+inline double len_h(const L2h &l) { return std::sqrt((l.x1 - l.x2) * (l.x1 - l.x2) + (l.y1 - l.y2) * (l.y1 - l.y2)); }
+// Line2d::coords (base/linebase.cc:35-39)
+inline void coords_h(const L2h &l, double c[3]) {
+  c[0] = l.y1 - l.y2; c[1] = l.x2 - l.x1; c[2] = l.x1 * l.y2 - l.x2 * l.y1;
+  const double n2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+  if (n2 > 0) { const double n = std::sqrt(n2); c[0] /= n; c[1] /= n; c[2] /= n; }
+}
+// BaseVPDetector::count_valid_supports_2d (vplib/base_vp_detector.cc:41-73)
+int count_valid_supports_2d_h(const std::vector<L2h> &lines, double th_perp) {
+  const size_t n = lines.size();
+  std::vector<int> parent(n, -1);
+  auto root = [&](size_t i) { while (parent[i] != -1) i = parent[i]; return i; };
+  auto dist = [&](const L2h &l, double qx, double qy) {
+    double c[3];
+    coords_h(l, c);
+    return std::fabs(c[0] * qx + c[1] * qy + c[2]) / std::sqrt(c[0] * c[0] + c[1] * c[1]);
+  };
+  for (size_t i = 0; i + 1 < n; ++i) {
+    const size_t ri = root(i);
+    for (size_t j = i + 1; j < n; ++j) {
+      const size_t rj = root(j);
+      if (rj == ri) continue;
+      size_t k1 = i, k2 = j;
+      if (len_h(lines[i]) > len_h(lines[j])) { k1 = j; k2 = i; }
+      const double ds = dist(lines[k2], lines[k1].x1, lines[k1].y1), de = dist(lines[k2], lines[k1].x2, lines[k1].y2);
+      if (((ds < de) ? de : ds) > th_perp) continue;
+      parent[rj] = (int)ri;
+    }
+  }
+  int cnt = 0;
+  for (size_t i = 0; i < n; ++i) cnt += parent[i] == -1;
+  return cnt;
+}
+// JLinkage::fitVP (JLinkage.cc:86-100): right singular vector of the smallest singular value
+void smallest_eigvec(const double Ain[3][3], double out[3]) {
+  double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  memcpy(A, Ain, sizeof(A));
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+    double diag = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+    if (off == 0 || off <= 1e-32 * diag) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (A[p][q] == 0) continue;
+        double theta = (A[q][q] - A[p][p]) / (2 * A[p][q]);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+        double cs = 1 / std::sqrt(t * t + 1), sn = t * cs;
+        for (int k = 0; k < 3; ++k) { double a = A[k][p], b = A[k][q]; A[k][p] = cs * a - sn * b; A[k][q] = sn * a + cs * b; }
+        for (int k = 0; k < 3; ++k) { double a = A[p][k], b = A[q][k]; A[p][k] = cs * a - sn * b; A[q][k] = sn * a + cs * b; }
+        for (int k = 0; k < 3; ++k) { double a = V[k][p], b = V[k][q]; V[k][p] = cs * a - sn * b; V[k][q] = sn * a + cs * b; }
+      }
+  }
+  int best = 0;
+  if (A[1][1] < A[best][best]) best = 1;
+  if (A[2][2] < A[best][best]) best = 2;
+  double n = std::sqrt(V[0][best] * V[0][best] + V[1][best] * V[1][best] + V[2][best] * V[2][best]);
+  for (int k = 0; k < 3; ++k) out[k] = V[k][best] / n;
+}
+
+} // namespace
+
+extern "C" {
+
+int64_t lm_vp_detect(lm_ctx *c, int32_t n_images, const int64_t *line_off, const double *segs, const lm_vp_config *cfg,
+                     int32_t *labels, int64_t *vp_off, double *vps, int64_t vp_cap) {
+  if (!c || !cfg || !line_off || !labels || !vp_off) return fail(LM_ERR_INVALID, "NULL argument");
+  if (n_images < 0) return fail(LM_ERR_INVALID, "bad sizes");
+  if (cfg->n_models <= 0 || cfg->n_models > 65535) return fail(LM_ERR_INVALID, "n_models must be in [1, 65535]");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  // ComputeVPLabels :17-36: segments of at least min_length px, cast to float
+  std::vector<float> pts;
+  std::vector<int64_t> valid_off(n_images + 1, 0);
+  std::vector<int32_t> valid_ids;
+  int max_n = 0;
+  for (int im = 0; im < n_images; ++im) {
+    for (int64_t l = line_off[im]; l < line_off[im + 1]; ++l) {
+      const double *g = segs + 4 * l;
+      const double len = std::sqrt((g[0] - g[2]) * (g[0] - g[2]) + (g[1] - g[3]) * (g[1] - g[3]));
+      if (len < cfg->min_length) continue;
+      valid_ids.push_back((int32_t)(l - line_off[im]));
+      for (int k = 0; k < 4; ++k) pts.push_back((float)g[k]);
+    }
+    valid_off[im + 1] = (int64_t)valid_ids.size();
+    max_n = std::max(max_n, (int)(valid_off[im + 1] - valid_off[im]));
+  }
+  if (max_n > 8192) return fail(LM_ERR_INVALID, "more than 8192 segments of min_length in one image");
+  const int64_t nv = (int64_t)valid_ids.size();
+  std::vector<int32_t> raw(std::max<int64_t>(nv, 1), -1), ncl(std::max(n_images, 1), 0);
+  const int min_lines = 2 * std::max(cfg->min_num_supports, 10);
+  if (nv > 0 && max_n >= min_lines) {
+    const int W = (cfg->n_models + 31) / 32;
+    int grid = std::min(n_images, c->sm_count * 2);
+    CU(c->d_vp_pts.ensure(16 * nv));
+    CU(c->d_vp_off.ensure(8 * (n_images + 1)));
+    CU(c->d_vp_labels.ensure(4 * nv));
+    CU(c->d_vp_nc.ensure(4 * n_images));
+    CU(c->d_vp_ps.ensure((size_t)grid * max_n * W * 4));
+    CU(c->d_vp_mat.ensure((size_t)grid * max_n * max_n * 4));
+    CU(cudaMemcpyAsync(c->d_vp_pts.p, pts.data(), 16 * nv, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->d_vp_off.p, valid_off.data(), 8 * (n_images + 1), cudaMemcpyHostToDevice, s));
+    lm::VPParams p;
+    p.pts = c->d_vp_pts.as<float4>();
+    p.valid_off = c->d_vp_off.as<int64_t>();
+    p.labels = c->d_vp_labels.as<int32_t>();
+    p.n_clusters = c->d_vp_nc.as<int32_t>();
+    p.ps_slab = c->d_vp_ps.as<uint32_t>();
+    p.mat_slab = c->d_vp_mat.as<uint32_t>();
+    p.n_images = n_images; p.n_models = cfg->n_models; p.max_n = max_n; p.min_lines = min_lines;
+    p.inlier_threshold = (float)cfg->inlier_threshold;
+    p.seed = cfg->seed;
+    if (lm::vp_smem_bytes(p.n_models, p.max_n) > (size_t)c->max_smem_optin)
+      return fail(LM_ERR_INVALID, "n_models too large for shared memory");
+    lm::launch_jlinkage(p, grid, s);
+    CU(cudaGetLastError());
+    c->stats.n_kernel_launches += 1;
+    CU(cudaMemcpyAsync(raw.data(), c->d_vp_labels.p, 4 * nv, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(ncl.data(), c->d_vp_nc.p, 4 * n_images, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  // JLinkage.cc:56-83 (cluster filtering) and AssociateVPs :102-127 (VP fitting), per image on the host
+  int64_t n_vps = 0;
+  for (int im = 0; im < n_images; ++im) {
+    vp_off[im] = n_vps;
+    const int64_t L = line_off[im + 1] - line_off[im];
+    int32_t *lab = labels + line_off[im];
+    for (int64_t l = 0; l < L; ++l) lab[l] = -1;
+    const int64_t v0 = valid_off[im], v1 = valid_off[im + 1];
+    const int nc = ncl[im];
+    if (nc <= 0 || v1 - v0 < min_lines) continue;
+    std::vector<std::vector<L2h>> sup(nc);
+    for (int64_t k = v0; k < v1; ++k) {
+      if (raw[k] < 0) continue;
+      const double *g = segs + 4 * (line_off[im] + valid_ids[k]);
+      sup[raw[k]].push_back(L2h{g[0], g[1], g[2], g[3]});
+    }
+    std::vector<int> vp_ids(nc, -1);
+    int counter = 0;
+    for (int q = 0; q < nc; ++q) {
+      if ((int)sup[q].size() < cfg->min_num_supports) continue;
+      if (count_valid_supports_2d_h(sup[q], cfg->th_perp_supports) < cfg->min_num_supports) continue;
+      vp_ids[q] = counter++;
+    }
+    std::vector<std::array<double, 9>> S(counter, std::array<double, 9>{});
+    for (int64_t k = v0; k < v1; ++k) {
+      if (raw[k] < 0 || vp_ids[raw[k]] < 0) continue;
+      const int v = vp_ids[raw[k]];
+      lab[valid_ids[k]] = v;
+      const double *g = segs + 4 * (line_off[im] + valid_ids[k]);
+      double cc[3];
+      coords_h(L2h{g[0], g[1], g[2], g[3]}, cc);
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) S[v][3 * a + b] += cc[a] * cc[b];
+    }
+    for (int v = 0; v < counter; ++v) {
+      double A[3][3], e[3];
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) A[a][b] = S[v][3 * a + b];
+      smallest_eigvec(A, e);
+      if (vps && n_vps < vp_cap) { vps[3 * n_vps] = e[0]; vps[3 * n_vps + 1] = e[1]; vps[3 * n_vps + 2] = e[2]; }
+      ++n_vps;
+    }
+  }
+  vp_off[n_images] = n_vps;
+  return n_vps;
 }
 
 } // extern "C"

@@ -102,6 +102,7 @@ struct Src {
   vec3<double> ray1s, ray1e; // normalised
   vec3<double> C1;
   vec3<double> pu, pv;       // orthonormal basis of the back-projection plane of l1
+  vec3<double> n1;           // getNormalDirection(l1, view1) (only for VP proposals)
   bool ok;
 };
 
@@ -241,6 +242,48 @@ LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const Src &src, uin
   return true;
 }
 
+// triangulate_line_with_direction (triangulation/functions.cc:389-446) for a VP proposal
+// (base_line_triangulator.cc:258-288): fp64, formulas as in the reference (this path is off by default).
+// `direction` is the unit world direction of the VP seen from view 1.
+LM_D bool gen_vp_candidate(const TriParams &p, const ViewD &v1, const ViewD &v2, const Src &src, vec3<double> c2s,
+                           vec3<double> c2e, vec3<double> direction, Cand &c) {
+  const double EPS = consts<double>::eps();
+  const vec3<double> n1 = src.n1;
+  vec3<double> direc = direction - n1 * dot(n1, direction);
+  if (norm(direc) < EPS) return false;
+  direc = normalized(direc);
+  const vec3<double> perp = cross(n1, direc);
+  double a1s = dot(src.ray1s, perp), a1e = dot(src.ray1e, perp);
+  if (a1s < 0) { a1s *= -1; a1e *= -1; }
+  if (a1s < 0.001 || a1e < 0.001) return false; // MIN_VALUE
+  const vec3<double> C2 = mk3(v2.C[0], v2.C[1], v2.C[2]);
+  const vec3<double> n2 = normalized(cross(c2s, c2e));
+  const double c1s = dot(n2, src.ray1s), c1e = dot(n2, src.ray1e), b = dot(n2, C2 - src.C1);
+  const double c1 = c1s, c2 = c1e * a1s / a1e;
+  const double d1s = (c1 + c2) * b / (c1 * c1 + c2 * c2);
+  const double d1e = d1s * a1s / a1e;
+  const vec3<double> Xs = src.ray1s * d1s + src.C1, Xe = src.ray1e * d1e + src.C1;
+  c.zs = v1.P[8] * Xs.x + v1.P[9] * Xs.y + v1.P[10] * Xs.z + v1.P[11];
+  c.ze = v1.P[8] * Xe.x + v1.P[9] * Xe.y + v1.P[10] * Xe.z + v1.P[11];
+  if (c.zs < EPS || c.ze < EPS) return false;
+  const double z2s = v2.P[8] * Xs.x + v2.P[9] * Xs.y + v2.P[10] * Xs.z + v2.P[11];
+  const double z2e = v2.P[8] * Xe.x + v2.P[9] * Xe.y + v2.P[10] * Xe.z + v2.P[11];
+  if (z2s < EPS || z2e < EPS) return false;
+  if (isnan(Xs.x) || isnan(Xe.x)) return false;
+  const double u1 = p.var2d * ((c.zs + c.ze) / 2.0) / v1.fbar;
+  const double u2 = p.var2d * ((z2s + z2e) / 2.0) / v2.fbar;
+  c.unc = smin(u1, u2);
+  if (p.ranges_flag) {
+    if (Xs.x < p.rlo[0] || Xs.x > p.rhi[0] || Xs.y < p.rlo[1] || Xs.y > p.rhi[1] || Xs.z < p.rlo[2] || Xs.z > p.rhi[2])
+      return false;
+    if (Xe.x < p.rlo[0] || Xe.x > p.rhi[0] || Xe.y < p.rlo[1] || Xe.y > p.rhi[1] || Xe.z < p.rlo[2] || Xe.z > p.rhi[2])
+      return false;
+  }
+  c.s = Xs;
+  c.e = Xe;
+  return true;
+}
+
 // Pair score of candidates (i, j) of one node (global_line_triangulator.cc:91-104):
 // min(LineLinker3d::compute_score(l_i, l_j), LineLinker2d::compute_score(proj_{view j}(l_i), seg_j)),
 // 0 when either is 0.
@@ -330,8 +373,9 @@ LM_D bool gate2d(const TriParams &p, const seg<vec3<double>> &Li, const Slab &sl
   return true;
 }
 
-template <bool SLAB>
+template <bool SLAB, bool VP>
 __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(const __grid_constant__ TriParams p) {
+  constexpr int NS = VP ? 3 : 1; // proposal slots per match row: [vp1, vp2, algebraic] (base_line_triangulator.cc:258-326)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_wtot[kWarps];
   __shared__ int s_nvalid;
@@ -369,21 +413,56 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
       src.C1 = mk3(v1.C[0], v1.C[1], v1.C[2]);
       src.pu = src.ray1s;
       src.pv = normalized(src.ray1e - src.ray1s * dot(src.ray1e, src.ray1s));
+      src.n1 = normalized(cross(src.w1s, src.w1e));
     }
     int count = 0;
     for (int base = 0; base < nrows; base += kThreads) {
       const int r = base + tid;
-      bool ok = false;
-      Cand c;
-      double4 l2;
+      Cand cs[NS];
+      bool oks[NS];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) oks[k] = false;
+      double4 l2 = make_double4(0, 0, 0, 0);
       uint32_t ng = 0;
       if (r < nrows && src.ok) {
         ng = __ldg(&p.row_ng[r0 + r]);
-        ok = gen_candidate(p, v1, src, ng >> 16, ng & 0xffffu, c, l2);
+        const uint32_t ngv = ng >> 16, ngl = ng & 0xffffu;
+        if (VP) {
+          // Step 2 (:258-288): proposals from the VP of the source line and of the matched line; both use view 1
+          const double4 l2v = ld_seg(&p.segs[p.line_off[ngv] + ngl]);
+          const double ddx = l2v.x - l2v.z, ddy = l2v.y - l2v.w;
+          if (!(sqrt(ddx * ddx + ddy * ddy) <= p.min_length_2d) && !p.disable_vp) {
+            const ViewD &v2 = p.views[ngv];
+            const vec3<double> c2s = mat3_mul_h(v2.M, l2v.x, l2v.y), c2e = mat3_mul_h(v2.M, l2v.z, l2v.w);
+            const int lab1 = p.vp_label[node];
+            if (lab1 >= 0) {
+              const double *vp = p.vps + 3 * (p.vp_off[v1i] + lab1);
+              oks[0] = gen_vp_candidate(p, v1, v2, src, c2s, c2e, normalized(mat3_mul(v1.M, mk3(vp[0], vp[1], vp[2]))), cs[0]);
+            }
+            const int lab2 = p.vp_label[p.line_off[ngv] + ngl];
+            if (lab2 >= 0) {
+              const double *vp = p.vps + 3 * (p.vp_off[ngv] + lab2);
+              oks[1] = gen_vp_candidate(p, v1, v2, src, c2s, c2e, normalized(mat3_mul(v1.M, mk3(vp[0], vp[1], vp[2]))), cs[1]);
+            }
+          }
+          l2 = l2v;
+        }
+        oks[NS - 1] = gen_candidate(p, v1, src, ngv, ngl, cs[NS - 1], l2);
       }
-      if (r < nrows && !ok) p.row_state[r0 + r] = 0;
-      const unsigned bal = __ballot_sync(0xffffffffu, ok);
-      if (lane == 0) s_wtot[warp] = __popc(bal);
+      int cnt = 0;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        if (r < nrows) p.row_state[(int64_t)(r0 + r) * NS + k] = 0;
+        cnt += oks[k];
+      }
+      // stable compaction: exclusive prefix of the per-row candidate counts
+      int incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      if (lane == 31) s_wtot[warp] = incl;
       __syncthreads();
       int woff = 0, tot = 0;
 #pragma unroll
@@ -391,8 +470,11 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         if (w < warp) woff += s_wtot[w];
         tot += s_wtot[w];
       }
-      if (ok) {
-        const int idx = count + woff + __popc(bal & lt_mask);
+      int idx = count + woff + incl - cnt;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        if (!oks[k]) continue;
+        const Cand &c = cs[k];
         const vec3<double> d = normalized(c.e - c.s);
         sl.sx[idx] = c.s.x; sl.sy[idx] = c.s.y; sl.sz[idx] = c.s.z;
         sl.ex[idx] = c.e.x; sl.ey[idx] = c.e.y; sl.ez[idx] = c.e.z;
@@ -400,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         sl.zs[idx] = c.zs; sl.ze[idx] = c.ze; sl.unc[idx] = c.unc;
         sl.q0[idx] = l2.x; sl.q1[idx] = l2.y; sl.q2[idx] = l2.z; sl.q3[idx] = l2.w;
         sl.ng[idx] = ng;
-        sl.row[idx] = (uint32_t)r;
+        sl.row[idx] = (uint32_t)r * NS + k;
         // fp32 gate copy, relative to the source camera centre (keeps |coord| ~ depth)
         const vec3<double> rs = c.s - src.C1, re = c.e - src.C1;
         // scale-invariance limit th * (z + EPS) widened by 0.5% plus 1e-5 of the coordinate magnitude
@@ -411,27 +493,25 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         GateRec g;
         g.dx = (float)d.x; g.dy = (float)d.y; g.dz = (float)d.z; g.lims2 = (float)(ls * ls * 1.000001);
         g.sx = (float)rs.x; g.sy = (float)rs.y; g.sz = (float)rs.z; g.lime2 = (float)(le * le * 1.000001);
-        g.ex = (float)re.x; g.ey = (float)re.y; g.ez = (float)re.z; g.pad = 0.f;
-        sl.gate[idx] = g;
+        g.ex = (float)re.x; g.ey = (float)re.y; g.ez = (float)re.z;
         // direction bucket: every candidate of the node lies in the back-projection plane of l1, so its
         // direction is an angle phi in [0, pi) within that plane; the 3d angle test can only pass for
         // candidates whose buckets (width >= th_angle + margin) are equal or adjacent
-        uint32_t bucket = 0;
+        uint32_t bucket = 0, accept = 0xffffffffu;
         if (p.n_buckets > 1) {
           float phi = atan2f((float)dot(d, src.pv), (float)dot(d, src.pu));
           if (phi < 0.f) phi += 3.14159265358979f;
-          int b = (int)(phi * p.bucket_scale);
-          bucket = (uint32_t)min(max(b, 0), p.n_buckets - 1);
-        }
-        sl.meta[idx] = (ng & 0xffff0000u) | bucket;
-        {
-          uint32_t accept = 0xffffffffu; // own bucket and both neighbours (circular)
+          const int bb = (int)(phi * p.bucket_scale);
+          bucket = (uint32_t)min(max(bb, 0), p.n_buckets - 1);
           if (p.n_buckets > 3) {
             const int b = (int)bucket, nb = p.n_buckets;
             accept = (1u << b) | (1u << (b + 1 == nb ? 0 : b + 1)) | (1u << (b == 0 ? nb - 1 : b - 1));
           }
-          sl.gate[idx].pad = __uint_as_float(accept);
         }
+        g.pad = __uint_as_float(accept);
+        sl.gate[idx] = g;
+        sl.meta[idx] = (ng & 0xffff0000u) | bucket;
+        ++idx;
       }
       count += tot;
       __syncthreads();
@@ -580,10 +660,10 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         }
         valid = rank < p.max_valid_conns;
       }
-      p.row_state[r0 + sl.row[i]] = valid ? 2 : 1;
+      p.row_state[(int64_t)r0 * NS + sl.row[i]] = valid ? 2 : 1;
       nvalid_local += valid;
       if (p.row_cand) {
-        double *o = p.row_cand + (int64_t)(r0 + sl.row[i]) * 10;
+        double *o = p.row_cand + ((int64_t)r0 * NS + sl.row[i]) * 10;
         o[0] = sl.sx[i]; o[1] = sl.sy[i]; o[2] = sl.sz[i]; o[3] = sl.ex[i]; o[4] = sl.ey[i]; o[5] = sl.ez[i];
         o[6] = sl.zs[i]; o[7] = sl.ze[i]; o[8] = sl.unc[i]; o[9] = sc;
       }
@@ -633,18 +713,22 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
   }
 }
 
-void launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem, cudaStream_t s) {
-  (void)block;
+template <bool VP> static void launch_tri_vp(const TriParams &p, int grid, size_t smem, cudaStream_t s) {
   static size_t configured = 0;
   if (p.use_slab) {
-    tri_node_kernel<true><<<grid, kThreads, 0, s>>>(p);
+    tri_node_kernel<true, VP><<<grid, kThreads, 0, s>>>(p);
     return;
   }
   if (smem > configured) {
-    cudaFuncSetAttribute(tri_node_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(tri_node_kernel<false, VP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  tri_node_kernel<false><<<grid, kThreads, smem, s>>>(p);
+  tri_node_kernel<false, VP><<<grid, kThreads, smem, s>>>(p);
+}
+void launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem, cudaStream_t s) {
+  (void)block;
+  if (p.use_vp) launch_tri_vp<true>(p, grid, smem, s);
+  else launch_tri_vp<false>(p, grid, smem, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -751,18 +835,18 @@ __global__ void extract_nvalid_kernel(const NodeRecord *__restrict__ nodes, int6
 }
 __global__ void compact_edges_kernel(const uint8_t *__restrict__ row_state, const uint32_t *__restrict__ row_ng,
                                      const uint32_t *__restrict__ node_row_off, const uint32_t *__restrict__ edge_off,
-                                     int64_t node_begin, int64_t n, uint32_t *__restrict__ edge_ng) {
+                                     int64_t node_begin, int64_t n, int ns, uint32_t *__restrict__ edge_ng) {
   const int lane = threadIdx.x & 31;
   const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
   if (i >= n) return;
-  const uint32_t r0 = node_row_off[node_begin + i], r1 = node_row_off[node_begin + i + 1];
+  const int64_t q0 = (int64_t)node_row_off[node_begin + i] * ns, q1 = (int64_t)node_row_off[node_begin + i + 1] * ns;
   uint32_t base = edge_off[i];
   if (edge_off[i + 1] == base) return;
-  for (uint32_t rb = r0; rb < r1; rb += 32) {
-    const uint32_t r = rb + lane;
-    const bool v = (r < r1) && row_state[r] == 2;
+  for (int64_t qb = q0; qb < q1; qb += 32) { // q = row * ns + slot: candidate order
+    const int64_t q = qb + lane;
+    const bool v = (q < q1) && row_state[q] == 2;
     const unsigned m = __ballot_sync(0xffffffffu, v);
-    if (v) edge_ng[base + __popc(m & ((1u << lane) - 1u))] = row_ng[r];
+    if (v) edge_ng[base + __popc(m & ((1u << lane) - 1u))] = row_ng[q / ns];
     base += __popc(m);
   }
 }
@@ -791,11 +875,11 @@ void launch_extract_nvalid(const NodeRecord *nodes, int64_t node_begin, int64_t 
   extract_nvalid_kernel<<<(int)((n + 1 + 255) / 256), 256, 0, s>>>(nodes, node_begin, n, out);
 }
 void launch_compact_edges_only(const uint8_t *row_state, const uint32_t *row_ng, const uint32_t *node_row_off,
-                               const uint32_t *edge_off, int64_t node_begin, int64_t n, uint32_t *edge_ng,
+                               const uint32_t *edge_off, int64_t node_begin, int64_t n, int ns, uint32_t *edge_ng,
                                cudaStream_t s) {
   if (n <= 0) return;
   compact_edges_kernel<<<(int)((n * 32 + 255) / 256), 256, 0, s>>>(row_state, row_ng, node_row_off, edge_off,
-                                                                   node_begin, n, edge_ng);
+                                                                   node_begin, n, ns, edge_ng);
 }
 
 // run_clustering edge weight (global_line_triangulator.cc:263-288): LineLinker3d::compute_score of the

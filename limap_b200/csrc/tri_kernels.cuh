@@ -38,8 +38,8 @@ struct TriParams {
   const int64_t *vp_off;       // [V+1]
   const double *vps;           // [sum n_vp][3]
   NodeRecord *nodes;           // [nodes] out
-  uint8_t *row_state;          // [rows] out: 0 rejected, 1 candidate, 2 valid connection
-  double *row_cand;            // [rows][10] out (debug_mode only, else NULL)
+  uint8_t *row_state;          // [rows][ns] out: 0 rejected, 1 candidate, 2 valid connection (ns = 3 with VPs)
+  double *row_cand;            // [rows][ns][10] out (debug_mode only, else NULL)
   unsigned long long *counters; // [4] n_candidates, n_valid, pairs past the 3d gates, pairs scored exactly
   char *slab;                  // global scratch for nodes whose rows exceed the smem capacity (or NULL)
   int64_t slab_stride;         // bytes per CTA
@@ -85,7 +85,7 @@ void launch_node_offsets(const uint32_t *d_sorted_key, int64_t n_rows, int64_t n
                          unsigned int *d_max_rows, cudaStream_t s);
 void launch_extract_nvalid(const NodeRecord *nodes, int64_t node_begin, int64_t n, uint32_t *out, cudaStream_t s);
 void launch_compact_edges_only(const uint8_t *row_state, const uint32_t *row_ng, const uint32_t *node_row_off,
-                               const uint32_t *edge_off, int64_t node_begin, int64_t n, uint32_t *edge_ng,
+                               const uint32_t *edge_off, int64_t node_begin, int64_t n, int ns, uint32_t *edge_ng,
                                cudaStream_t s);
 void launch_edge_pairs(const uint32_t *edge_off, const uint32_t *edge_ng, const int64_t *line_off,
                        int64_t node_begin, int64_t n_nodes, int64_t n_edges, int64_t *out, cudaStream_t s);

@@ -125,6 +125,25 @@ class OracleTri:
     def set_ranges(self, lo, hi):
         lib().orc_tri_set_ranges(self._h, _p(_f64(lo)), _p(_f64(hi)))
 
+    def set_vps(self, vpresults, img_ids=None, line_off=None):
+        """InitVPResults: {img_id: object with .labels and .vps}."""
+        ids = [int(i) for i in self.img_ids if int(i) in vpresults]
+        label_off, vp_off, labels, vps = [0], [0], [], []
+        for i in ids:
+            r = vpresults[i]
+            lab = np.asarray(r.labels, np.int32).reshape(-1)
+            v = np.asarray(r.vps, np.float64).reshape(-1, 3)
+            labels.append(lab)
+            vps.append(v)
+            label_off.append(label_off[-1] + len(lab))
+            vp_off.append(vp_off[-1] + len(v))
+        labels = np.ascontiguousarray(np.concatenate(labels) if labels else np.zeros(0, np.int32))
+        vps = np.ascontiguousarray(np.concatenate(vps) if vps else np.zeros((0, 3)))
+        L = lib()
+        L.orc_tri_set_vps.argtypes = [_P, C.c_int, _P, _P, _P, _P, _P]
+        L.orc_tri_set_vps(self._h, len(ids), _p(np.asarray(ids, np.int32)), _p(np.asarray(label_off, np.int64)),
+                          _p(labels), _p(np.asarray(vp_off, np.int64)), _p(vps))
+
     def add_image_matches(self, img_id, ng_ids, row_off, pairs):
         ng_ids = np.ascontiguousarray(ng_ids, np.int32)
         row_off = np.ascontiguousarray(row_off, np.int64)
@@ -210,3 +229,27 @@ def refine_tracks(ts, max_num_iterations=100, min_num_images=4, num_outliers=2, 
          np.ascontiguousarray(ts.img_ids, np.int32), _f64(ts.line3d), _f64(ts.line_init)]
     L.orc_refine_tracks(T, *[_p(x) for x in a], C.byref(cfg), _p(out_line), _p(out_min), _p(iters), _p(cost))
     return dict(line=out_line, minimal=out_min, iters=iters, cost=cost)
+
+
+class VPCfg(C.Structure):
+    _fields_ = [("min_length", C.c_double), ("inlier_threshold", C.c_double), ("th_perp_supports", C.c_double),
+                ("min_num_supports", C.c_int32), ("n_models", C.c_int32), ("seed", C.c_uint64)]
+
+
+def detect_vps(line_off, segs, min_length=40.0, inlier_threshold=1.0, min_num_supports=5, th_perp_supports=3.0,
+               n_models=5000, seed=0, threads=None):
+    """CPU restatement of JLinkage::AssociateVPs over a batch of images (flat segments)."""
+    L = lib()
+    L.orc_set_num_threads(int(threads) if threads else min(8, usable_cpus()))
+    L.orc_vp_detect.restype = C.c_longlong
+    L.orc_vp_detect.argtypes = [C.c_int, _P, _P, _P, _P, _P, _P, C.c_longlong]
+    line_off = np.ascontiguousarray(line_off, np.int64)
+    segs = _f64(segs)
+    n = len(line_off) - 1
+    cfg = VPCfg(min_length, inlier_threshold, th_perp_supports, min_num_supports, n_models, seed)
+    labels = np.full(int(line_off[-1]), -1, np.int32)
+    vp_off = np.zeros(n + 1, np.int64)
+    cap = 64 * max(n, 1)
+    vps = np.zeros((cap, 3))
+    tot = L.orc_vp_detect(n, _p(line_off), _p(segs), C.byref(cfg), _p(labels), _p(vp_off), _p(vps), cap)
+    return labels, vp_off, vps[:tot]

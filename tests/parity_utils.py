@@ -7,7 +7,7 @@ ENDPOINT_TOL = 1e-4   # BASELINE.json north_star: "within 1e-4 absolute on 3D li
 SCORE_TOL = 1e-6
 
 
-def run_both(scene, cfg, exhaustive=False, use_ranges=True):
+def run_both(scene, cfg, exhaustive=False, use_ranges=True, vpresults=None):
     from limap_b200.engine import TriEngine
     from oracle.oracle import OracleTri
     eng, orc = TriEngine(cfg), OracleTri(cfg)
@@ -15,6 +15,8 @@ def run_both(scene, cfg, exhaustive=False, use_ranges=True):
         t.upload(scene)
         if use_ranges:
             t.set_ranges(*scene.ranges)
+        if vpresults is not None:
+            t.set_vps(vpresults, scene.img_ids, scene.line_off)
         for i in scene.img_ids:
             if exhaustive:
                 t.add_image_exhaustive(int(i), scene.neighbors[int(i)])
