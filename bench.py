@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-lm", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -343,6 +344,55 @@ def main():
                          "fp64 restatement with the reference's loop structure (OpenMP over connections / "
                          "candidates of one node)"}
 
+    # ---- M2: line-BA LM iterations/s (BASELINE.json configs[3]: 10k tracks x 30 supporting views per rank) ----
+    lm_ba = None
+    if not args.no_lm:
+        from limap_b200.engine import BAEngine
+        from limap_b200.synth import make_tracks
+        ts = make_tracks(T=10000, S=30, V=300, seed=1237 + rank)
+        ba = BAEngine(ctx=eng.ctx)
+        views, first_idx = np.unique(ts.img_ids, return_index=True)
+        remap = np.zeros(int(views.max()) + 1, np.int32)
+        remap[views] = np.arange(len(views), dtype=np.int32)
+        a = (ts.kvec[first_idx], ts.qvec[first_idx], ts.tvec[first_idx], ts.sup_off, remap[ts.img_ids], ts.segs,
+             ts.line3d, ts.line_init)
+        for _ in range(2):
+            out = ba.solve(*a, max_num_iterations=100)
+        barrier()
+        t0 = time.perf_counter()
+        k_ms, iters = [], 0
+        for _ in range(args.steps):
+            out = ba.solve(*a, max_num_iterations=100)
+            k_ms.append(out["stats"]["solve_ms"])
+            iters += out["stats"]["total_iterations"]
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt, float(np.sum(k_ms)) * 1e-3], device="cuda", dtype=torch.float64)
+        ii = torch.tensor([float(iters)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ii, op=dist.ReduceOp.SUM)
+        lm_ba = {"metric": "line-BA LM iters/sec", "unit": "track LM iterations/s",
+                 "config": {"workload": "ba10k", "tracks_per_gpu": 10000, "supports": 30, "max_num_iterations": 100},
+                 "value_kernel": float(ii.item() / tt[1].item()), "e2e": {"value": float(ii.item() / tt[0].item()),
+                                                                         "note": "lm_ba_solve from host arrays: H2D, "
+                                                                                 "solve, segment cut, D2H"},
+                 "kernel_ms": float(np.mean(k_ms)), "iterations_per_solve": int(iters // args.steps),
+                 "dtype": "f64"}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as orc
+            sub = make_tracks(T=1500, S=30, V=300, seed=1237)
+            best = None
+            for th in sorted({1, min(8, orc.usable_cpus()), orc.usable_cpus()}):
+                t0 = time.perf_counter()
+                o = orc.refine_tracks(sub, max_num_iterations=100, threads=th)
+                v = float(o["iters"][:, 0].sum() / (time.perf_counter() - t0))
+                if best is None or v > best[0]:
+                    best = (v, th)
+            lm_ba["cpu_baseline"] = {"value": best[0], "unit": "track LM iterations/s", "cores": best[1], "kind": "port",
+                                     "sample": "1500 tracks x 30 supports, Ceres-style LM restatement, OpenMP over "
+                                               "tracks"}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -354,7 +404,7 @@ def main():
                            "parallelism": f"source-image shards x{world}",
                            "l2": "inputs larger than L2 (match rows + sort buffers > 126 MB per step)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "lm_ba": lm_ba}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

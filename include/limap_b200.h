@@ -171,6 +171,7 @@ typedef struct lm_ba_config {
   int32_t min_num_images;     /* 4: tracks seen in fewer distinct images stay constant */
   int32_t num_outliers;       /* num_outliers_aggregate = 2 */
   int32_t max_num_consecutive_invalid_steps; /* 10 */
+  double vp_multiplier;       /* weight of the VP residual relative to the line weight (yaml: 0.1) */
 } lm_ba_config;
 
 typedef struct lm_ba_stats {
@@ -186,10 +187,12 @@ typedef struct lm_ba_stats {
  * segs[k][4], line3d[k][6] (track.line3d_list, used only to cut the output segment,
  * base/infinite_line.cc:265-287); line_init[T][6] = track.line. Outputs: out_line[T][6] refined segment,
  * out_minimal[T][6] = (uvec, wvec), out_iters[T][2] = (iterations, successful), out_cost[T][2] =
- * (initial, final) cost. Any output may be NULL. */
+ * (initial, final) cost. Any output may be NULL. sup_vp[k][3] (may be NULL): vanishing point of supporting
+ * line k for the VP residual of RefinementEngine::AddVPResiduals (refine.cc:86-127), NaN = none. */
 int lm_ba_solve(lm_ctx *ctx, int32_t n_views, const double *kvec, const double *qvec, const double *tvec,
                 int64_t n_tracks, const int64_t *sup_off, const int32_t *sup_view, const double *segs,
-                const double *line3d, const double *line_init, const lm_ba_config *cfg, double *out_line,
+                const double *line3d, const double *line_init, const double *sup_vp, const lm_ba_config *cfg,
+                double *out_line,
                 double *out_minimal, int32_t *out_iters, double *out_cost);
 int lm_ba_get_stats(lm_ctx *ctx, lm_ba_stats *out);
 

@@ -26,7 +26,8 @@ class TriStats(C.Structure):
 class BAConfig(C.Structure):
     _fields_ = [("geometric_alpha", C.c_double), ("cauchy_scale", C.c_double),
                 ("max_num_iterations", C.c_int32), ("min_num_images", C.c_int32),
-                ("num_outliers", C.c_int32), ("max_num_consecutive_invalid_steps", C.c_int32)]
+                ("num_outliers", C.c_int32), ("max_num_consecutive_invalid_steps", C.c_int32),
+                ("vp_multiplier", C.c_double)]
 
 
 class VPConfig(C.Structure):
@@ -74,7 +75,7 @@ _SIGS = {
     "lm_scene_node_offset": (C.c_int64, [_P, C.c_int32]),
     "lm_tri_build_tracks": (C.c_int64, [_P, C.POINTER(C.c_int64)]),
     "lm_tri_get_tracks": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
-    "lm_ba_solve": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "lm_ba_solve": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lm_ba_get_stats": (C.c_int, [_P, _P]),
     "lm_vp_detect": (C.c_int64, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64]),
 }

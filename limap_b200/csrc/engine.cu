@@ -1265,8 +1265,8 @@ extern "C" {
 
 int lm_ba_solve(lm_ctx *c, int32_t n_views, const double *kvec, const double *qvec, const double *tvec, int64_t T,
                 const int64_t *sup_off, const int32_t *sup_view, const double *segs, const double *line3d,
-                const double *line_init, const lm_ba_config *cfg, double *out_line, double *out_minimal,
-                int32_t *out_iters, double *out_cost) {
+                const double *line_init, const double *sup_vp, const lm_ba_config *cfg, double *out_line,
+                double *out_minimal, int32_t *out_iters, double *out_cost) {
   if (!c || !cfg || !sup_off) return fail(LM_ERR_INVALID, "NULL argument");
   if (T < 0 || n_views <= 0) return fail(LM_ERR_INVALID, "bad sizes");
   CU(cudaSetDevice(c->device));
@@ -1294,7 +1294,8 @@ int lm_ba_solve(lm_ctx *c, int32_t n_views, const double *kvec, const double *qv
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   const size_t o_k = take(32 * n_views), o_q = take(32 * n_views), o_t = take(24 * n_views), o_s = take(32 * n),
-               o_x = take(48 * T), o_so = take(8 * (T + 1)), o_sv = take(4 * n), o_a = take(T);
+               o_x = take(48 * T), o_so = take(8 * (T + 1)), o_sv = take(4 * n), o_a = take(T),
+               o_vp = take(sup_vp ? 24 * n : 0), o_l3 = take((line3d && out_line) ? 48 * n : 0);
   CU(c->d_ba_in.ensure(off + 256));
   char *in = c->d_ba_in.as<char>();
   CU(cudaMemcpyAsync(in + o_k, kvec, 32 * n_views, cudaMemcpyHostToDevice, s));
@@ -1305,16 +1306,22 @@ int lm_ba_solve(lm_ctx *c, int32_t n_views, const double *kvec, const double *qv
   CU(cudaMemcpyAsync(in + o_so, sup_off, 8 * (T + 1), cudaMemcpyHostToDevice, s));
   if (n) CU(cudaMemcpyAsync(in + o_sv, sup_view, 4 * n, cudaMemcpyHostToDevice, s));
   if (T) CU(cudaMemcpyAsync(in + o_a, active.data(), T, cudaMemcpyHostToDevice, s));
+  if (sup_vp && n) CU(cudaMemcpyAsync(in + o_vp, sup_vp, 24 * n, cudaMemcpyHostToDevice, s));
+  const bool dev_seg = line3d && out_line && n;
+  if (dev_seg) CU(cudaMemcpyAsync(in + o_l3, line3d, 48 * n, cudaMemcpyHostToDevice, s));
   CU(c->d_ba_blocks.ensure(sizeof(lm::LMBlockDev) * std::max<int64_t>(n, 1)));
   size_t oo = 0;
   auto take_o = [&](size_t bytes) { size_t o = oo; oo += (bytes + 255) / 256 * 256; return o; };
-  const size_t oo_x = take_o(48 * T), oo_i = take_o(8 * T), oo_c = take_o(16 * T), oo_t = take_o(4 * T);
+  const size_t oo_x = take_o(48 * T), oo_i = take_o(8 * T), oo_c = take_o(16 * T), oo_t = take_o(4 * T),
+               oo_s = take_o(48 * T);
   CU(c->d_ba_out.ensure(oo + 256));
   char *out = c->d_ba_out.as<char>();
   CU(cudaEventRecord(c->ev0, s));
   lm::launch_lm_prepare(reinterpret_cast<const double *>(in + o_s), reinterpret_cast<const int32_t *>(in + o_sv),
                         reinterpret_cast<const double *>(in + o_k), reinterpret_cast<const double *>(in + o_q),
-                        reinterpret_cast<const double *>(in + o_t), n, c->d_ba_blocks.as<lm::LMBlockDev>(), s);
+                        reinterpret_cast<const double *>(in + o_t),
+                        (sup_vp && n) ? reinterpret_cast<const double *>(in + o_vp) : nullptr, cfg->vp_multiplier, n,
+                        c->d_ba_blocks.as<lm::LMBlockDev>(), s);
   CU(cudaEventRecord(c->evk0, s));
   lm::LMParams p;
   p.blocks = c->d_ba_blocks.as<lm::LMBlockDev>();
@@ -1325,6 +1332,9 @@ int lm_ba_solve(lm_ctx *c, int32_t n_views, const double *kvec, const double *qv
   p.iters = reinterpret_cast<int32_t *>(out + oo_i);
   p.cost = reinterpret_cast<double *>(out + oo_c);
   p.term = reinterpret_cast<int32_t *>(out + oo_t);
+  p.line3d = dev_seg ? reinterpret_cast<const double *>(in + o_l3) : nullptr;
+  p.seg_out = dev_seg ? reinterpret_cast<double *>(out + oo_s) : nullptr;
+  p.num_outliers = cfg->num_outliers;
   p.T = T;
   p.geometric_alpha = cfg->geometric_alpha;
   p.cauchy_scale = cfg->cauchy_scale;
@@ -1335,7 +1345,9 @@ int lm_ba_solve(lm_ctx *c, int32_t n_views, const double *kvec, const double *qv
   CU(cudaEventRecord(c->evk1, s));
   std::vector<double> xf(6 * std::max<int64_t>(T, 1)), cost(2 * std::max<int64_t>(T, 1));
   std::vector<int32_t> iters(2 * std::max<int64_t>(T, 1));
+  std::vector<double> segd(dev_seg ? 6 * std::max<int64_t>(T, 1) : 0);
   if (T) {
+    if (dev_seg) CU(cudaMemcpyAsync(segd.data(), out + oo_s, 48 * T, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(xf.data(), out + oo_x, 48 * T, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(iters.data(), out + oo_i, 8 * T, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(cost.data(), out + oo_c, 16 * T, cudaMemcpyDeviceToHost, s));
@@ -1356,7 +1368,9 @@ int lm_ba_solve(lm_ctx *c, int32_t n_views, const double *kvec, const double *qv
     if (out_minimal) memcpy(out_minimal + 6 * t, &xf[6 * t], 48);
     if (out_iters) { out_iters[2 * t] = iters[2 * t]; out_iters[2 * t + 1] = iters[2 * t + 1]; }
     if (out_cost) { out_cost[2 * t] = cost[2 * t]; out_cost[2 * t + 1] = cost[2 * t + 1]; }
-    if (out_line) {
+    if (out_line && dev_seg && !std::isnan(segd[6 * t])) {
+      memcpy(out_line + 6 * t, &segd[6 * t], 48); // cut on the device
+    } else if (out_line) {
       const int64_t a = sup_off[t], b = sup_off[t + 1];
       if (b > a && 2 * (b - a) - 1 - cfg->num_outliers >= 0 && cfg->num_outliers < 2 * (b - a))
         segment_from_minimal(&xf[6 * t], line3d + 6 * a, b - a, cfg->num_outliers, out_line + 6 * t);

@@ -24,6 +24,8 @@
 
 namespace lm {
 
+static constexpr int kSegMax = 128; // supports per track handled by the in-kernel segment cut
+
 template <int N> struct Dual {
   double a;
   double v[N];
@@ -141,6 +143,8 @@ LM_D void line_from_minimal(const double x[6], bool want_jac, LineLocal &L) {
 struct BlockEval {
   double r[2];     // raw residuals
   double J[8];     // 2x4 local Jacobian (raw)
+  double rv;       // VP residual (VPConstraintsFunctor), only when B.wvp > 0
+  double Jv[4];
 };
 
 // One residual block: from (d, m) to the two cosine-weighted point-line distances.
@@ -177,6 +181,23 @@ LM_D void eval_block(const LMBlockDev &B, const LineLocal &L, double alpha, bool
   const Dual<3> r1 = ((c0 * B.p[2] + c1 * B.p[3] + c2) / dn) * weight;
   o.r[0] = r0.a;
   o.r[1] = r1.a;
+  Dual<3> rvp = dconst<3>(0.0);
+  if (B.wvp > 0.0) {
+    // VPConstraintsFunctor (cost_functions.h:60-85): sine between R d and the VP direction
+    // (CeresComputeDist3D_sine, ceresbase/line_dists.h:40-57); duals seeded on R d
+    Dual<3> a[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { a[i].a = Rd[i]; a[i].v[0] = (i == 0); a[i].v[1] = (i == 1); a[i].v[2] = (i == 2); }
+    const Dual<3> e3 = dconst<3>(consts<double>::eps());
+    const Dual<3> n1 = dsqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + e3);
+    const double n2 = sqrt(B.vdir[0] * B.vdir[0] + B.vdir[1] * B.vdir[1] + B.vdir[2] * B.vdir[2] + consts<double>::eps());
+    const Dual<3> ax = a[0] / n1, ay = a[1] / n1, az = a[2] / n1;
+    const double bx = B.vdir[0] / n2, by = B.vdir[1] / n2, bz = B.vdir[2] / n2;
+    const Dual<3> cx_ = ay * bz - az * by, cy_ = az * bx - ax * bz, cz_ = ax * by - ay * bx;
+    rvp = dsqrt(cx_ * cx_ + cy_ * cy_ + cz_ * cz_ + e3);
+    if (rvp.a > 1.0) rvp = dconst<3>(1.0);
+  }
+  o.rv = rvp.a;
   if (!want_jac) return;
   // G = d m_c / d local (3x4) = R Dm + t x (R Dd)
 #pragma unroll
@@ -192,6 +213,7 @@ LM_D void eval_block(const LMBlockDev &B, const LineLocal &L, double alpha, bool
     const double g2 = rm[2] + (B.t[0] * rd[1] - B.t[1] * rd[0]);
     o.J[c] = r0.v[0] * g0 + r0.v[1] * g1 + r0.v[2] * g2;
     o.J[4 + c] = r1.v[0] * g0 + r1.v[1] * g1 + r1.v[2] * g2;
+    o.Jv[c] = rvp.v[0] * rd[0] + rvp.v[1] * rd[1] + rvp.v[2] * rd[2];
   }
 }
 
@@ -223,6 +245,7 @@ LM_D void eval_track(const LMBlockDev *blocks, int S, const double x[6], double 
     const double sum = 1.0 + s * cq, inv = 1.0 / sum;
     const double rho0 = B.w * bq * log(sum), rho1 = B.w * fmax(DBL_MIN, inv), rho2 = B.w * (-cq * (inv * inv));
     cost += 0.5 * rho0;
+    if (B.wvp > 0.0) cost += 0.5 * B.wvp * e.rv * e.rv; // ScaledLoss(TrivialLoss, w * vp_multiplier)
     if (!want_jac) continue;
     const double sqrt_rho1 = sqrt(rho1);
     double residual_scaling = sqrt_rho1, alpha_sq_norm = 0.0;
@@ -245,12 +268,23 @@ LM_D void eval_track(const LMBlockDev *blocks, int S, const double x[6], double 
       if (scale) { J0[c] *= scale[c]; J1[c] *= scale[c]; }
     }
     const double r0 = e.r[0] * residual_scaling, r1 = e.r[1] * residual_scaling;
+    double J2[4] = {0, 0, 0, 0}, r2 = 0.0;
+    if (B.wvp > 0.0) {
+      const double sq = sqrt(B.wvp);
+      r2 = sq * e.rv;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        J2[c] = sq * e.Jv[c];
+        cn2[c] += J2[c] * J2[c];
+        if (scale) J2[c] *= scale[c];
+      }
+    }
     int idx = 0;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      g[a] += J0[a] * r0 + J1[a] * r1;
+      g[a] += J0[a] * r0 + J1[a] * r1 + J2[a] * r2;
 #pragma unroll
-      for (int b = a; b < 4; ++b) A[idx++] += J0[a] * J0[b] + J1[a] * J1[b];
+      for (int b = a; b < 4; ++b) A[idx++] += J0[a] * J0[b] + J1[a] * J1[b] + J2[a] * J2[b];
     }
   }
   N.cost = warp_sum(cost);
@@ -406,12 +440,61 @@ __global__ void __launch_bounds__(128) lm_refine_kernel(const __grid_constant__ 
     p.cost[2 * t] = cost0; p.cost[2 * t + 1] = cost;
     p.term[t] = term;
   }
+  // GetLineSegmentFromInfiniteLine3d(inf_line, track.line3d_list, num_outliers) (base/infinite_line.cc:265-287)
+  // on the infinite line of MinimalInfiniteLine3d::GetInfiniteLine (:220-231)
+  if (p.seg_out) {
+    __shared__ double s_vals[4][2 * kSegMax];
+    double *vals = s_vals[warp_in_block];
+    const int n2 = 2 * S;
+    const bool ok = p.line3d && S > 0 && S <= kSegMax && p.num_outliers >= 0 && p.num_outliers < n2 &&
+                    n2 - 1 - p.num_outliers >= 0;
+    if (!ok) {
+      if (lane < 6) p.seg_out[6 * t + lane] = __longlong_as_double(0x7ff8000000000000ll);
+      return;
+    }
+    // limap QuaternionToRotationMatrix (base/pose.cc:12-18): normalised quaternion
+    double q[4];
+    {
+      const double nq = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+      if (nq == 0) { q[0] = 1.0; q[1] = x[1]; q[2] = x[2]; q[3] = x[3]; }
+      else { q[0] = x[0] / nq; q[1] = x[1] / nq; q[2] = x[2] / nq; q[3] = x[3] / nq; }
+    }
+    const double qw = q[0], qx = q[1], qy = q[2], qz = q[3];
+    const double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz, twx = tx * qw, twy = ty * qw, twz = tz * qw;
+    const double txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+    const double d0 = 1 - (tyy + tzz), d1 = txy + twz, d2 = txz - twy;       // Q.col(0)
+    const double f = fabs(x[5]) / fabs(x[4]);
+    const double m0 = (txy - twz) * f, m1 = (1 - (txx + tzz)) * f, m2 = (tyz + twx) * f; // Q.col(1) * |w1|/|w0|
+    const double *l3 = p.line3d + 6 * s0;
+    // p_ref = point_projection(line3ds[0].start): q + d x (m + d x q) (:73-78)
+    double pr0, pr1, pr2;
+    {
+      const double a0 = l3[0], a1 = l3[1], a2 = l3[2];
+      const double c0 = m0 + (d1 * a2 - d2 * a1), c1 = m1 + (d2 * a0 - d0 * a2), c2 = m2 + (d0 * a1 - d1 * a0);
+      pr0 = a0 + (d1 * c2 - d2 * c1); pr1 = a1 + (d2 * c0 - d0 * c2); pr2 = a2 + (d0 * c1 - d1 * c0);
+    }
+    for (int k = lane; k < n2; k += 32) {
+      const double *e = l3 + 3 * k; // endpoint k (start/end interleaved)
+      vals[k] = (e[0] - pr0) * d0 + (e[1] - pr1) * d1 + (e[2] - pr2) * d2;
+    }
+    __syncwarp();
+    // order statistics by rank counting (values[num_outliers] and values[2S-1-num_outliers] of the sorted list)
+    const int ka = p.num_outliers, kb = n2 - 1 - p.num_outliers;
+    for (int k = lane; k < n2; k += 32) {
+      const double v = vals[k];
+      int rank = 0;
+      for (int j = 0; j < n2; ++j) { const double u = vals[j]; rank += (u < v) || (u == v && j < k); }
+      if (rank == ka) { p.seg_out[6 * t] = pr0 + d0 * v; p.seg_out[6 * t + 1] = pr1 + d1 * v; p.seg_out[6 * t + 2] = pr2 + d2 * v; }
+      if (rank == kb) { p.seg_out[6 * t + 3] = pr0 + d0 * v; p.seg_out[6 * t + 4] = pr1 + d1 * v; p.seg_out[6 * t + 5] = pr2 + d2 * v; }
+    }
+  }
 }
 
 // supports -> digested blocks: R from qvec via ceres::QuaternionToRotation (normalising), loss weight |seg|/30
 __global__ void lm_prepare_blocks_kernel(const double *__restrict__ segs, const int32_t *__restrict__ sup_view,
                                          const double *__restrict__ kvec, const double *__restrict__ qvec,
-                                         const double *__restrict__ tvec, int64_t n, LMBlockDev *__restrict__ out) {
+                                         const double *__restrict__ tvec, const double *__restrict__ sup_vp,
+                                         double vp_multiplier, int64_t n, LMBlockDev *__restrict__ out) {
   const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int v = sup_view[k];
@@ -428,13 +511,24 @@ __global__ void lm_prepare_blocks_kernel(const double *__restrict__ segs, const 
   for (int i = 0; i < 3; ++i) B.t[i] = tvec[3 * v + i];
   const double dx = B.p[0] - B.p[2], dy = B.p[1] - B.p[3];
   B.w = sqrt(dx * dx + dy * dy) / 30.0; // ComputeLineWeights (base/linetrack.cc:315-322)
+  B.vdir[0] = B.vdir[1] = B.vdir[2] = 0.0;
+  B.wvp = 0.0;
+  if (sup_vp && !isnan(sup_vp[3 * k])) {
+    const double v0 = sup_vp[3 * k], v1 = sup_vp[3 * k + 1], v2 = sup_vp[3 * k + 2];
+    const double e0 = v0 / B.k[0] - B.k[2] / B.k[0] * v2, e1 = v1 / B.k[1] - B.k[3] / B.k[1] * v2, e2 = v2;
+    const double nn = sqrt(e0 * e0 + e1 * e1 + e2 * e2 + consts<double>::eps());
+    B.vdir[0] = e0 / nn; B.vdir[1] = e1 / nn; B.vdir[2] = e2 / nn;
+    B.wvp = B.w * vp_multiplier;
+  }
   out[k] = B;
 }
 
 void launch_lm_prepare(const double *segs, const int32_t *sup_view, const double *kvec, const double *qvec,
-                       const double *tvec, int64_t n, LMBlockDev *out, cudaStream_t s) {
+                       const double *tvec, const double *sup_vp, double vp_multiplier, int64_t n, LMBlockDev *out,
+                       cudaStream_t s) {
   if (n <= 0) return;
-  lm_prepare_blocks_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(segs, sup_view, kvec, qvec, tvec, n, out);
+  lm_prepare_blocks_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(segs, sup_view, kvec, qvec, tvec, sup_vp,
+                                                                  vp_multiplier, n, out);
 }
 void launch_lm_refine(const LMParams &p, cudaStream_t s) {
   if (p.T <= 0) return;

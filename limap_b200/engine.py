@@ -173,20 +173,21 @@ class BAEngine:
 
     def solve(self, kvec, qvec, tvec, sup_off, sup_view, segs, line3d, line_init, max_num_iterations=100,
               min_num_images=4, num_outliers=2, geometric_alpha=10.0, cauchy_scale=0.25,
-              max_num_consecutive_invalid_steps=10):
+              max_num_consecutive_invalid_steps=10, sup_vp=None, vp_multiplier=1.0):
         f64 = lambda a: np.ascontiguousarray(a, np.float64)
         kvec, qvec, tvec, segs, line3d, line_init = map(f64, (kvec, qvec, tvec, segs, line3d, line_init))
         sup_off = np.ascontiguousarray(sup_off, np.int64)
         sup_view = np.ascontiguousarray(sup_view, np.int32)
         T = len(sup_off) - 1
         cfg = _cabi.BAConfig(geometric_alpha, cauchy_scale, max_num_iterations, min_num_images, num_outliers,
-                             max_num_consecutive_invalid_steps)
+                             max_num_consecutive_invalid_steps, float(vp_multiplier))
+        sup_vp = None if sup_vp is None else f64(sup_vp)
         out_line = np.zeros((T, 6))
         out_min = np.zeros((T, 6))
         iters = np.zeros((T, 2), np.int32)
         cost = np.zeros((T, 2))
         check(lib().lm_ba_solve(self.ctx.handle, len(kvec), ptr(kvec), ptr(qvec), ptr(tvec), T, ptr(sup_off),
-                                ptr(sup_view), ptr(segs), ptr(line3d), ptr(line_init), C.byref(cfg),
+                                ptr(sup_view), ptr(segs), ptr(line3d), ptr(line_init), ptr(sup_vp), C.byref(cfg),
                                 ptr(out_line), ptr(out_min), ptr(iters), ptr(cost)))
         st = _cabi.BAStats()
         check(lib().lm_ba_get_stats(self.ctx.handle, C.byref(st)))
@@ -195,14 +196,7 @@ class BAEngine:
 
     def solve_trackset(self, ts, **kw):
         """TrackSet (limap_b200.synth.make_tracks) carries per-support cameras; dedupe them into a view table."""
-        views = np.unique(ts.img_ids)
-        first = {int(v): int(np.flatnonzero(ts.img_ids == v)[0]) for v in views} if len(views) < 4096 else None
-        if first is None:
-            order = np.argsort(ts.img_ids, kind="stable")
-            _, idx = np.unique(ts.img_ids[order], return_index=True)
-            first_idx = order[idx]
-        else:
-            first_idx = np.array([first[int(v)] for v in views])
+        views, first_idx = np.unique(ts.img_ids, return_index=True)
         remap = np.zeros(int(views.max()) + 1, np.int32)
         remap[views] = np.arange(len(views), dtype=np.int32)
         return self.solve(ts.kvec[first_idx], ts.qvec[first_idx], ts.tvec[first_idx], ts.sup_off,

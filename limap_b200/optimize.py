@@ -86,6 +86,16 @@ def _tracks_to_arrays(tracks, view_of):
             np.asarray(init, np.float64).reshape(-1, 6))
 
 
+def _support_vps(tracks, vpresult_of):
+    """[n_support, 3] VP of every supporting 2D line (NaN where the line has none)."""
+    out = []
+    for t in tracks:
+        for img, line_id in zip(t.image_id_list, t.line_id_list):
+            r = vpresult_of(img)
+            out.append(r.GetVP(line_id) if (r is not None and r.HasVP(line_id)) else [np.nan] * 3)
+    return np.asarray(out, np.float64).reshape(-1, 3)
+
+
 class HybridBAEngine:
     """HybridBAEngine (hybrid_bundle_adjustment.h) for line tracks with constant cameras."""
 
@@ -181,14 +191,15 @@ class RefinementEngine:
 
     def __init__(self, cfg=None, device=0):
         self.config_ = cfg if isinstance(cfg, RefinementConfig) else RefinementConfig(cfg)
-        self._track, self._views, self._res = None, None, None
+        self._track, self._views, self._res, self._vpresults = None, None, None, None
         self._ba = BAEngine(device=device)
 
     def Initialize(self, track, p_camviews):
         self._track, self._views = track, list(p_camviews)
 
     def InitializeVPs(self, p_vpresults):
-        raise NotImplementedError("VP residuals (use_vp) are not built yet (SURVEY.md §8 a15)")
+        """p_vpresults[i] = VPResult of the i-th image of track.GetSortedImageIds() (refine.cc:30-35)."""
+        self._vpresults = list(p_vpresults)
 
     def SetUp(self):
         pass
@@ -202,9 +213,13 @@ class RefinementEngine:
         tvec = np.array([v.pose.tvec for v in self._views])
         arr = _tracks_to_arrays([t], view_of)
         c = self.config_
+        sup_vp = None
+        if self._vpresults is not None:  # AddVPResiduals (refine.cc:86-127)
+            sup_vp = _support_vps([t], lambda img: self._vpresults[view_of[img]])
         self._res = self._ba.solve(kvec, qvec, tvec, *arr, max_num_iterations=c.solver_options.max_num_iterations,
                                    min_num_images=0, num_outliers=c.num_outliers_aggregate,
-                                   geometric_alpha=c.geometric_alpha, cauchy_scale=c.line_geometric_loss_scale)
+                                   geometric_alpha=c.geometric_alpha, cauchy_scale=c.line_geometric_loss_scale,
+                                   sup_vp=sup_vp, vp_multiplier=c.vp_multiplier)
         return True
 
     def GetLine3d(self):
@@ -237,8 +252,9 @@ def line_refinement(cfg, tracks, imagecols, heatmap_dir=None, patch_dir=None, fe
     """line_refinement.py:15-147: refine each track (>= n_visible_views images) with fixed cameras. The
     reference loops over tracks with one Ceres problem each; here all selected tracks go to the GPU in one
     batched solve."""
-    if cfg.get("use_vp") or cfg.get("use_heatmap") or cfg.get("use_feature"):
-        raise NotImplementedError("only the geometric residual is on the hot path")
+    if cfg.get("use_heatmap") or cfg.get("use_feature"):
+        raise NotImplementedError("pixel-wise residuals need INTERPOLATION_ENABLED (off by default)")
+    use_vp = bool(cfg.get("use_vp"))
     rf_config = RefinementConfig(cfg)
     ids = [k for k in range(len(tracks)) if tracks[k].count_images() >= n_visible_views]
     sel = [k for k in ids if tracks[k].count_images() >= rf_config.min_num_images]
@@ -247,10 +263,12 @@ def line_refinement(cfg, tracks, imagecols, heatmap_dir=None, patch_dir=None, fe
         img_ids, _, kvec, qvec, tvec = imagecols.arrays()
         view_of = {int(i): v for v, i in enumerate(img_ids)}
         arr = _tracks_to_arrays([tracks[k] for k in sel], view_of)
+        sup_vp = _support_vps([tracks[k] for k in sel], lambda img: vpresults[img]) if use_vp else None
         res = BAEngine().solve(kvec, qvec, tvec, *arr, max_num_iterations=rf_config.solver_options.max_num_iterations,
                                min_num_images=0, num_outliers=rf_config.num_outliers_aggregate,
                                geometric_alpha=rf_config.geometric_alpha,
-                               cauchy_scale=rf_config.line_geometric_loss_scale)
+                               cauchy_scale=rf_config.line_geometric_loss_scale, sup_vp=sup_vp,
+                               vp_multiplier=rf_config.vp_multiplier)
         for n, k in enumerate(sel):
             t = base.LineTrack(tracks[k])
             t.line = base.Line3d(res["line"][n, 0:3], res["line"][n, 3:6])

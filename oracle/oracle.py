@@ -209,24 +209,26 @@ class LMCfg(C.Structure):
     _fields_ = [("geometric_alpha", C.c_double), ("cauchy_scale", C.c_double),
                 ("max_num_iterations", C.c_int32), ("min_num_images", C.c_int32),
                 ("num_outliers", C.c_int32), ("mode", C.c_int32), ("parallel_tracks", C.c_int32),
-                ("pad", C.c_int32)]
+                ("pad", C.c_int32), ("vp_multiplier", C.c_double)]
 
 
 def refine_tracks(ts, max_num_iterations=100, min_num_images=4, num_outliers=2, geometric_alpha=10.0,
-                  cauchy_scale=0.25, mode=0, parallel_tracks=True, threads=None):
+                  cauchy_scale=0.25, mode=0, parallel_tracks=True, threads=None, sup_vp=None, vp_multiplier=1.0,
+                  max_num_consecutive_invalid_steps=10):
     """CPU restatement of solve_line_bundle_adjustment / per-track RefinementEngine on a TrackSet."""
     L = lib()
     L.orc_set_num_threads(int(threads) if threads else min(8, usable_cpus()))
-    L.orc_refine_tracks.argtypes = [C.c_int] + [_P] * 13
+    L.orc_refine_tracks.argtypes = [C.c_int] + [_P] * 14
     T = ts.n_tracks
     cfg = LMCfg(geometric_alpha, cauchy_scale, max_num_iterations, min_num_images, num_outliers, mode,
-                int(parallel_tracks), 0)
+                int(parallel_tracks), 0, float(vp_multiplier))
     out_line = np.zeros((T, 6))
     out_min = np.zeros((T, 6))
     iters = np.zeros((T, 2), np.int32)
     cost = np.zeros((T, 2))
     a = [np.ascontiguousarray(ts.sup_off, np.int64), _f64(ts.segs), _f64(ts.kvec), _f64(ts.qvec), _f64(ts.tvec),
-         np.ascontiguousarray(ts.img_ids, np.int32), _f64(ts.line3d), _f64(ts.line_init)]
+         np.ascontiguousarray(ts.img_ids, np.int32), _f64(ts.line3d), _f64(ts.line_init),
+         None if sup_vp is None else _f64(sup_vp)]
     L.orc_refine_tracks(T, *[_p(x) for x in a], C.byref(cfg), _p(out_line), _p(out_min), _p(iters), _p(cost))
     return dict(line=out_line, minimal=out_min, iters=iters, cost=cost)
 

@@ -12,6 +12,7 @@ extern "C" {
 struct orc_lm_cfg {
   double geometric_alpha, cauchy_scale;
   int32_t max_num_iterations, min_num_images, num_outliers, mode, parallel_tracks, pad;
+  double vp_multiplier;
 };
 
 // Batched refinement of T tracks with constant cameras.
@@ -23,7 +24,7 @@ struct orc_lm_cfg {
 // out_line[T][6], out_min[T][6] = uvec,wvec; out_iters[T][2] = iterations, successful; out_cost[T][2].
 int orc_refine_tracks(int T, const int64_t *sup_off, const double *segs, const double *kvec, const double *qvec,
                       const double *tvec, const int32_t *img_ids, const double *l3d, const double *line_init,
-                      const orc_lm_cfg *cfg, double *out_line, double *out_min, int32_t *out_iters, double *out_cost) {
+                      const double *sup_vp /* [n][3] or NULL; NaN = no VP */, const orc_lm_cfg *cfg, double *out_line, double *out_min, int32_t *out_iters, double *out_cost) {
 #pragma omp parallel for schedule(dynamic, 8) if (cfg->parallel_tracks)
   for (int t = 0; t < T; ++t) {
     const int64_t a = sup_off[t], b = sup_off[t + 1];
@@ -45,6 +46,11 @@ int orc_refine_tracks(int T, const int64_t *sup_off, const double *segs, const d
       // ComputeLineWeights (base/linetrack.cc:315-322): length / 30
       const double dx = blk.p1[0] - blk.p2[0], dy = blk.p1[1] - blk.p2[1];
       blk.w = std::sqrt(dx * dx + dy * dy) / 30.0;
+      if (sup_vp && !std::isnan(sup_vp[3 * k])) {
+        blk.has_vp = true;
+        for (int i = 0; i < 3; ++i) blk.vp[i] = sup_vp[3 * k + i];
+        blk.wvp = blk.w * cfg->vp_multiplier;
+      }
       prob.blocks.push_back(blk);
     }
     const bool active = (int)imgs.size() >= cfg->min_num_images;

@@ -116,7 +116,42 @@ template <typename T> inline void Ceres_CosineWeightedPerpendicularDist2D_1D(con
 // GeometricRefinementFunctor::operator() (cost_functions.h:170-186), cameras constant
 struct LMBlock {
   double p1[2], p2[2], kvec[4], qvec[4], tvec[3], w;
+  bool has_vp = false;  // VPConstraintsFunctor block attached to this support (refine.cc:86-127)
+  double vp[3] = {0, 0, 0};
+  double wvp = 0;       // weights[k] * vp_multiplier
 };
+// ceresbase/line_projection.h:125-135
+template <typename T> inline void GetDirectionFromVP(const T vp[3], const T kvec[4], T direc[3]) {
+  direc[0] = vp[0] / kvec[0] - kvec[2] / kvec[0] * vp[2];
+  direc[1] = vp[1] / kvec[1] - kvec[3] / kvec[1] * vp[2];
+  direc[2] = vp[2];
+  T norm = sqrt(direc[0] * direc[0] + direc[1] * direc[1] + direc[2] * direc[2] + T(EPS));
+  direc[0] = direc[0] / norm; direc[1] = direc[1] / norm; direc[2] = direc[2] / norm;
+}
+// ceresbase/line_dists.h:40-57
+template <typename T> inline T CeresComputeDist3D_sine(const T dir1[3], const T dir2[3]) {
+  T n1 = sqrt(dir1[0] * dir1[0] + dir1[1] * dir1[1] + dir1[2] * dir1[2] + T(EPS));
+  T n2 = sqrt(dir2[0] * dir2[0] + dir2[1] * dir2[1] + dir2[2] * dir2[2] + T(EPS));
+  T a[3] = {dir1[0] / n1, dir1[1] / n1, dir1[2] / n1}, b[3] = {dir2[0] / n2, dir2[1] / n2, dir2[2] / n2};
+  T r[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+  T sine = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + T(EPS));
+  if (sine > T(1.0)) sine = T(1.0);
+  return sine;
+}
+// VPConstraintsFunctor::operator() (optimize/line_refinement/cost_functions.h:60-85), camera constant
+template <typename T> inline T VPResidual(const LMBlock &b, const T uvec[4], const T wvec[2]) {
+  T kvec[4] = {T(b.kvec[0]), T(b.kvec[1]), T(b.kvec[2]), T(b.kvec[3])};
+  T dir3d[3], m[3];
+  MinimalPluckerToPlucker(uvec, wvec, dir3d, m);
+  T q[4] = {T(b.qvec[0]), T(b.qvec[1]), T(b.qvec[2]), T(b.qvec[3])};
+  T R[9];
+  CeresQuaternionToRotation(q, R); // ceres::QuaternionRotatePoint normalises the quaternion: same rotation
+  T rot[3];
+  for (int i = 0; i < 3; ++i) rot[i] = R[3 * i] * dir3d[0] + R[3 * i + 1] * dir3d[1] + R[3 * i + 2] * dir3d[2];
+  T vpvec[3] = {T(b.vp[0]), T(b.vp[1]), T(b.vp[2])}, direc[3];
+  GetDirectionFromVP(vpvec, kvec, direc);
+  return CeresComputeDist3D_sine(rot, direc);
+}
 template <typename T> inline void GeometricResidual(const LMBlock &b, const T uvec[4], const T wvec[2], double alpha, T res[2]) {
   T kvec[4] = {T(b.kvec[0]), T(b.kvec[1]), T(b.kvec[2]), T(b.kvec[3])};
   T qvec[4] = {T(b.qvec[0]), T(b.qvec[1]), T(b.qvec[2]), T(b.qvec[3])};
@@ -243,17 +278,22 @@ struct LMProblem {
   std::vector<LMBlock> blocks;
   LMOptions opt;
   // cost (and optionally loss-corrected residuals + local Jacobian [2S x 4]) at x = (uvec, wvec)
+  // Residual layout: 3 rows per support (2 geometric + 1 VP row, zero when the support has no VP).
   double evaluate(const double x[6], std::vector<double> *res, std::vector<double> *jac) const {
     const int S = (int)blocks.size();
     const double bq = opt.cauchy_scale * opt.cauchy_scale, cq = 1.0 / bq;
     double cost = 0;
-    double Pq[12], Ps[2];
-    if (jac) { QuaternionPlusJacobian(x, Pq); Sphere2PlusJacobian(x + 4, Ps); jac->assign(8 * S, 0.0); }
-    if (res) res->assign(2 * S, 0.0);
+    double Pq[12] = {0}, Ps[2] = {0, 0};
+    if (jac) { QuaternionPlusJacobian(x, Pq); Sphere2PlusJacobian(x + 4, Ps); jac->assign(12 * S, 0.0); }
+    if (res) res->assign(3 * S, 0.0);
+    auto to_local = [&](const double J6[6], double Jl[4]) {
+      for (int c = 0; c < 3; ++c) Jl[c] = J6[0] * Pq[c] + J6[1] * Pq[3 + c] + J6[2] * Pq[6 + c] + J6[3] * Pq[9 + c];
+      Jl[3] = J6[4] * Ps[0] + J6[5] * Ps[1];
+    };
     for (int k = 0; k < S; ++k) {
-      double r[2], J6[12];
+      double r[2], J6[12] = {0};
+      typedef Jet<6> J;
       if (jac) {
-        typedef Jet<6> J;
         J u[4] = {J(x[0], 0), J(x[1], 1), J(x[2], 2), J(x[3], 3)}, w[2] = {J(x[4], 4), J(x[5], 5)}, rr[2];
         GeometricResidual<J>(blocks[k], u, w, opt.geometric_alpha, rr);
         for (int i = 0; i < 2; ++i) { r[i] = rr[i].a; for (int j = 0; j < 6; ++j) J6[6 * i + j] = rr[i].v[j]; }
@@ -268,33 +308,50 @@ struct LMProblem {
       const double a = blocks[k].w;
       const double rho0 = a * bq * std::log(sum), rho1 = a * std::max(std::numeric_limits<double>::min(), inv), rho2 = a * (-cq * (inv * inv));
       cost += 0.5 * rho0;
-      if (!res && !jac) continue;
-      // Corrector (ceres corrector.cc)
-      const double sqrt_rho1 = std::sqrt(rho1);
-      double residual_scaling, alpha_sq_norm;
-      if (s == 0.0 || rho2 <= 0.0) { residual_scaling = sqrt_rho1; alpha_sq_norm = 0.0; }
-      else {
-        const double D = 1.0 + 2.0 * s * rho2 / rho1;
-        const double alpha = 1.0 - std::sqrt(D);
-        residual_scaling = sqrt_rho1 / (1 - alpha);
-        alpha_sq_norm = alpha / s;
-      }
-      if (jac) {
-        double Jl[8]; // 2x4 local = J6 * blockdiag(Pq[4x3], Ps[2x1])
-        for (int i = 0; i < 2; ++i) {
-          for (int c = 0; c < 3; ++c) Jl[4 * i + c] = J6[6 * i] * Pq[c] + J6[6 * i + 1] * Pq[3 + c] + J6[6 * i + 2] * Pq[6 + c] + J6[6 * i + 3] * Pq[9 + c];
-          Jl[4 * i + 3] = J6[6 * i + 4] * Ps[0] + J6[6 * i + 5] * Ps[1];
-        }
-        if (alpha_sq_norm == 0.0) { for (int i = 0; i < 8; ++i) (*jac)[8 * k + i] = sqrt_rho1 * Jl[i]; }
+      if (res || jac) {
+        // Corrector (ceres corrector.cc)
+        const double sqrt_rho1 = std::sqrt(rho1);
+        double residual_scaling, alpha_sq_norm;
+        if (s == 0.0 || rho2 <= 0.0) { residual_scaling = sqrt_rho1; alpha_sq_norm = 0.0; }
         else {
-          for (int c = 0; c < 4; ++c) {
-            const double rtj = r[0] * Jl[c] + r[1] * Jl[4 + c];
-            (*jac)[8 * k + c] = sqrt_rho1 * (Jl[c] - alpha_sq_norm * r[0] * rtj);
-            (*jac)[8 * k + 4 + c] = sqrt_rho1 * (Jl[4 + c] - alpha_sq_norm * r[1] * rtj);
+          const double D = 1.0 + 2.0 * s * rho2 / rho1;
+          const double alpha = 1.0 - std::sqrt(D);
+          residual_scaling = sqrt_rho1 / (1 - alpha);
+          alpha_sq_norm = alpha / s;
+        }
+        if (jac) {
+          double Jl[8];
+          to_local(J6, Jl); to_local(J6 + 6, Jl + 4);
+          if (alpha_sq_norm == 0.0) { for (int i = 0; i < 8; ++i) (*jac)[12 * k + i] = sqrt_rho1 * Jl[i]; }
+          else {
+            for (int c = 0; c < 4; ++c) {
+              const double rtj = r[0] * Jl[c] + r[1] * Jl[4 + c];
+              (*jac)[12 * k + c] = sqrt_rho1 * (Jl[c] - alpha_sq_norm * r[0] * rtj);
+              (*jac)[12 * k + 4 + c] = sqrt_rho1 * (Jl[4 + c] - alpha_sq_norm * r[1] * rtj);
+            }
           }
         }
+        if (res) { (*res)[3 * k] = r[0] * residual_scaling; (*res)[3 * k + 1] = r[1] * residual_scaling; }
       }
-      if (res) { (*res)[2 * k] = r[0] * residual_scaling; (*res)[2 * k + 1] = r[1] * residual_scaling; }
+      // VP block: ScaledLoss(TrivialLoss, weight * vp_multiplier) (refine.cc:100-123)
+      if (blocks[k].has_vp) {
+        double rv, Jv6[6] = {0, 0, 0, 0, 0, 0};
+        if (jac) {
+          J u[4] = {J(x[0], 0), J(x[1], 1), J(x[2], 2), J(x[3], 3)}, w[2] = {J(x[4], 4), J(x[5], 5)};
+          J rj = VPResidual<J>(blocks[k], u, w);
+          rv = rj.a;
+          for (int j = 0; j < 6; ++j) Jv6[j] = rj.v[j];
+        } else
+          rv = VPResidual<double>(blocks[k], x, x + 4);
+        const double wv = blocks[k].wvp, sq = std::sqrt(wv);
+        cost += 0.5 * wv * rv * rv;
+        if (res) (*res)[3 * k + 2] = sq * rv;
+        if (jac) {
+          double Jl[4];
+          to_local(Jv6, Jl);
+          for (int c = 0; c < 4; ++c) (*jac)[12 * k + 8 + c] = sq * Jl[c];
+        }
+      }
     }
     return cost;
   }
@@ -312,10 +369,10 @@ struct LMProblem {
     sum.initial_cost = cost;
     double scale[4] = {1, 1, 1, 1};
     if (opt.jacobi_scaling) for (int c = 0; c < 4; ++c) {
-      double n2 = 0; for (int i = 0; i < 2 * S; ++i) n2 += J[4 * i + c] * J[4 * i + c];
+      double n2 = 0; for (int i = 0; i < 3 * S; ++i) n2 += J[4 * i + c] * J[4 * i + c];
       scale[c] = 1.0 / (1.0 + std::sqrt(n2));
     }
-    auto scale_cols = [&](std::vector<double> &Jm) { for (int i = 0; i < 2 * S; ++i) for (int c = 0; c < 4; ++c) Jm[4 * i + c] *= scale[c]; };
+    auto scale_cols = [&](std::vector<double> &Jm) { for (int i = 0; i < 3 * S; ++i) for (int c = 0; c < 4; ++c) Jm[4 * i + c] *= scale[c]; };
     scale_cols(J);
     double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
     bool reuse_diagonal = false;
@@ -326,13 +383,13 @@ struct LMProblem {
       // FinalizeIterationAndCheckIfMinimizerCanContinue
       if (it >= opt.max_num_iterations) { sum.termination = 1; break; }
       if (radius <= opt.min_trust_region_radius) { sum.termination = 2; break; }
-      { double gmax = 0; for (int c = 0; c < 4; ++c) { double g = 0; for (int i = 0; i < 2 * S; ++i) g += J[4 * i + c] / scale[c] * r[i]; gmax = std::max(gmax, std::abs(g)); }
+      { double gmax = 0; for (int c = 0; c < 4; ++c) { double g = 0; for (int i = 0; i < 3 * S; ++i) g += J[4 * i + c] / scale[c] * r[i]; gmax = std::max(gmax, std::abs(g)); }
         if (gmax <= 0.0) { sum.termination = 3; break; } }
       ++it;
       // LevenbergMarquardtStrategy::ComputeStep
       double A[16], g[4];
       for (int a = 0; a < 4; ++a) { g[a] = 0; for (int b = 0; b < 4; ++b) A[4 * a + b] = 0; }
-      for (int i = 0; i < 2 * S; ++i) for (int a = 0; a < 4; ++a) { g[a] += J[4 * i + a] * r[i]; for (int b = 0; b < 4; ++b) A[4 * a + b] += J[4 * i + a] * J[4 * i + b]; }
+      for (int i = 0; i < 3 * S; ++i) for (int a = 0; a < 4; ++a) { g[a] += J[4 * i + a] * r[i]; for (int b = 0; b < 4; ++b) A[4 * a + b] += J[4 * i + a] * J[4 * i + b]; }
       if (!reuse_diagonal) for (int c = 0; c < 4; ++c) diag[c] = std::min(std::max(A[5 * c], opt.min_lm_diagonal), opt.max_lm_diagonal);
       for (int c = 0; c < 4; ++c) A[5 * c] += diag[c] / radius; // D^T D, D = sqrt(diag / radius)
       reuse_diagonal = true;
@@ -342,7 +399,7 @@ struct LMProblem {
       double model_cost_change = 0;
       if (ok) {
         // model_residuals = J step ; change = -model_residuals . (r + model_residuals / 2)
-        for (int i = 0; i < 2 * S; ++i) {
+        for (int i = 0; i < 3 * S; ++i) {
           double mr = 0; for (int c = 0; c < 4; ++c) mr += J[4 * i + c] * step[c];
           model_cost_change -= mr * (r[i] + mr / 2.0);
         }

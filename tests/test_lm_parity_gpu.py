@@ -73,3 +73,28 @@ def test_large_support_and_asset_units():
     d = np.minimum(np.abs(g["line"] - o["line"]).max(1),
                    np.abs(g["line"] - o["line"][:, [3, 4, 5, 0, 1, 2]]).max(1))
     assert d.max() <= 100 * ENDPOINT_TOL  # asset units: 1e-4 of the scene scale
+
+
+def test_vp_residuals_match_oracle():
+    # VPConstraintsFunctor blocks (RefinementEngine::AddVPResiduals, refine.cc:86-127): half of the supports
+    # carry the (noisy) vanishing point of their track's 3D direction
+    from limap_b200.base import _quat_to_R
+    ts = make_tracks(T=150, S=10, V=50, seed=34)
+    rng = np.random.default_rng(0)
+    vp = np.full((len(ts.segs), 3), np.nan)
+    for t in range(ts.n_tracks):
+        d = ts.gt[t, 3:] - ts.gt[t, :3]
+        for k in range(ts.sup_off[t], ts.sup_off[t + 1]):
+            if rng.random() < 0.5:
+                K = np.array([[ts.kvec[k, 0], 0, ts.kvec[k, 2]], [0, ts.kvec[k, 1], ts.kvec[k, 3]], [0, 0, 1.0]])
+                v = K @ _quat_to_R(ts.qvec[k]) @ (d + rng.normal(scale=0.01, size=3))
+                vp[k] = v / np.linalg.norm(v)
+    g, o = _run(ts, max_num_iterations=100, sup_vp=vp, vp_multiplier=0.5)
+    g0, _ = _run(ts, max_num_iterations=100)
+    assert np.abs(g["cost"][:, 0] - o["cost"][:, 0]).max() < 1e-9 * (1 + o["cost"][:, 0].max())
+    assert (g["cost"][:, 0] > g0["cost"][:, 0]).mean() > 0.9        # the VP blocks add cost
+    rel = np.abs(g["cost"][:, 1] - o["cost"][:, 1]) / (1e-12 + o["cost"][:, 1])
+    assert np.median(rel) < 1e-9 and rel.max() < 1e-5
+    d = np.minimum(np.abs(g["line"] - o["line"]).max(1),
+                   np.abs(g["line"] - o["line"][:, [3, 4, 5, 0, 1, 2]]).max(1))
+    assert d.max() <= ENDPOINT_TOL
