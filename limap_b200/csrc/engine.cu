@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -685,6 +686,12 @@ int lm_tri_run(lm_ctx *c) {
       p.n_buckets = std::max(1, std::min(32, nb));
     }
     p.bucket_scale = (float)(p.n_buckets / kPi);
+    p.fast_forms = (p.l2d.use_innerseg || getenv("LIMAP_B200_REFERENCE_FORMS")) ? 0 : 1;
+    p.inv_sig_a3 = 1.0 / (p.l3d.th_angle * p.l3d.mult);
+    p.inv_sig_s3 = 1.0 / (p.l3d.th_scaleinv * p.l3d.mult);
+    p.inv_sig_a2 = 1.0 / (p.l2d.th_angle * p.l2d.mult);
+    p.inv_sig_p2 = 1.0 / (p.l2d.th_perp * p.l2d.mult);
+    p.q_cut3 = -2.0 * std::log(p.l3d.score_th) * (1.0 + 1e-9);
   }
   if ((int64_t)max_rows * ns > 65535) return fail(LM_ERR_INVALID, "more than 65535 candidates possible for one 2D line");
   int cap = 32;

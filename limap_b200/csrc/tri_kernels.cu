@@ -315,6 +315,87 @@ LM_D double pair_score(const TriParams &p, const seg<vec3<double>> &Li, vec3<dou
   return smin(score3, score2);
 }
 
+// The same pair score in algebraically reduced form (used unless innerseg is enabled on the 2d linker):
+// every sub-score of the two linkers is exp(-q_k/2) with q_k = (v_k/sigma_k)^2 zeroed below score_th, and
+// their minimum is exp(-max_k q_k / 2) because exp is monotone -- one exp instead of up to six; distances
+// enter as squares (no square roots: (d/sigma)^2 = d^2/sigma^2, max of the four perpendicular distances =
+// sqrt of the max of their squares), directions are never normalised (|cos| = |a.b|/sqrt(|a|^2|b|^2)) and
+// homogeneous divisions use one reciprocal. NaN angles are ignored exactly like std::min ignores a NaN
+// sub-score (line_dists.h:62-66). Polynomial early-outs skip the transcendental part for clear failures.
+LM_D double pair_score_fast(const TriParams &p, const Slab &sl, int i, int j, uint32_t vj) {
+  const double EPS = consts<double>::eps();
+  const LinkerDev<double> &c3 = p.l3d;
+  const LinkerDev<double> &c2 = p.l2d;
+  const vec3<double> si = mk3(sl.sx[i], sl.sy[i], sl.sz[i]), ei = mk3(sl.ex[i], sl.ey[i], sl.ez[i]);
+  double Q = 0.0; // running maximum of the squared normalised deviations
+  // ---- 3d: angle (line_linker.cc:185-192) + scale-invariant endpoint distance (:269-277)
+  {
+    const double cs = fabs(sl.dx[i] * sl.dx[j] + sl.dy[i] * sl.dy[j] + sl.dz[i] * sl.dz[j]);
+    const double angle = acos(cs) * consts<double>::rad2deg();
+    const double qa = angle * p.inv_sig_a3;
+    if (angle == angle) Q = qa * qa;
+    const vec3<double> ds = si - mk3(sl.sx[j], sl.sy[j], sl.sz[j]), de = ei - mk3(sl.ex[j], sl.ey[j], sl.ez[j]);
+    const double zs = sl.zs[i] + EPS, ze = sl.ze[i] + EPS;
+    const double r2 = fmax(dot(ds, ds) / (zs * zs), dot(de, de) / (ze * ze));
+    Q = fmax(Q, r2 * p.inv_sig_s3 * p.inv_sig_s3);
+    if (Q > p.q_cut3) return 0.0; // some 3d sub-score is clearly below score_th
+  }
+  // ---- 2d: projection of l_i into the view of candidate j (linebase.cc:93-98)
+  const ViewD &v = p.views[vj];
+  const vec3<double> hs = proj_h(v.P, si), he = proj_h(v.P, ei);
+  const double ws = 1.0 / (hs.z + EPS), we = 1.0 / (he.z + EPS);
+  const vec2<double> as = mk2(hs.x * ws, hs.y * ws), ae = mk2(he.x * we, he.y * we);
+  const vec2<double> bs = mk2(sl.q0[j], sl.q1[j]), be = mk2(sl.q2[j], sl.q3[j]);
+  const vec2<double> va = ae - as, vb = be - bs;
+  const double na2 = dot(va, va), nb2 = dot(vb, vb);
+  const double dab = dot(va, vb);
+  double Q2 = 0.0;
+  double angle2 = 0.0;
+  if (c2.use_angle) {
+    if (dab * dab < p.cos2_th2d * na2 * nb2 * (1.0 - 1e-9)) return 0.0; // |cos| clearly below cos(th_angle)
+    const double cos2 = (na2 > 0.0 && nb2 > 0.0) ? fabs(dab) / sqrt(na2 * nb2) : 0.0;
+    angle2 = acos(cos2) * consts<double>::rad2deg();
+    const double qa = angle2 * p.inv_sig_a2;
+    if (angle2 == angle2) Q2 = qa * qa;
+  }
+  double bio = 0.0;
+  if (c2.use_overlap) { // compute_bioverlap (line_dists.h:190-208)
+    const double inb = 1.0 / nb2, ina = 1.0 / na2;
+    double p1 = dot(as - bs, vb) * inb, p2 = dot(ae - bs, vb) * inb;
+    if (p1 > p2) { const double t = p1; p1 = p2; p2 = t; }
+    const double o1 = smin(p2, 1.0) - smax(p1, 0.0);
+    double r1 = dot(bs - as, va) * ina, r2 = dot(be - as, va) * ina;
+    if (r1 > r2) { const double t = r1; r1 = r2; r2 = t; }
+    const double o2 = smin(r2, 1.0) - smax(r1, 0.0);
+    bio = smax(o1, o2);
+    if (!(bio > c2.th_overlap)) return 0.0;
+  }
+  if (c2.use_angle && c2.use_overlap && c2.use_smartangle) { // line_linker.cc:49-65
+    double th_angle = c2.th_angle;
+    if (bio < c2.th_smartoverlap) {
+      double ratio = (c2.th_smartoverlap - bio) / (c2.th_smartoverlap - c2.th_overlap);
+      ratio = smin(ratio, 1.0);
+      th_angle = c2.th_angle - ratio * (c2.th_angle - c2.th_smartangle);
+    }
+    const double qa = angle2 / (th_angle * c2.mult);
+    if (angle2 == angle2) Q2 = fmax(Q2, qa * qa);
+  }
+  if (c2.use_perp) { // max of the four endpoint-to-infinite-line distances, squared (line_dists.h:105-133)
+    const vec2<double> d0 = as - bs, d1 = ae - bs, d2 = bs - as, d3 = be - as;
+    const double t0 = dot(d0, vb), t1 = dot(d1, vb), t2 = dot(d2, va), t3 = dot(d3, va);
+    const double inb = 1.0 / nb2, ina = 1.0 / na2;
+    double m = fmax(dot(d0, d0) - t0 * t0 * inb, 0.0);
+    m = fmax(m, dot(d1, d1) - t1 * t1 * inb);
+    m = fmax(m, dot(d2, d2) - t2 * t2 * ina);
+    m = fmax(m, dot(d3, d3) - t3 * t3 * ina);
+    Q2 = fmax(Q2, m * p.inv_sig_p2 * p.inv_sig_p2);
+  }
+  // thresholds of the two linkers are applied separately (each has its own score_th)
+  const double e3 = exp(-Q * 0.5), e2 = exp(-Q2 * 0.5);
+  if (e3 < c3.score_th || e2 < c2.score_th) return 0.0;
+  return smin(e3, e2);
+}
+
 // ---- pruning gates -----------------------------------------------------------------------------------
 // The reference decides every sub-test on exp(-(v/sigma)^2/2) >= score_th, i.e. v <= th. The gates below
 // only discard pairs that fail a sub-test by a margin far above the arithmetic error of the gate (fp32
@@ -568,25 +649,30 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
       __syncwarp();
       n1_total += n1;
       if (n1 == 0) continue;
-      // B2: fp64 margin gates of the 2d tests
-      int n2 = 0;
-      for (int kb = 0; kb < n1; kb += 32) {
-        const int k = kb + lane;
-        bool pass = false;
-        uint32_t e = 0;
-        if (k < n1) {
-          e = list1[k];
-          const int i = e >> 16, j = e & 0xffffu;
-          seg<vec3<double>> Li;
-          Li.s = mk3(sl.sx[i], sl.sy[i], sl.sz[i]);
-          Li.e = mk3(sl.ex[i], sl.ey[i], sl.ez[i]);
-          pass = gate2d(p, Li, sl, j, sl.ng[j] >> 16);
+      // B2 (only with the reference-structured scorer): fp64 margin gates of the 2d tests
+      int n2 = n1;
+      uint32_t *listS = list1;
+      if (!p.fast_forms) {
+        n2 = 0;
+        for (int kb = 0; kb < n1; kb += 32) {
+          const int k = kb + lane;
+          bool pass = false;
+          uint32_t e = 0;
+          if (k < n1) {
+            e = list1[k];
+            const int i = e >> 16, j = e & 0xffffu;
+            seg<vec3<double>> Li;
+            Li.s = mk3(sl.sx[i], sl.sy[i], sl.sz[i]);
+            Li.e = mk3(sl.ex[i], sl.ey[i], sl.ez[i]);
+            pass = gate2d(p, Li, sl, j, sl.ng[j] >> 16);
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, pass);
+          if (pass) list2[n2 + __popc(bal & lt_mask)] = e;
+          n2 += __popc(bal);
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (pass) list2[n2 + __popc(bal & lt_mask)] = e;
-        n2 += __popc(bal);
+        __syncwarp();
+        listS = list2;
       }
-      __syncwarp();
       n2_total += n2;
       // B3: exact reference scores; maximum per (row, image), summed per row (:97-112). Entries are ordered
       // by (row, image), so both reductions are segmented warp scans with a carry across batches.
@@ -597,15 +683,18 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         double sc = 0.0;
         uint32_t key = 0xfffffffeu, row = 0xfffffffeu; // key = row << 16 | view
         if (k < n2) {
-          const uint32_t e = list2[k];
+          const uint32_t e = listS[k];
           const int i = e >> 16, j = e & 0xffffu;
           const uint32_t vj = sl.ng[j] >> 16;
           row = (uint32_t)i;
           key = (row << 16) | vj;
-          seg<vec3<double>> Li;
-          Li.s = mk3(sl.sx[i], sl.sy[i], sl.sz[i]);
-          Li.e = mk3(sl.ex[i], sl.ey[i], sl.ez[i]);
-          sc = pair_score(p, Li, mk3(sl.dx[i], sl.dy[i], sl.dz[i]), sl.zs[i], sl.ze[i], sl, j, vj);
+          if (p.fast_forms) sc = pair_score_fast(p, sl, i, j, vj);
+          else {
+            seg<vec3<double>> Li;
+            Li.s = mk3(sl.sx[i], sl.sy[i], sl.sz[i]);
+            Li.e = mk3(sl.ex[i], sl.ey[i], sl.ez[i]);
+            sc = pair_score(p, Li, mk3(sl.dx[i], sl.dy[i], sl.dz[i]), sl.zs[i], sl.ze[i], sl, j, vj);
+          }
         }
         if (key == carry_key && carry_max > sc) sc = carry_max;
 #pragma unroll
@@ -617,7 +706,7 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         uint32_t knext = __shfl_down_sync(0xffffffffu, key, 1);
         if (lane == 31) {
           knext = 0xfffffffdu;
-          if (k + 1 < n2) { const uint32_t e2 = list2[k + 1]; knext = (e2 & 0xffff0000u) | (sl.ng[e2 & 0xffffu] >> 16); }
+          if (k + 1 < n2) { const uint32_t e2 = listS[k + 1]; knext = (e2 & 0xffff0000u) | (sl.ng[e2 & 0xffffu] >> 16); }
         }
         const bool seg_end = (k < n2) && (knext != key);
         // one image contributes its maximum once (:110-112): add the segment maxima to their row's total in

@@ -61,6 +61,10 @@ struct TriParams {
   double sin2_sens;       // sin^2(sensitivity_threshold); valid when sens_poly_ok
   int tri_poly_ok, sens_poly_ok; // thresholds inside (0, 90): the polynomial forms are equivalent
   int n_buckets;          // direction buckets over [0, pi) (1 = prefilter off)
+  // reduced-form scorer constants: 1/sigma of the angle / scale-invariance / perpendicular tests and the
+  // largest q = (v/sigma)^2 that can still reach score_th (with a 1e-9 margin)
+  int fast_forms;
+  double inv_sig_a3, inv_sig_s3, inv_sig_a2, inv_sig_p2, q_cut3;
   float bucket_scale;     // n_buckets / pi
 };
 
