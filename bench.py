@@ -280,30 +280,27 @@ def main():
     # ---- e2e through the public API with host buffers (rank-local; N=1 headline) -------------------
     e2e = None
     if not args.no_e2e:
-        pinned = {}
-        for i in my_ids:
-            ng, off, pairs = flat[i]
-            tp = torch.empty(pairs.shape, dtype=torch.int32, pin_memory=True)
-            tp.numpy()[...] = pairs
-            pinned[i] = (ng, off, tp.numpy(), tp)
+        bsrc, bng, boff, bpairs = scene.bulk_matches(my_ids)
+        tp = torch.empty(bpairs.shape, dtype=torch.int32, pin_memory=True)
+        tp.numpy()[...] = bpairs
+        pinned_pairs = tp.numpy()
         eng2 = TriEngine(cfg, device=local_rank)
         eng2.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         h2d = (scene.segs.nbytes + scene.kvec.nbytes + scene.qvec.nbytes + scene.tvec.nbytes +
-               scene.line_off.nbytes + sum(p[2].nbytes for p in pinned.values()))
+               scene.line_off.nbytes + pinned_pairs.nbytes)
+        nodes_out = torch.empty(int(scene.line_off[-1]) * NODE_RECORD_DTYPE.itemsize, dtype=torch.uint8,
+                                pin_memory=True).numpy().view(NODE_RECORD_DTYPE)
 
         def e2e_step():
+            # public API, bulk form: Init + SetRanges + TriangulateImage(all images) + run + results to host
             eng2.upload(scene)
             eng2.set_ranges(*scene.ranges)
-            for i in my_ids:
-                eng2.add_image_matches(i, pinned[i][0], pinned[i][1], pinned[i][2])
+            eng2.add_matches_bulk(bsrc, bng, boff, pinned_pairs)
             eng2.set_shard(per * rank, per * (rank + 1))
             s2 = eng2.run()
-            n_out = 0
-            for i in my_ids:
-                line, ng, nc = eng2.get_best(i)
-                off, edges = eng2.get_valid_edges(i)
-                n_out += line.nbytes + ng.nbytes + nc.nbytes + edges.nbytes
-            return s2, n_out
+            nodes = eng2.get_nodes(nodes_out)
+            off, edges = eng2.get_all_valid_edges()
+            return s2, nodes.nbytes + off.nbytes + edges.nbytes
 
         for _ in range(2):
             e2e_step()

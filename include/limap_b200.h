@@ -147,6 +147,17 @@ int lm_tri_import_edges(lm_ctx *ctx, int64_t n, const void *d_in /* int64[n][2] 
 /* first node index of a view (ascending img_id order) */
 int64_t lm_scene_node_offset(lm_ctx *ctx, int32_t view_index);
 
+/* ---- bulk forms of the calls above (same semantics, one call per scene instead of one per image) ------- */
+/* TriangulateImage for many images at once: block b holds the matches of (src_img_ids[b], ng_img_ids[b]) in
+ * pairs[row_off[b] .. row_off[b+1]). All blocks of one source image must be given in the same call. */
+int lm_tri_add_matches_bulk(lm_ctx *ctx, int32_t n_blocks, const int32_t *src_img_ids, const int32_t *ng_img_ids,
+                            const int64_t *row_off, const int32_t *pairs);
+/* All node records (lm_tri_num_nodes of them, node order = images ascending, lines ascending); ng_view in the
+ * record is the view index (position in the ascending image id list). */
+int lm_tri_get_nodes(lm_ctx *ctx, lm_node_record *out);
+/* All valid connections: node_off[n_nodes+1], edges[n][2] = (ng_img_id, ng_line_id). edges == NULL: count. */
+int64_t lm_tri_get_all_valid_edges(lm_ctx *ctx, int64_t *node_off, int32_t *edges);
+
 /* ComputeLineTracks (global_line_triangulator.cc:353-359): run_clustering (:234-291) +
  * ComputeLineTrackLabelsGreedy (merging/merging.cc:18-103) + Aggregator::aggregate_line3d_list
  * (merging/aggregator.cc:53-101). Returns the number of tracks (>= 0) or <0. */

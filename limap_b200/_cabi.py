@@ -75,6 +75,9 @@ _SIGS = {
     "lm_scene_node_offset": (C.c_int64, [_P, C.c_int32]),
     "lm_tri_build_tracks": (C.c_int64, [_P, C.POINTER(C.c_int64)]),
     "lm_tri_get_tracks": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "lm_tri_add_matches_bulk": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
+    "lm_tri_get_nodes": (C.c_int, [_P, _P]),
+    "lm_tri_get_all_valid_edges": (C.c_int64, [_P, _P, _P]),
     "lm_ba_solve": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lm_ba_get_stats": (C.c_int, [_P, _P]),
     "lm_vp_detect": (C.c_int64, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64]),

@@ -508,6 +508,77 @@ int lm_tri_add_image_matches_device(lm_ctx *c, int32_t img_id, int32_t n_ng, con
                                     const int64_t *row_off, const int32_t *d_pairs) {
   return add_matches_impl(c, img_id, n_ng, ng_ids, row_off, d_pairs, true);
 }
+int lm_tri_add_matches_bulk(lm_ctx *c, int32_t n_blocks, const int32_t *src_img_ids, const int32_t *ng_img_ids,
+                            const int64_t *row_off, const int32_t *pairs) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  if (!c->have_scene) return fail(LM_ERR_STATE, "lm_scene_upload must precede TriangulateImage");
+  if (c->any_exhaustive) return fail(LM_ERR_STATE, "cannot mix exhaustive and match-based triangulation in one run");
+  CU(cudaSetDevice(c->device));
+  const int64_t total = n_blocks > 0 ? row_off[n_blocks] : 0;
+  std::vector<char> seen_img(c->V, 0);
+  std::vector<MatchBlock> nb;
+  nb.reserve(n_blocks);
+  for (int b = 0; b < n_blocks; ++b) {
+    auto is = c->id2view.find(src_img_ids[b]), in_ = c->id2view.find(ng_img_ids[b]);
+    if (is == c->id2view.end() || in_ == c->id2view.end()) return fail(LM_ERR_INVALID, "unknown image id in matches");
+    if (c->image_added[is->second]) return fail(LM_ERR_STATE, "image " + std::to_string(src_img_ids[b]) + " was already triangulated");
+    if (row_off[b + 1] < row_off[b]) return fail(LM_ERR_INVALID, "row_off must be non-decreasing");
+    seen_img[is->second] = 1;
+    MatchBlock m;
+    m.src_view = is->second; m.ng_view = in_->second; m.n_rows = row_off[b + 1] - row_off[b];
+    m.pair_off = c->pairs_rows + row_off[b]; m.order = 0;
+    nb.push_back(m);
+  }
+  if ((size_t)(c->pairs_rows + total) * 8 > c->d_pairs.cap) {
+    DevBuf nbuf;
+    CU(nbuf.ensure(std::max<size_t>((size_t)(c->pairs_rows + total) * 8 * 2, 1 << 20)));
+    if (c->pairs_rows) CU(cudaMemcpyAsync(nbuf.p, c->d_pairs.p, c->pairs_rows * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->d_pairs.release();
+    c->d_pairs = nbuf;
+  }
+  if (total)
+    CU(cudaMemcpyAsync(c->d_pairs.as<char>() + c->pairs_rows * 8, pairs, total * 8, cudaMemcpyHostToDevice, c->stream));
+  c->blocks.insert(c->blocks.end(), nb.begin(), nb.end());
+  c->pairs_rows += total;
+  for (int v = 0; v < c->V; ++v) if (seen_img[v]) c->image_added[v] = 1;
+  c->any_matches = true;
+  c->ran = false;
+  return LM_OK;
+}
+
+int lm_tri_get_nodes(lm_ctx *c, lm_node_record *out) {
+  if (!c || !out) return fail(LM_ERR_INVALID, "NULL argument");
+  int rc = ensure_ran(c);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, c->d_nodes.p, sizeof(lm::NodeRecord) * c->n_nodes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int64_t lm_tri_get_all_valid_edges(lm_ctx *c, int64_t *node_off, int32_t *edges) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  int rc = ensure_ran(c);
+  if (rc) return rc;
+  if ((rc = fetch_edges(c))) return rc;
+  const int64_t nsh = c->node_end - c->node_begin;
+  if (node_off) {
+    for (int64_t n = 0; n <= c->n_nodes; ++n) {
+      int64_t v = 0;
+      if (n >= c->node_begin && n <= c->node_end) v = c->h_edge_off[n - c->node_begin];
+      else if (n > c->node_end) v = nsh > 0 ? c->h_edge_off[nsh] : 0;
+      node_off[n] = v;
+    }
+  }
+  const int64_t ne = (int64_t)c->h_edge_ng.size();
+  if (edges)
+    for (int64_t e = 0; e < ne; ++e) {
+      edges[2 * e] = c->img_ids[c->h_edge_ng[e] >> 16];
+      edges[2 * e + 1] = (int32_t)(c->h_edge_ng[e] & 0xffffu);
+    }
+  return ne;
+}
+
 int lm_tri_add_image_exhaustive(lm_ctx *c, int32_t img_id, int32_t n_ng, const int32_t *ng_ids) {
   if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
   if (!c->have_scene) return fail(LM_ERR_STATE, "lm_scene_upload must precede TriangulateImageExhaustiveMatch");

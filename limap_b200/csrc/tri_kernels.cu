@@ -119,9 +119,9 @@ LM_D int cmp_margin(double lhs, double rhs) {
 // Line3d::sensitivity(view) > th  (base/linebase.cc:100-107), decided without acos when clear:
 // 90 - acos|c| > th  <=>  |c| > sin(th).
 LM_D bool sensitivity_exceeds(const TriParams &p, const ViewD &v, vec3<double> Xs, vec3<double> Xe, vec3<double> dir_raw) {
-  const vec2<double> ps = dehom(proj_h(v.P, Xs));
-  const vec2<double> pe = dehom(proj_h(v.P, Xe));
-  const vec2<double> mid = (ps + pe) * 0.5;
+  const vec3<double> hs = proj_h(v.P, Xs), he = proj_h(v.P, Xe);
+  const double is = 1.0 / (hs.z + consts<double>::eps()), ie = 1.0 / (he.z + consts<double>::eps());
+  const vec2<double> mid = mk2((hs.x * is + he.x * ie) * 0.5, (hs.y * is + he.y * ie) * 0.5);
   const vec3<double> d3 = mat3_mul_h(v.M, mid.x, mid.y);
   const double t = dot(dir_raw, d3);
   const int cm = cmp_margin(t * t, p.sin2_sens * dot(dir_raw, dir_raw) * dot(d3, d3));
@@ -139,7 +139,13 @@ LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const Src &src, uin
   const vec2<double> s2 = mk2(l2.x, l2.y), e2 = mk2(l2.z, l2.w);
   const vec2<double> v2d = e2 - s2;
   const double len2sq = dot(v2d, v2d);
-  if (sqrt(len2sq) <= p.min_length_2d) return false; // :177
+  { // |l2| <= min_length_2d (:177), squared with an exact tie fallback
+    const double m2 = p.min_length_2d * p.min_length_2d;
+    if (p.min_length_2d >= 0.0) {
+      if (len2sq <= m2 * (1.0 - 1e-12)) return false;
+      if (len2sq < m2 * (1.0 + 1e-12) && sqrt(len2sq) <= p.min_length_2d) return false;
+    }
+  }
   if (p.disable_algebraic) return false;
   const ViewD &v2 = p.views[ngv];
   const vec3<double> c2s = mat3_mul_h(v2.M, l2.x, l2.y);
@@ -166,16 +172,17 @@ LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const Src &src, uin
   {
     const vec3<double> base = src.C1 - C2;
     const vec3<double> l2h = cross(mk3(l2.x, l2.y, 1.0), mk3(l2.z, l2.w, 1.0));
-    const double nl = norm(l2h);
+    const double nl2 = dot(l2h, l2h);
     const vec3<double> eps_ = mat3T_mul(v2.M, cross(base, src.w1s));
     const vec3<double> hs = cross(l2h, eps_);
-    const double ws = hs.z + consts<double>::eps() * nl * norm(eps_);
+    const double ws = 1.0 / (hs.z + consts<double>::eps() * sqrt(nl2 * dot(eps_, eps_)));
     const vec3<double> epe_ = mat3T_mul(v2.M, cross(base, src.w1e));
     const vec3<double> he = cross(l2h, epe_);
-    const double we = he.z + consts<double>::eps() * nl * norm(epe_);
-    const vec2<double> cs = mk2(hs.x / ws, hs.y / ws), ce = mk2(he.x / we, he.y / we);
-    double c1 = dot(cs - s2, v2d) / len2sq;
-    double c2 = dot(ce - s2, v2d) / len2sq;
+    const double we = 1.0 / (he.z + consts<double>::eps() * sqrt(nl2 * dot(epe_, epe_)));
+    const vec2<double> cs = mk2(hs.x * ws, hs.y * ws), ce = mk2(he.x * we, he.y * we);
+    const double il2 = 1.0 / len2sq;
+    double c1 = dot(cs - s2, v2d) * il2;
+    double c2 = dot(ce - s2, v2d) * il2;
     if (c1 > c2) { double t = c1; c1 = c2; c2 = t; }
     double IoU = (smin(c2, 1.0) - smax(c1, 0.0)) / (smax(c2, 1.0) - smin(c1, 0.0));
     if (fabs(IoU - p.IoU_threshold) < 1e-7) {
@@ -556,7 +563,9 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
       for (int k = 0; k < NS; ++k) {
         if (!oks[k]) continue;
         const Cand &c = cs[k];
-        const vec3<double> d = normalized(c.e - c.s);
+        const vec3<double> dr = c.e - c.s;
+        const double dn2 = dot(dr, dr);
+        const vec3<double> d = (dn2 > 0.0) ? dr * (1.0 / sqrt(dn2)) : dr;
         sl.sx[idx] = c.s.x; sl.sy[idx] = c.s.y; sl.sz[idx] = c.s.z;
         sl.ex[idx] = c.e.x; sl.ey[idx] = c.e.y; sl.ez[idx] = c.e.z;
         sl.dx[idx] = d.x; sl.dy[idx] = d.y; sl.dz[idx] = d.z;
@@ -568,7 +577,7 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         const vec3<double> rs = c.s - src.C1, re = c.e - src.C1;
         // scale-invariance limit th * (z + EPS) widened by 0.5% plus 1e-5 of the coordinate magnitude
         // (fp32 rounding of the two endpoints is < 1e-6 of it); see DESIGN.md "gates"
-        const double rad = fmax(norm(rs), norm(re));
+        const double rad = sqrt(fmax(dot(rs, rs), dot(re, re)));
         const double ls = p.l3d.th_scaleinv * (c.zs + consts<double>::eps()) * 1.005 + 1e-5 * rad;
         const double le = p.l3d.th_scaleinv * (c.ze + consts<double>::eps()) * 1.005 + 1e-5 * rad;
         GateRec g;

@@ -100,6 +100,32 @@ class TriEngine:
         pairs = np.concatenate(parts, 0) if parts else np.zeros((0, 2), np.int32)
         self.add_image_matches(img_id, np.asarray(ngs, np.int32), row_off, pairs)
 
+    def add_matches_bulk(self, src_ids, ng_ids, row_off, pairs):
+        """Many (image, neighbour) match tables in one call (lm_tri_add_matches_bulk)."""
+        src_ids = np.ascontiguousarray(src_ids, np.int32)
+        ng_ids = np.ascontiguousarray(ng_ids, np.int32)
+        row_off = np.ascontiguousarray(row_off, np.int64)
+        pairs = np.ascontiguousarray(pairs, np.int32)
+        self.ctx._keep.append(pairs)
+        check(lib().lm_tri_add_matches_bulk(self.ctx.handle, len(src_ids), ptr(src_ids), ptr(ng_ids), ptr(row_off),
+                                            ptr(pairs)))
+
+    def get_nodes(self, out=None):
+        """All node records as a structured array (NODE_RECORD_DTYPE)."""
+        n = int(self.line_off[-1])
+        if out is None:
+            out = np.zeros(n, _cabi.NODE_RECORD_DTYPE)
+        check(lib().lm_tri_get_nodes(self.ctx.handle, ptr(out)))
+        return out
+
+    def get_all_valid_edges(self):
+        n = int(self.line_off[-1])
+        off = np.zeros(n + 1, np.int64)
+        ne = check(lib().lm_tri_get_all_valid_edges(self.ctx.handle, ptr(off), None))
+        edges = np.zeros((max(ne, 1), 2), np.int32)
+        check(lib().lm_tri_get_all_valid_edges(self.ctx.handle, ptr(off), ptr(edges)))
+        return off, edges[:ne]
+
     def add_image_exhaustive(self, img_id, neighbors):
         ng = np.ascontiguousarray(neighbors, np.int32)
         check(lib().lm_tri_add_image_exhaustive(self.ctx.handle, int(img_id), len(ng), ptr(ng)))

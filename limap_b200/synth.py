@@ -41,6 +41,21 @@ class Scene:
     def lines_of(self, view):
         return self.segs[self.line_off[view]:self.line_off[view + 1]]
 
+    def bulk_matches(self, img_ids=None):
+        """(src_ids[b], ng_ids[b], row_off[b+1], pairs[rows,2]) over all (image, neighbour) blocks."""
+        ids = sorted(self.matches.keys()) if img_ids is None else list(img_ids)
+        src, ng, off, parts = [], [], [0], []
+        for i in ids:
+            for g in sorted(self.matches[i].keys()):
+                m = self.matches[i][g]
+                src.append(i)
+                ng.append(g)
+                off.append(off[-1] + len(m))
+                parts.append(m)
+        pairs = np.concatenate(parts, 0) if parts else np.zeros((0, 2), np.int32)
+        return (np.asarray(src, np.int32), np.asarray(ng, np.int32), np.asarray(off, np.int64),
+                np.ascontiguousarray(pairs, dtype=np.int32))
+
     def flat_matches(self, img_id):
         """(ng_ids[n], row_off[n+1], pairs[rows,2]) of one image, neighbours ascending (std::map order)."""
         m = self.matches[img_id]
