@@ -290,6 +290,8 @@ def main():
                scene.line_off.nbytes + pinned_pairs.nbytes)
         nodes_out = torch.empty(int(scene.line_off[-1]) * NODE_RECORD_DTYPE.itemsize, dtype=torch.uint8,
                                 pin_memory=True).numpy().view(NODE_RECORD_DTYPE)
+        off_out = torch.empty(int(scene.line_off[-1]) + 1, dtype=torch.int64, pin_memory=True).numpy()
+        edges_out = torch.empty((max(int(st["n_valid_edges"]) * 2, 1), 2), dtype=torch.int32, pin_memory=True).numpy()
 
         def e2e_step():
             # public API, bulk form: Init + SetRanges + TriangulateImage(all images) + run + results to host
@@ -299,7 +301,7 @@ def main():
             eng2.set_shard(per * rank, per * (rank + 1))
             s2 = eng2.run()
             nodes = eng2.get_nodes(nodes_out)
-            off, edges = eng2.get_all_valid_edges()
+            off, edges = eng2.get_all_valid_edges(off_out, edges_out)
             return s2, nodes.nbytes + off.nbytes + edges.nbytes
 
         for _ in range(2):

@@ -108,6 +108,10 @@ int lm_tri_clear(lm_ctx *ctx);
 /* Restrict the next lm_tri_run to source images with view index in [begin, end) of the ascending
  * img_id order (multi-GPU sharding by source image). Default: all. */
 int lm_tri_set_shard(lm_ctx *ctx, int32_t view_begin, int32_t view_end);
+/* Split lm_tri_run into n groups of whole source images (default 1): sort + node kernel of group g are issued as
+ * soon as the match chunks of its images have arrived on the copy stream, so they can run under the upload of
+ * the later groups. Results do not depend on n (nodes are independent). */
+int lm_tri_set_pipeline_groups(lm_ctx *ctx, int32_t n_groups);
 
 /* Candidate generation + scoring + selection for every enqueued image:
  * triangulateOneNode (base_line_triangulator.cc:161-337) + scoreOneNode

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
@@ -114,6 +115,16 @@ struct lm_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  // match uploads run on their own stream so that a run can start on the first source images while the rest
+  // of the tables is still crossing PCIe
+  cudaStream_t copy_stream = nullptr;
+  struct CopyChunk { int64_t row_end; cudaEvent_t ev; };
+  std::vector<CopyChunk> chunks;
+  std::vector<cudaEvent_t> event_pool;
+  double node_kernel_ms_acc = 0;
+  DevBuf d_raw_blocks, d_bkey, d_bkey2, d_bval, d_bval2, d_blk_rows; // device mirror of `blocks` + sort scratch
+  int64_t raw_uploaded = 0;
+  cudaEvent_t ev_raw = nullptr; // recorded on the copy stream after the latest descriptor upload
   int sm_count = 148;
   int max_smem_optin = 0;
   // scene
@@ -125,7 +136,7 @@ struct lm_ctx {
   std::vector<double> h_segs; // after add_halfpix
   std::vector<double> h_segs_raw;
   int64_t n_nodes = 0;
-  DevBuf d_views, d_segs, d_node_view, d_line_off;
+  DevBuf d_views, d_segs, d_node_view, d_line_off, d_img_ids, d_host_edges;
   // config
   bool have_cfg = false;
   lm_tri_config cfg;
@@ -143,6 +154,7 @@ struct lm_ctx {
   int64_t pairs_rows = 0;
   bool any_exhaustive = false, any_matches = false;
   int shard_begin = 0, shard_end = -1;
+  int pipeline_groups = 1; // lm_tri_set_pipeline_groups
   // run buffers
   DevBuf d_blk_row_off, d_blk_src, d_blk_ng, d_blk_pair_off;
   DevBuf d_key, d_key2, d_val, d_val2, d_sort_tmp;
@@ -257,6 +269,7 @@ int lm_ctx_create(int device, lm_ctx **out) {
   CU(cudaEventCreate(&c->ev1));
   CU(cudaEventCreate(&c->evk0));
   CU(cudaEventCreate(&c->evk1));
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   memset(&c->stats, 0, sizeof(c->stats));
@@ -269,16 +282,20 @@ void lm_ctx_destroy(lm_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf *bufs[] = {&c->d_views, &c->d_segs, &c->d_node_view, &c->d_line_off, &c->d_pairs, &c->d_blk_row_off,
+  DevBuf *bufs[] = {&c->d_img_ids, &c->d_host_edges, &c->d_views, &c->d_segs, &c->d_node_view, &c->d_line_off, &c->d_pairs, &c->d_blk_row_off,
                     &c->d_blk_src, &c->d_blk_ng, &c->d_blk_pair_off, &c->d_key, &c->d_key2, &c->d_val, &c->d_val2,
                     &c->d_sort_tmp, &c->d_node_row_off, &c->d_scalars, &c->d_nodes, &c->d_row_state, &c->d_row_cand,
                     &c->d_slab, &c->d_edges, &c->d_edges2, &c->d_edge_keys, &c->d_edge_keys2, &c->d_edge_w,
-                    &c->d_edge_cnt, &c->d_nvalid, &c->d_edge_off, &c->d_edge_ng, &c->d_ba_in, &c->d_ba_blocks, &c->d_ba_out, &c->d_vp_label, &c->d_vp_voff, &c->d_vp_vps, &c->d_vp_pts, &c->d_vp_off, &c->d_vp_labels, &c->d_vp_nc, &c->d_vp_ps, &c->d_vp_mat};
+                    &c->d_edge_cnt, &c->d_nvalid, &c->d_edge_off, &c->d_edge_ng, &c->d_ba_in, &c->d_ba_blocks, &c->d_ba_out, &c->d_raw_blocks, &c->d_bkey, &c->d_bkey2, &c->d_bval, &c->d_bval2, &c->d_blk_rows, &c->d_vp_label, &c->d_vp_voff, &c->d_vp_vps, &c->d_vp_pts, &c->d_vp_off, &c->d_vp_labels, &c->d_vp_nc, &c->d_vp_ps, &c->d_vp_mat};
   for (DevBuf *b : bufs) b->release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->evk0) cudaEventDestroy(c->evk0);
   if (c->evk1) cudaEventDestroy(c->evk1);
+  if (c->ev_raw) cudaEventDestroy(c->ev_raw);
+  for (auto &ch : c->chunks) cudaEventDestroy(ch.ev);
+  for (auto e : c->event_pool) cudaEventDestroy(e);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -295,6 +312,7 @@ int lm_ctx_set_stream(lm_ctx *c, void *s) {
 int lm_ctx_synchronize(lm_ctx *c) {
   if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
   CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->copy_stream));
   return sync_stream(c);
 }
 
@@ -359,6 +377,8 @@ int lm_scene_upload(lm_ctx *c, int32_t n_views, const int32_t *img_ids, const in
   if (c->n_nodes)
     CU(cudaMemcpyAsync(c->d_node_view.p, node_view.data(), 2 * c->n_nodes, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_line_off.p, c->line_off.data(), 8 * (n_views + 1), cudaMemcpyHostToDevice, c->stream));
+  CU(c->d_img_ids.ensure(4 * n_views));
+  CU(cudaMemcpyAsync(c->d_img_ids.p, c->img_ids.data(), 4 * n_views, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream)); // host vectors above go out of scope
   c->have_scene = true;
   int rc = upload_segs(c);
@@ -436,8 +456,12 @@ int lm_tri_set_vps(lm_ctx *c, int32_t n_images, const int32_t *img_ids, const in
 int lm_tri_clear(lm_ctx *c) {
   if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
   c->blocks.clear();
+  c->raw_uploaded = 0;
   std::fill(c->image_added.begin(), c->image_added.end(), 0);
   std::fill(c->image_norder.begin(), c->image_norder.end(), 0);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  for (auto &ch : c->chunks) c->event_pool.push_back(ch.ev);
+  c->chunks.clear();
   c->pairs_rows = 0;
   c->any_exhaustive = c->any_matches = false;
   c->ran = false;
@@ -447,11 +471,75 @@ int lm_tri_clear(lm_ctx *c) {
   c->graph_nodes.clear();
   return LM_OK;
 }
+int lm_tri_set_pipeline_groups(lm_ctx *c, int32_t n) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  if (n < 1 || n > 64) return fail(LM_ERR_INVALID, "pipeline groups must be in [1, 64]");
+  c->pipeline_groups = n;
+  return LM_OK;
+}
+
 int lm_tri_set_shard(lm_ctx *c, int32_t b, int32_t e) {
   if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
   c->shard_begin = b;
   c->shard_end = e;
   c->ran = false;
+  return LM_OK;
+}
+
+// Mirror the block descriptors added since the last call on the device (copy stream, ahead of their matches).
+static int upload_raw_blocks(lm_ctx *c) {
+  const int64_t n = (int64_t)c->blocks.size();
+  if (n <= c->raw_uploaded) return LM_OK;
+  if ((size_t)n * sizeof(lm::RawBlock) > c->d_raw_blocks.cap) {
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->stream));
+    DevBuf nbuf;
+    CU(nbuf.ensure(std::max<size_t>((size_t)n * sizeof(lm::RawBlock) * 2, 1 << 16)));
+    if (c->raw_uploaded)
+      CU(cudaMemcpy(nbuf.p, c->d_raw_blocks.p, c->raw_uploaded * sizeof(lm::RawBlock), cudaMemcpyDeviceToDevice));
+    c->d_raw_blocks.release();
+    c->d_raw_blocks = nbuf;
+  }
+  std::vector<lm::RawBlock> tmp(n - c->raw_uploaded);
+  for (int64_t i = c->raw_uploaded; i < n; ++i) {
+    const MatchBlock &b = c->blocks[i];
+    lm::RawBlock &r = tmp[i - c->raw_uploaded];
+    r.src_view = b.src_view; r.ng_view = b.ng_view; r.n_rows = b.n_rows; r.pair_off = b.pair_off; r.order = b.order; r.pad = 0;
+  }
+  // pageable source: the runtime stages it, so `tmp` may die at scope exit
+  CU(cudaMemcpyAsync(c->d_raw_blocks.as<lm::RawBlock>() + c->raw_uploaded, tmp.data(), tmp.size() * sizeof(lm::RawBlock),
+                     cudaMemcpyHostToDevice, c->copy_stream));
+  if (!c->ev_raw) CU(cudaEventCreateWithFlags(&c->ev_raw, cudaEventDisableTiming));
+  CU(cudaEventRecord(c->ev_raw, c->copy_stream));
+  c->raw_uploaded = n;
+  return LM_OK;
+}
+
+// Upload `total` match rows into the device store in chunks, one event per chunk, on the copy stream.
+static int upload_pairs(lm_ctx *c, const int32_t *pairs, int64_t total, bool on_device) {
+  if ((size_t)(c->pairs_rows + total) * 8 > c->d_pairs.cap) {
+    CU(cudaStreamSynchronize(c->copy_stream));
+    DevBuf nbuf;
+    CU(nbuf.ensure(std::max<size_t>((size_t)(c->pairs_rows + total) * 8 * 2, 1 << 20)));
+    if (c->pairs_rows) CU(cudaMemcpyAsync(nbuf.p, c->d_pairs.p, c->pairs_rows * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->d_pairs.release();
+    c->d_pairs = nbuf;
+  }
+  const int64_t kChunk = 2 << 20, kEventEvery = 1; // 16 MB copies, one event each
+  int64_t k = 0;
+  for (int64_t o = 0; o < total; o += kChunk, ++k) {
+    const int64_t n = std::min(kChunk, total - o);
+    CU(cudaMemcpyAsync(c->d_pairs.as<char>() + (c->pairs_rows + o) * 8, pairs + 2 * o, n * 8,
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->copy_stream));
+    if ((k + 1) % kEventEvery == 0 || o + n >= total) {
+      cudaEvent_t ev;
+      if (!c->event_pool.empty()) { ev = c->event_pool.back(); c->event_pool.pop_back(); }
+      else CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      CU(cudaEventRecord(ev, c->copy_stream));
+      c->chunks.push_back({c->pairs_rows + o + n, ev});
+    }
+  }
   return LM_OK;
 }
 
@@ -473,18 +561,6 @@ static int add_matches_impl(lm_ctx *c, int32_t img_id, int32_t n_ng, const int32
     if (!seen.insert(ng_ids[g]).second) return fail(LM_ERR_INVALID, "duplicate neighbor id in one TriangulateImage call");
     if (row_off[g + 1] < row_off[g]) return fail(LM_ERR_INVALID, "row_off must be non-decreasing");
   }
-  // grow the device pairs store (amortised doubling, old content preserved)
-  if ((size_t)(c->pairs_rows + total) * 8 > c->d_pairs.cap) {
-    DevBuf nb;
-    CU(nb.ensure(std::max<size_t>((size_t)(c->pairs_rows + total) * 8 * 2, 1 << 20)));
-    if (c->pairs_rows) CU(cudaMemcpyAsync(nb.p, c->d_pairs.p, c->pairs_rows * 8, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    c->d_pairs.release();
-    c->d_pairs = nb;
-  }
-  if (total)
-    CU(cudaMemcpyAsync(c->d_pairs.as<char>() + c->pairs_rows * 8, pairs, total * 8,
-                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   for (int g = 0; g < n_ng; ++g) {
     MatchBlock b;
     b.src_view = sv;
@@ -493,6 +569,11 @@ static int add_matches_impl(lm_ctx *c, int32_t img_id, int32_t n_ng, const int32
     b.pair_off = c->pairs_rows + row_off[g];
     b.order = 0; // std::map order = ascending neighbour id (base_line_triangulator.cc:74)
     c->blocks.push_back(b);
+  }
+  {
+    int rc_ = upload_raw_blocks(c);
+    if (!rc_) rc_ = upload_pairs(c, pairs, total, on_device);
+    if (rc_) return rc_;
   }
   c->pairs_rows += total;
   c->image_added[sv] = 1;
@@ -529,17 +610,12 @@ int lm_tri_add_matches_bulk(lm_ctx *c, int32_t n_blocks, const int32_t *src_img_
     m.pair_off = c->pairs_rows + row_off[b]; m.order = 0;
     nb.push_back(m);
   }
-  if ((size_t)(c->pairs_rows + total) * 8 > c->d_pairs.cap) {
-    DevBuf nbuf;
-    CU(nbuf.ensure(std::max<size_t>((size_t)(c->pairs_rows + total) * 8 * 2, 1 << 20)));
-    if (c->pairs_rows) CU(cudaMemcpyAsync(nbuf.p, c->d_pairs.p, c->pairs_rows * 8, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    c->d_pairs.release();
-    c->d_pairs = nbuf;
-  }
-  if (total)
-    CU(cudaMemcpyAsync(c->d_pairs.as<char>() + c->pairs_rows * 8, pairs, total * 8, cudaMemcpyHostToDevice, c->stream));
   c->blocks.insert(c->blocks.end(), nb.begin(), nb.end());
+  {
+    int rc_ = upload_raw_blocks(c);
+    if (!rc_) rc_ = upload_pairs(c, pairs, total, false);
+    if (rc_) return rc_;
+  }
   c->pairs_rows += total;
   for (int v = 0; v < c->V; ++v) if (seen_img[v]) c->image_added[v] = 1;
   c->any_matches = true;
@@ -560,22 +636,20 @@ int64_t lm_tri_get_all_valid_edges(lm_ctx *c, int64_t *node_off, int32_t *edges)
   if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
   int rc = ensure_ran(c);
   if (rc) return rc;
-  if ((rc = fetch_edges(c))) return rc;
+  const int64_t ne = c->stats.n_valid_edges;
+  if (!node_off && !edges) return ne;
+  // converted on the device and copied straight into the caller's buffers (pinned buffers avoid staging)
   const int64_t nsh = c->node_end - c->node_begin;
-  if (node_off) {
-    for (int64_t n = 0; n <= c->n_nodes; ++n) {
-      int64_t v = 0;
-      if (n >= c->node_begin && n <= c->node_end) v = c->h_edge_off[n - c->node_begin];
-      else if (n > c->node_end) v = nsh > 0 ? c->h_edge_off[nsh] : 0;
-      node_off[n] = v;
-    }
-  }
-  const int64_t ne = (int64_t)c->h_edge_ng.size();
-  if (edges)
-    for (int64_t e = 0; e < ne; ++e) {
-      edges[2 * e] = c->img_ids[c->h_edge_ng[e] >> 16];
-      edges[2 * e + 1] = (int32_t)(c->h_edge_ng[e] & 0xffffu);
-    }
+  const size_t off_bytes = 8 * (size_t)(c->n_nodes + 1), pair_bytes = 8 * (size_t)std::max<int64_t>(ne, 1);
+  CU(c->d_host_edges.ensure(off_bytes + pair_bytes + 256));
+  int64_t *d_off = c->d_host_edges.as<int64_t>();
+  int32_t *d_pairs = reinterpret_cast<int32_t *>(c->d_host_edges.as<char>() + ((off_bytes + 255) / 256) * 256);
+  lm::launch_edges_for_host(c->d_edge_off.as<uint32_t>(), c->d_edge_ng.as<uint32_t>(), c->d_img_ids.as<int32_t>(), nsh,
+                            ne, c->node_begin, c->n_nodes, d_off, d_pairs, c->stream);
+  c->stats.n_kernel_launches += 1;
+  if (node_off) CU(cudaMemcpyAsync(node_off, d_off, off_bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (edges && ne) CU(cudaMemcpyAsync(edges, d_pairs, 8 * (size_t)ne, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return ne;
 }
 
@@ -602,7 +676,7 @@ int lm_tri_add_image_exhaustive(lm_ctx *c, int32_t img_id, int32_t n_ng, const i
   c->image_added[sv] = 1;
   c->any_exhaustive = true;
   c->ran = false;
-  return LM_OK;
+  return upload_raw_blocks(c);
 }
 
 int lm_tri_run(lm_ctx *c) {
@@ -641,8 +715,8 @@ int lm_tri_run(lm_ctx *c) {
   c->tracks.clear();
 
   CU(c->d_blk_row_off.ensure(8 * (nb + 1)));
-  CU(c->d_blk_src.ensure(4 * std::max(nb, 1)));
-  CU(c->d_blk_ng.ensure(4 * std::max(nb, 1)));
+  CU(c->d_blk_src.ensure(4 * std::max(nb + 1, 2)));
+  CU(c->d_blk_ng.ensure(4 * std::max(nb + 1, 2)));
   CU(c->d_blk_pair_off.ensure(8 * std::max(nb, 1)));
   CU(c->d_key.ensure(4 * std::max<int64_t>(n_rows, 1)));
   CU(c->d_key2.ensure(4 * std::max<int64_t>(n_rows, 1)));
@@ -657,64 +731,45 @@ int lm_tri_run(lm_ctx *c) {
   if (c->cfg.debug_mode) CU(c->d_row_cand.ensure(80 * std::max<int64_t>(n_rows * ns, 1)));
 
   CU(cudaEventRecord(c->ev0, s));
-  CU(cudaMemsetAsync(c->d_scalars.p, 0, 64, s));
-  CU(cudaMemcpyAsync(c->d_blk_row_off.p, row_off.data(), 8 * (nb + 1), cudaMemcpyHostToDevice, s));
-  if (nb) {
-    CU(cudaMemcpyAsync(c->d_blk_src.p, bsrc.data(), 4 * nb, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(c->d_blk_ng.p, bng.data(), 4 * nb, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(c->d_blk_pair_off.p, pair_off.data(), 8 * nb, cudaMemcpyHostToDevice, s));
+  lm::launch_zero_words(c->d_scalars.p, 16, s);
+  // block tables, derived on the device from the descriptors uploaded with the matches (no transfer now)
+  {
+    const int n_all = (int)c->blocks.size();
+    CU(c->d_blk_rows.ensure(8 * (nb + 2)));
+    if (n_all) {
+      CU(c->d_bkey.ensure(4 * n_all)); CU(c->d_bkey2.ensure(4 * n_all));
+      CU(c->d_bval.ensure(4 * n_all)); CU(c->d_bval2.ensure(4 * n_all));
+      // the descriptors travel on the copy stream ahead of their matches (bulk add: ahead of all matches)
+      if (c->ev_raw) CU(cudaStreamWaitEvent(s, c->ev_raw, 0));
+      lm::launch_block_keys(c->d_raw_blocks.as<lm::RawBlock>(), n_all, vb, ve, exhaustive ? 1 : 0, c->d_bkey.as<uint32_t>(),
+                            c->d_bval.as<uint32_t>(), s);
+      cub::DoubleBuffer<uint32_t> bk(c->d_bkey.as<uint32_t>(), c->d_bkey2.as<uint32_t>());
+      cub::DoubleBuffer<uint32_t> bv(c->d_bval.as<uint32_t>(), c->d_bval2.as<uint32_t>());
+      size_t tmpb = 0;
+      CU(cub::DeviceRadixSort::SortPairs(nullptr, tmpb, bk, bv, n_all, 0, 32, s));
+      CU(c->d_sort_tmp.ensure(tmpb));
+      CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, tmpb, bk, bv, n_all, 0, 32, s));
+      lm::launch_block_gather(c->d_raw_blocks.as<lm::RawBlock>(), bv.Current(), nb, c->d_blk_src.as<int32_t>(),
+                              c->d_blk_ng.as<int32_t>(), c->d_blk_pair_off.as<int64_t>(), c->d_blk_rows.as<int64_t>(), s);
+    } else {
+      lm::launch_zero_words(c->d_blk_rows.p, 4, s);
+    }
+    size_t tmps = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmps, c->d_blk_rows.as<int64_t>(), c->d_blk_row_off.as<int64_t>(), nb + 1, s));
+    CU(c->d_sort_tmp.ensure(tmps));
+    CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmps, c->d_blk_rows.as<int64_t>(), c->d_blk_row_off.as<int64_t>(),
+                                     nb + 1, s));
   }
   unsigned int *d_max_rows = c->d_scalars.as<unsigned int>();
   int *d_err = c->d_scalars.as<int>() + 1;
   unsigned long long *d_counters = reinterpret_cast<unsigned long long *>(c->d_scalars.as<char>() + 16);
   int launches = 0;
-  if (n_rows) {
-    if (exhaustive)
-      lm::launch_expand_exhaustive(c->d_blk_row_off.as<int64_t>(), c->d_blk_src.as<int32_t>(), c->d_blk_ng.as<int32_t>(),
-                                   nb, c->d_line_off.as<int64_t>(), n_rows, c->d_key.as<uint32_t>(),
-                                   c->d_val.as<uint32_t>(), s);
-    else
-      lm::launch_expand_rows(c->d_pairs.as<int32_t>(), c->d_blk_row_off.as<int64_t>(), c->d_blk_src.as<int32_t>(),
-                             c->d_blk_ng.as<int32_t>(), c->d_blk_pair_off.as<int64_t>(), nb,
-                             c->d_line_off.as<int64_t>(), n_rows, c->d_key.as<uint32_t>(), c->d_val.as<uint32_t>(),
-                             d_err, s);
-    ++launches;
-    // stable LSD radix sort by node id keeps (neighbour, row) order inside every node
-    int nbits = 1;
-    while (((int64_t)1 << nbits) < c->n_nodes) ++nbits;
-    cub::DoubleBuffer<uint32_t> dk(c->d_key.as<uint32_t>(), c->d_key2.as<uint32_t>());
-    cub::DoubleBuffer<uint32_t> dv(c->d_val.as<uint32_t>(), c->d_val2.as<uint32_t>());
-    size_t tmp = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)n_rows, 0, nbits, s));
-    CU(c->d_sort_tmp.ensure(tmp));
-    CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, tmp, dk, dv, (int)n_rows, 0, nbits, s));
-    launches += (nbits + 7) / 8 + 1;
-    c->sorted_key = dk.Current();
-    c->sorted_val = dv.Current();
-  } else {
-    c->sorted_key = c->d_key.as<uint32_t>();
-    c->sorted_val = c->d_val.as<uint32_t>();
-  }
-  lm::launch_node_offsets(c->sorted_key, n_rows, c->n_nodes, c->d_node_row_off.as<uint32_t>(), d_max_rows, s);
-  ++launches;
-  // the shared-memory staging area is sized from the largest node (one 8-byte read-back)
-  unsigned int hs[2] = {0, 0};
-  CU(cudaMemcpyAsync(hs, c->d_scalars.p, 8, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  if (hs[1] == 1)
-    return fail(LM_ERR_INVALID, "IndexError! Out-of-index matches exist (line_id >= number of lines of the image). "
-                                "Please make sure you are reusing the correct descriptors and matches.");
-  if (hs[1] == 2) return fail(LM_ERR_INVALID, "IndexError! Out-of-index neighbor line id in matches.");
-  const int max_rows = (int)hs[0];
-  c->stats.max_rows_per_node = max_rows;
-
   lm::TriParams p;
   memset(&p, 0, sizeof(p));
   p.views = c->d_views.as<lm::ViewD>();
   p.segs = c->d_segs.as<double4>();
   p.node_view = c->d_node_view.as<uint16_t>();
   p.line_off = c->d_line_off.as<int64_t>();
-  p.row_ng = c->sorted_val;
   p.node_row_off = c->d_node_row_off.as<uint32_t>();
   p.nodes = c->d_nodes.as<lm::NodeRecord>();
   p.row_state = c->d_row_state.as<uint8_t>();
@@ -764,33 +819,118 @@ int lm_tri_run(lm_ctx *c) {
     p.inv_sig_p2 = 1.0 / (p.l2d.th_perp * p.l2d.mult);
     p.q_cut3 = -2.0 * std::log(p.l3d.score_th) * (1.0 + 1e-9);
   }
-  if ((int64_t)max_rows * ns > 65535) return fail(LM_ERR_INVALID, "more than 65535 candidates possible for one 2D line");
-  int cap = 32;
-  while (cap < max_rows * ns) cap += 32;
-  size_t smem = lm::tri_smem_bytes(cap);
+  // ---- groups of source images: sort + node kernel of group g overlap the upload of group g+1 -----------
+  int nbits = 1;
+  while (((int64_t)1 << nbits) < c->n_nodes) ++nbits;
+  // canonical sorted buffers: d_key2 / d_val2
+  c->sorted_key = c->d_key2.as<uint32_t>();
+  c->sorted_val = c->d_val2.as<uint32_t>();
+  p.row_ng = c->sorted_val;
+  const int n_groups = exhaustive ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(c->pipeline_groups, n_rows >> 16));
+  int max_rows_all = 0;
+  c->node_kernel_ms_acc = 0;
+  int bg0 = 0, gv0 = vb;
   const int64_t n_shard_nodes = c->node_end - c->node_begin;
-  int grid;
-  const size_t smem_limit = (size_t)std::max(0, c->max_smem_optin - 1024);
-  if (smem <= smem_limit) {
-    p.use_slab = 0;
-    p.cap = cap;
-    grid = (int)std::min<int64_t>(n_shard_nodes, (int64_t)1 << 30);
-  } else {
-    // nodes larger than shared memory (exhaustive matching): persistent CTAs with a global staging slab
-    p.use_slab = 1;
-    p.cap = cap;
-    grid = (int)std::min<int64_t>(n_shard_nodes, (int64_t)c->sm_count * 4);
-    p.slab_stride = (int64_t)((smem + 255) / 256 * 256);
-    CU(c->d_slab.ensure((size_t)p.slab_stride * grid));
-    p.slab = c->d_slab.as<char>();
-    smem = 0;
-  }
-  CU(cudaEventRecord(c->evk0, s));
-  if (n_shard_nodes > 0) {
-    lm::launch_tri_node_kernel(p, grid, 128, smem, s);
+  for (int g = 0; g < n_groups; ++g) {
+    // blocks [bg0, bg1) with whole source images, views [gv0, gv1)
+    int bg1 = nb, gv1 = ve;
+    if (g + 1 < n_groups) {
+      const int64_t target = n_rows * (g + 1) / n_groups;
+      bg1 = bg0;
+      while (bg1 < nb && row_off[bg1] < target) ++bg1;
+      while (bg1 < nb && bg1 > 0 && blk[bg1].src_view == blk[bg1 - 1].src_view) ++bg1; // finish the image
+      gv1 = (bg1 < nb) ? blk[bg1].src_view : ve;
+    }
+    const int64_t rb = row_off[bg0], re = row_off[bg1];
+    const int64_t node_lo = c->line_off[gv0], node_hi = c->line_off[gv1];
+    if (!exhaustive && re > rb) {
+      int64_t need = 0;
+      for (int b2 = bg0; b2 < bg1; ++b2) need = std::max(need, pair_off[b2] + blk[b2].n_rows);
+      size_t ci = 0;
+      for (const auto &ch : c->chunks) { // chunks complete in order: wait for the first one that covers `need`
+        if (ch.row_end >= need) { CU(cudaStreamWaitEvent(s, ch.ev, 0)); break; }
+        ++ci;
+      }
+    }
+    lm::launch_zero_words(c->d_scalars.p, 2, s);
+    if (re > rb) {
+      if (exhaustive)
+        lm::launch_expand_exhaustive(c->d_blk_row_off.as<int64_t>(), c->d_blk_src.as<int32_t>(), c->d_blk_ng.as<int32_t>(),
+                                     nb, c->d_line_off.as<int64_t>(), n_rows, c->d_key.as<uint32_t>(),
+                                     c->d_val.as<uint32_t>(), s);
+      else
+        lm::launch_expand_rows(c->d_pairs.as<int32_t>(), c->d_blk_row_off.as<int64_t>(), c->d_blk_src.as<int32_t>(),
+                               c->d_blk_ng.as<int32_t>(), c->d_blk_pair_off.as<int64_t>(), nb,
+                               c->d_line_off.as<int64_t>(), rb, re, c->d_key.as<uint32_t>(), c->d_val.as<uint32_t>(),
+                               d_err, s);
+      ++launches;
+      // stable LSD radix sort by node id keeps (neighbour, row) order inside every node
+      cub::DoubleBuffer<uint32_t> dk(c->d_key.as<uint32_t>() + rb, c->d_key2.as<uint32_t>() + rb);
+      cub::DoubleBuffer<uint32_t> dv(c->d_val.as<uint32_t>() + rb, c->d_val2.as<uint32_t>() + rb);
+      size_t tmp = 0;
+      CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)(re - rb), 0, nbits, s));
+      CU(c->d_sort_tmp.ensure(tmp));
+      CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, tmp, dk, dv, (int)(re - rb), 0, nbits, s));
+      launches += (nbits + 7) / 8 + 1;
+      if (dk.Current() != c->d_key2.as<uint32_t>() + rb) {
+        CU(cudaMemcpyAsync(c->d_key2.as<uint32_t>() + rb, dk.Current(), 4 * (re - rb), cudaMemcpyDeviceToDevice, s));
+        CU(cudaMemcpyAsync(c->d_val2.as<uint32_t>() + rb, dv.Current(), 4 * (re - rb), cudaMemcpyDeviceToDevice, s));
+      }
+    }
+    lm::launch_node_offsets(c->sorted_key + rb, re - rb, rb, node_lo, node_hi, c->d_node_row_off.as<uint32_t>(),
+                            d_max_rows, s);
     ++launches;
+    // the shared-memory staging area is sized from the largest node of the group (one 8-byte read-back)
+    unsigned int hs[2] = {0, 0};
+    CU(cudaMemcpyAsync(hs, c->d_scalars.p, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (hs[1] == 1)
+      return fail(LM_ERR_INVALID, "IndexError! Out-of-index matches exist (line_id >= number of lines of the image). "
+                                  "Please make sure you are reusing the correct descriptors and matches.");
+    if (hs[1] == 2) return fail(LM_ERR_INVALID, "IndexError! Out-of-index neighbor line id in matches.");
+    const int max_rows = (int)hs[0];
+    max_rows_all = std::max(max_rows_all, max_rows);
+    p.node_begin = node_lo;
+    p.node_end = node_hi;
+    const int64_t n_group_nodes = node_hi - node_lo;
+    if ((int64_t)max_rows * ns > 65535) return fail(LM_ERR_INVALID, "more than 65535 candidates possible for one 2D line");
+    int cap = 32;
+    while (cap < max_rows * ns) cap += 32;
+    size_t smem = lm::tri_smem_bytes(cap);
+    int grid;
+    const size_t smem_limit = (size_t)std::max(0, c->max_smem_optin - 1024);
+    if (smem <= smem_limit) {
+      p.use_slab = 0;
+      p.cap = cap;
+      grid = (int)std::min<int64_t>(n_group_nodes, (int64_t)1 << 30);
+    } else {
+      // nodes larger than shared memory (exhaustive matching): persistent CTAs with a global staging slab
+      p.use_slab = 1;
+      p.cap = cap;
+      grid = (int)std::min<int64_t>(n_group_nodes, (int64_t)c->sm_count * 4);
+      p.slab_stride = (int64_t)((smem + 255) / 256 * 256);
+      CU(c->d_slab.ensure((size_t)p.slab_stride * grid));
+      p.slab = c->d_slab.as<char>();
+      smem = 0;
+    }
+    CU(cudaEventRecord(c->evk0, s));
+    if (n_group_nodes > 0) {
+      lm::launch_tri_node_kernel(p, grid, 128, smem, s);
+      ++launches;
+    }
+    CU(cudaEventRecord(c->evk1, s));
+    if (n_group_nodes > 0) {
+      float msk = 0;
+      CU(cudaEventSynchronize(c->evk1));
+      CU(cudaEventElapsedTime(&msk, c->evk0, c->evk1));
+      c->node_kernel_ms_acc += msk;
+    }
+    bg0 = bg1;
+    gv0 = gv1;
   }
-  CU(cudaEventRecord(c->evk1, s));
+  c->stats.max_rows_per_node = max_rows_all;
+  p.node_begin = c->node_begin;
+  p.node_end = c->node_end;
   // valid_edges_ in compact form: per-node counts -> exclusive scan -> ordered scatter
   if (n_shard_nodes > 0) {
     CU(c->d_nvalid.ensure(4 * (n_shard_nodes + 1)));
@@ -810,11 +950,10 @@ int lm_tri_run(lm_ctx *c) {
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev1, s));
   CU(cudaStreamSynchronize(s));
+  CU(cudaStreamSynchronize(c->copy_stream)); // uploads of images outside this shard may still be in flight
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  float msk = 0;
-  CU(cudaEventElapsedTime(&msk, c->evk0, c->evk1));
-  c->stats.last_node_kernel_ms = msk;
+  c->stats.last_node_kernel_ms = c->node_kernel_ms_acc;
   unsigned long long cnt[4];
   CU(cudaMemcpy(cnt, d_counters, 32, cudaMemcpyDeviceToHost));
   c->stats.n_rows = n_rows;

@@ -829,6 +829,49 @@ void launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem
   else launch_tri_vp<false>(p, grid, smem, s);
 }
 
+// The per-run block tables (match tables ordered by (source view, neighbour), row offsets) are derived on the
+// device from block descriptors that were uploaded together with the matches. Nothing has to cross PCIe when
+// a run starts: any host->device transfer issued then (copy-engine copies, large kernel parameters, even
+// zero-copy reads) was measured to wait ~3 ms behind a 160 MB match upload still in flight.
+__global__ void block_keys_kernel(const RawBlock *__restrict__ raw, int n_all, int vb, int ve, int exhaustive,
+                                  uint32_t *__restrict__ key, uint32_t *__restrict__ val) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_all) return;
+  const RawBlock b = raw[i];
+  const bool in = b.src_view >= vb && b.src_view < ve;
+  key[i] = in ? (((uint32_t)b.src_view << 16) | (uint32_t)(exhaustive ? b.order : b.ng_view)) : 0xffffffffu;
+  val[i] = (uint32_t)i;
+}
+__global__ void block_gather_kernel(const RawBlock *__restrict__ raw, const uint32_t *__restrict__ sorted_idx, int nb,
+                                    int32_t *__restrict__ blk_src, int32_t *__restrict__ blk_ng,
+                                    int64_t *__restrict__ blk_pair_off, int64_t *__restrict__ blk_rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nb) return;
+  if (i == nb) { blk_rows[i] = 0; return; }
+  const RawBlock b = raw[sorted_idx[i]];
+  blk_src[i] = b.src_view;
+  blk_ng[i] = b.ng_view;
+  blk_pair_off[i] = b.pair_off;
+  blk_rows[i] = b.n_rows;
+}
+void launch_block_keys(const RawBlock *raw, int n_all, int vb, int ve, int exhaustive, uint32_t *key, uint32_t *val,
+                       cudaStream_t s) {
+  if (n_all <= 0) return;
+  block_keys_kernel<<<(n_all + 255) / 256, 256, 0, s>>>(raw, n_all, vb, ve, exhaustive, key, val);
+}
+void launch_block_gather(const RawBlock *raw, const uint32_t *sorted_idx, int nb, int32_t *blk_src, int32_t *blk_ng,
+                         int64_t *blk_pair_off, int64_t *blk_rows, cudaStream_t s) {
+  block_gather_kernel<<<(nb + 1 + 255) / 256, 256, 0, s>>>(raw, sorted_idx, nb, blk_src, blk_ng, blk_pair_off, blk_rows);
+}
+__global__ void zero_words_kernel(unsigned int *p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0u;
+}
+// cudaMemsetAsync may be routed to a copy engine and then waits behind a running match upload
+void launch_zero_words(void *d_dst, int n_words, cudaStream_t s) {
+  zero_words_kernel<<<(n_words + 127) / 128, 128, 0, s>>>(static_cast<unsigned int *>(d_dst), n_words);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Match tables -> node-major rows. Flat row order = (source view asc, neighbour view asc, row), the
 // order in which TriangulateImage appends to tris_ (base_line_triangulator.cc:74-100); a stable sort
@@ -836,9 +879,10 @@ void launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem
 __global__ void expand_rows_kernel(const int32_t *__restrict__ pairs, const int64_t *__restrict__ blk_row_off,
                                    const int32_t *__restrict__ blk_src, const int32_t *__restrict__ blk_ng,
                                    const int64_t *__restrict__ blk_pair_off, int n_blocks,
-                                   const int64_t *__restrict__ line_off, int64_t n_rows,
+                                   const int64_t *__restrict__ line_off, int64_t r_begin, int64_t n_rows,
                                    uint32_t *__restrict__ key, uint32_t *__restrict__ val, int *err) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t r = r_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows;
+       r += (int64_t)gridDim.x * blockDim.x) {
     int lo = 0, hi = n_blocks; // largest b with blk_row_off[b] <= r
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
@@ -859,13 +903,13 @@ __global__ void expand_rows_kernel(const int32_t *__restrict__ pairs, const int6
 }
 void launch_expand_rows(const int32_t *d_pairs, const int64_t *d_blk_row_off, const int32_t *d_blk_src_view,
                         const int32_t *d_blk_ng_view, const int64_t *d_blk_pair_off, int n_blocks,
-                        const int64_t *d_line_off, int64_t n_rows, uint32_t *d_key, uint32_t *d_val, int *d_err,
-                        cudaStream_t s) {
-  if (n_rows == 0) return;
-  int grid = (int)((n_rows + 255) / 256);
+                        const int64_t *d_line_off, int64_t r_begin, int64_t r_end, uint32_t *d_key, uint32_t *d_val,
+                        int *d_err, cudaStream_t s) {
+  if (r_end <= r_begin) return;
+  int grid = (int)((r_end - r_begin + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
   expand_rows_kernel<<<grid, 256, 0, s>>>(d_pairs, d_blk_row_off, d_blk_src_view, d_blk_ng_view, d_blk_pair_off,
-                                          n_blocks, d_line_off, n_rows, d_key, d_val, d_err);
+                                          n_blocks, d_line_off, r_begin, r_end, d_key, d_val, d_err);
 }
 
 // TriangulateImageExhaustiveMatch (base_line_triangulator.cc:111-136): every line of the neighbour.
@@ -897,18 +941,20 @@ void launch_expand_exhaustive(const int64_t *d_blk_row_off, const int32_t *d_blk
                                                 n_rows, d_key, d_val);
 }
 
-__global__ void node_offsets_kernel(const uint32_t *__restrict__ key, int64_t n_rows, int64_t n_nodes,
-                                    uint32_t *__restrict__ off, unsigned int *max_rows) {
-  const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (n > n_nodes) return;
-  // lower_bound(key, n)
-  int64_t lo = 0, hi = n_rows;
+// Row range of every node in [node_lo, node_hi] from the node-sorted keys of one group (rows
+// [row_base, row_base + n_rows) of the run); off[n] is a row index of the whole run.
+__global__ void node_offsets_kernel(const uint32_t *__restrict__ key, int64_t n_rows, int64_t row_base,
+                                    int64_t node_lo, int64_t node_hi, uint32_t *__restrict__ off,
+                                    unsigned int *max_rows) {
+  const int64_t n = node_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n > node_hi) return;
+  int64_t lo = 0, hi = n_rows; // lower_bound(key, n)
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
     if (key[mid] < (uint32_t)n) lo = mid + 1; else hi = mid;
   }
-  off[n] = (uint32_t)lo;
-  if (n < n_nodes) {
+  off[n] = (uint32_t)(row_base + lo);
+  if (n < node_hi) {
     int64_t lo2 = lo, hi2 = n_rows;
     while (lo2 < hi2) {
       const int64_t mid = (lo2 + hi2) >> 1;
@@ -918,10 +964,11 @@ __global__ void node_offsets_kernel(const uint32_t *__restrict__ key, int64_t n_
     if (cnt) atomicMax(max_rows, cnt);
   }
 }
-void launch_node_offsets(const uint32_t *d_sorted_key, int64_t n_rows, int64_t n_nodes, uint32_t *d_node_row_off,
-                         unsigned int *d_max_rows, cudaStream_t s) {
-  const int grid = (int)((n_nodes + 1 + 255) / 256);
-  node_offsets_kernel<<<grid, 256, 0, s>>>(d_sorted_key, n_rows, n_nodes, d_node_row_off, d_max_rows);
+void launch_node_offsets(const uint32_t *d_sorted_key, int64_t n_rows, int64_t row_base, int64_t node_lo,
+                         int64_t node_hi, uint32_t *d_node_row_off, unsigned int *d_max_rows, cudaStream_t s) {
+  const int grid = (int)((node_hi - node_lo + 1 + 255) / 256);
+  node_offsets_kernel<<<grid, 256, 0, s>>>(d_sorted_key, n_rows, row_base, node_lo, node_hi, d_node_row_off,
+                                           d_max_rows);
 }
 
 // valid_edges_ (global_line_triangulator.cc:130-142) in compact, node-major, candidate-ordered form.
@@ -978,6 +1025,32 @@ void launch_compact_edges_only(const uint8_t *row_state, const uint32_t *row_ng,
   if (n <= 0) return;
   compact_edges_kernel<<<(int)((n * 32 + 255) / 256), 256, 0, s>>>(row_state, row_ng, node_row_off, edge_off,
                                                                    node_begin, n, ns, edge_ng);
+}
+
+// valid connections as (ng_img_id, ng_line_id) int32 pairs + int64 node offsets, ready for the caller's buffer
+__global__ void edges_for_host_kernel(const uint32_t *__restrict__ edge_off, const uint32_t *__restrict__ edge_ng,
+                                      const int32_t *__restrict__ img_ids, int64_t n_nodes_shard, int64_t n_edges,
+                                      int64_t node_begin, int64_t n_nodes_total, int64_t *__restrict__ node_off,
+                                      int32_t *__restrict__ pairs) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n_edges) {
+    const uint32_t ng = edge_ng[t];
+    pairs[2 * t] = img_ids[ng >> 16];
+    pairs[2 * t + 1] = (int32_t)(ng & 0xffffu);
+  }
+  if (t <= n_nodes_total) {
+    int64_t v = 0;
+    if (t >= node_begin && t <= node_begin + n_nodes_shard) v = edge_off[t - node_begin];
+    else if (t > node_begin + n_nodes_shard) v = n_edges;
+    node_off[t] = v;
+  }
+}
+void launch_edges_for_host(const uint32_t *edge_off, const uint32_t *edge_ng, const int32_t *img_ids,
+                           int64_t n_nodes_shard, int64_t n_edges, int64_t node_begin, int64_t n_nodes_total,
+                           int64_t *node_off, int32_t *pairs, cudaStream_t s) {
+  const int64_t n = (n_edges > n_nodes_total + 1) ? n_edges : n_nodes_total + 1;
+  edges_for_host_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(edge_off, edge_ng, img_ids, n_nodes_shard, n_edges,
+                                                               node_begin, n_nodes_total, node_off, pairs);
 }
 
 // run_clustering edge weight (global_line_triangulator.cc:263-288): LineLinker3d::compute_score of the

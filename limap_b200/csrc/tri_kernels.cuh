@@ -80,19 +80,34 @@ size_t tri_smem_bytes(int cap);
 void launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem, cudaStream_t s);
 void launch_expand_rows(const int32_t *d_pairs, const int64_t *d_blk_row_off, const int32_t *d_blk_src_view,
                         const int32_t *d_blk_ng_view, const int64_t *d_blk_pair_off, int n_blocks,
-                        const int64_t *d_line_off, int64_t n_rows, uint32_t *d_key, uint32_t *d_val,
+                        const int64_t *d_line_off, int64_t r_begin, int64_t r_end, uint32_t *d_key, uint32_t *d_val,
                         int *d_err, cudaStream_t s);
 void launch_expand_exhaustive(const int64_t *d_blk_row_off, const int32_t *d_blk_src_view,
                               const int32_t *d_blk_ng_view, int n_blocks, const int64_t *d_line_off,
                               int64_t n_rows, uint32_t *d_key, uint32_t *d_val, cudaStream_t s);
-void launch_node_offsets(const uint32_t *d_sorted_key, int64_t n_rows, int64_t n_nodes, uint32_t *d_node_row_off,
-                         unsigned int *d_max_rows, cudaStream_t s);
+void launch_node_offsets(const uint32_t *d_sorted_key, int64_t n_rows, int64_t row_base, int64_t node_lo,
+                         int64_t node_hi, uint32_t *d_node_row_off, unsigned int *d_max_rows, cudaStream_t s);
 void launch_extract_nvalid(const NodeRecord *nodes, int64_t node_begin, int64_t n, uint32_t *out, cudaStream_t s);
 void launch_compact_edges_only(const uint8_t *row_state, const uint32_t *row_ng, const uint32_t *node_row_off,
                                const uint32_t *edge_off, int64_t node_begin, int64_t n, int ns, uint32_t *edge_ng,
                                cudaStream_t s);
 void launch_edge_pairs(const uint32_t *edge_off, const uint32_t *edge_ng, const int64_t *line_off,
                        int64_t node_begin, int64_t n_nodes, int64_t n_edges, int64_t *out, cudaStream_t s);
+void launch_edges_for_host(const uint32_t *edge_off, const uint32_t *edge_ng, const int32_t *img_ids,
+                           int64_t n_nodes_shard, int64_t n_edges, int64_t node_begin, int64_t n_nodes_total,
+                           int64_t *node_off, int32_t *pairs, cudaStream_t s);
+void launch_zero_words(void *d_dst, int n_words, cudaStream_t s);
+// one (source image, neighbour) match table as uploaded at TriangulateImage time
+struct RawBlock {
+  int32_t src_view, ng_view;
+  int64_t n_rows;
+  int64_t pair_off; // row offset into the device match store (-1: exhaustive)
+  int32_t order, pad;
+};
+void launch_block_keys(const RawBlock *raw, int n_all, int vb, int ve, int exhaustive, uint32_t *key, uint32_t *val,
+                       cudaStream_t s);
+void launch_block_gather(const RawBlock *raw, const uint32_t *sorted_idx, int nb, int32_t *blk_src, int32_t *blk_ng,
+                         int64_t *blk_pair_off, int64_t *blk_rows, cudaStream_t s);
 void launch_edge_weights(const EdgeParams &p, cudaStream_t s);
 
 } // namespace lm

@@ -118,11 +118,15 @@ class TriEngine:
         check(lib().lm_tri_get_nodes(self.ctx.handle, ptr(out)))
         return out
 
-    def get_all_valid_edges(self):
+    def get_all_valid_edges(self, off=None, edges=None):
+        """(node_off[n_nodes+1], edges[n,2] = (ng_img_id, ng_line_id)); pass preallocated (pinned) arrays to
+        avoid staging copies."""
         n = int(self.line_off[-1])
-        off = np.zeros(n + 1, np.int64)
-        ne = check(lib().lm_tri_get_all_valid_edges(self.ctx.handle, ptr(off), None))
-        edges = np.zeros((max(ne, 1), 2), np.int32)
+        ne = int(self.ctx.stats()["n_valid_edges"])
+        if off is None:
+            off = np.zeros(n + 1, np.int64)
+        if edges is None or len(edges) < ne:
+            edges = np.zeros((max(ne, 1), 2), np.int32)
         check(lib().lm_tri_get_all_valid_edges(self.ctx.handle, ptr(off), ptr(edges)))
         return off, edges[:ne]
 
@@ -136,6 +140,9 @@ class TriEngine:
 
     def set_shard(self, view_begin, view_end):
         check(lib().lm_tri_set_shard(self.ctx.handle, int(view_begin), int(view_end)))
+
+    def set_pipeline_groups(self, n_groups):
+        check(lib().lm_tri_set_pipeline_groups(self.ctx.handle, int(n_groups)))
 
     def run(self):
         check(lib().lm_tri_run(self.ctx.handle))

@@ -159,3 +159,30 @@ def test_full_size_properties_hypersim100_shape():
             a2, b2, c2 = eng.get_best(int(sc.img_ids[v]))
             assert np.array_equal(best1[v][0], a2) and np.array_equal(best1[v][2], c2)
     assert tot == s1["n_candidates"]
+
+
+def test_bulk_add_and_pipeline_groups_match_per_image_adds():
+    """lm_tri_add_matches_bulk + lm_tri_set_pipeline_groups(n): same node records and valid connections as
+    per-image adds in one group (groups split the run by source image; nodes are independent)."""
+    from limap_b200.engine import TriEngine
+    sc = make_scene(V=30, L=500, N=10, K=10, seed=23)
+    ref = TriEngine(_cfg())
+    ref.upload(sc)
+    ref.set_ranges(*sc.ranges)
+    for i in sc.img_ids:
+        ref.add_image_matches(int(i), *sc.flat_matches(int(i)))
+    s_ref = ref.run()
+    nodes_ref = ref.get_nodes().copy()
+    off_ref, edges_ref = ref.get_all_valid_edges()
+    src, ng, off, pairs = sc.bulk_matches()
+    for n_groups in (1, 3, 7):
+        eng = TriEngine(_cfg())
+        eng.upload(sc)
+        eng.set_ranges(*sc.ranges)
+        eng.set_pipeline_groups(n_groups)
+        eng.add_matches_bulk(src, ng, off, pairs)
+        st = eng.run()
+        assert st["n_candidates"] == s_ref["n_candidates"] and st["n_valid_edges"] == s_ref["n_valid_edges"]
+        assert eng.get_nodes().tobytes() == nodes_ref.tobytes()
+        o2, e2 = eng.get_all_valid_edges()
+        assert np.array_equal(o2, off_ref) and np.array_equal(e2[: o2[-1]], edges_ref[: off_ref[-1]])
