@@ -171,6 +171,45 @@ int64_t lm_tri_build_tracks(lm_ctx *ctx, int64_t *n_support_total);
 int lm_tri_get_tracks(lm_ctx *ctx, int64_t *track_off, int32_t *img_ids, int32_t *line_ids,
                       int32_t *node_ids, double *node_line3d, double *track_line);
 
+/* ---- post-triangulation track filters and remerge --------------------------------
+ * The steps of runners/line_triangulation.py:171-200 between ComputeLineTracks and the line BA. Tracks are flat
+ * arrays like lm_ba_solve's: sup_off[T+1], per supporting line its view index (position in the camera arrays)
+ * and 2D segment; cameras as kvec[4] / qvec[4] / tvec[3] per view (model_ids NULL = all PINHOLE). */
+typedef struct lm_filter_config {
+  double th_angular_2d;    /* CheckReprojection: angle(line2d, projection) > th fails (merging_utils.cc:39-43) */
+  double th_perp_2d;       /* ... then endpoint-to-line distance > th fails (:44-49) */
+  double th_sv_angular_3d; /* CheckSensitivity: Line3d::sensitivity(view) > th fails (merging_utils.cc:101-107) */
+  double th_overlap;       /* FilterTracksByOverlap: compute_overlap(projection, line2d) >= th counts (:147-149) */
+} lm_filter_config;
+typedef struct lm_merge_stats {
+  int64_t n_supports;        /* last lm_tracks_support_flags */
+  int64_t n_tracks;          /* last lm_remerge_labels */
+  int64_t n_pairs_gated;     /* pairs that passed the fp32 angle gate and were checked in fp64 */
+  int64_t n_edges;           /* connected pairs */
+  int64_t n_kernel_launches; /* cumulative */
+  float last_flags_ms, last_flags_kernel_ms, last_remerge_ms, last_remerge_kernel_ms;
+} lm_merge_stats;
+/* out_flags[S]: bit0 = CheckReprojection result (merging_utils.cc:27-50), bit1 = CheckSensitivity result (:89-109),
+ * bit2 = overlap test of FilterTracksByOverlap (:143-150), each for support s of its track's line
+ * track_line[t][6] = start3, end3. The callers' selection logic (FilterSupportingLines :52-87,
+ * FilterTracksBySensitivity :111-131, FilterTracksByOverlap :133-155) works on these bits. */
+int lm_tracks_support_flags(lm_ctx *ctx, int32_t n_views, const int32_t *model_ids, const double *kvec,
+                            const double *qvec, const double *tvec, int64_t T, const int64_t *sup_off,
+                            const int32_t *sup_view, const double *segs, const double *track_line,
+                            const lm_filter_config *cfg, uint8_t *out_flags);
+/* Aggregator::aggregate_line3d_list (merging/aggregator.cc:9-101) for T groups of 3D lines:
+ * lines[off[T]][7] = start3, end3, uncertainty; scores[off[T]]; out_line[T][7]. Host arithmetic (a 3x3
+ * eigen-problem and a sort per group), no device work. */
+int lm_aggregate_lines(int64_t T, const int64_t *off, const double *lines, const double *scores,
+                       int32_t num_outliers, double *out_line);
+/* One pass of RemergeLineTracks up to the group labels (merging/merging.cc:513-598): all-pairs
+ * LineLinker3d::check_connection under set_to_spatial_merging() on the device, union-find with the group-size
+ * heuristic on the host. track_line[T][7] = start3, end3, uncertainty; active[T]; out_labels[T] = group of each
+ * track (groups numbered by their root track, ascending). Returns the number of groups or <0. */
+int64_t lm_remerge_labels(lm_ctx *ctx, int64_t T, const double *track_line, const uint8_t *active,
+                          const lm_linker_config *linker3d, int32_t *out_labels, int64_t *out_n_edges);
+int lm_merge_get_stats(lm_ctx *ctx, lm_merge_stats *out);
+
 /* ---- line refinement / line bundle adjustment (cameras constant) ---------------------------------
  * Replaces HybridBAEngine::{InitLineTracks,SetUp,Solve,GetOutputLineTracks}
  * (optimize/hybrid_bundle_adjustment/hybrid_bundle_adjustment.cc:39-59,156-264,298-310) as called by

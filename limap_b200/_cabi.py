@@ -40,6 +40,18 @@ class BAStats(C.Structure):
                 ("total_successful", C.c_int64), ("solve_ms", C.c_double), ("prepare_ms", C.c_double)]
 
 
+class FilterConfig(C.Structure):
+    _fields_ = [("th_angular_2d", C.c_double), ("th_perp_2d", C.c_double), ("th_sv_angular_3d", C.c_double),
+                ("th_overlap", C.c_double)]
+
+
+class MergeStats(C.Structure):
+    _fields_ = [("n_supports", C.c_int64), ("n_tracks", C.c_int64), ("n_pairs_gated", C.c_int64),
+                ("n_edges", C.c_int64), ("n_kernel_launches", C.c_int64), ("last_flags_ms", C.c_float),
+                ("last_flags_kernel_ms", C.c_float), ("last_remerge_ms", C.c_float),
+                ("last_remerge_kernel_ms", C.c_float)]
+
+
 NODE_RECORD_DTYPE = np.dtype([("line", np.float64, 9), ("score", np.float64), ("ng_view", np.int32),
                               ("ng_line", np.int32), ("n_cand", np.int32), ("n_valid", np.int32)])
 
@@ -82,6 +94,10 @@ _SIGS = {
     "lm_ba_solve": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lm_ba_get_stats": (C.c_int, [_P, _P]),
     "lm_vp_detect": (C.c_int64, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64]),
+    "lm_tracks_support_flags": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
+    "lm_aggregate_lines": (C.c_int, [C.c_int64, _P, _P, _P, C.c_int32, _P]),
+    "lm_remerge_labels": (C.c_int64, [_P, C.c_int64, _P, _P, _P, _P, _P]),
+    "lm_merge_get_stats": (C.c_int, [_P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

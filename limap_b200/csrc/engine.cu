@@ -13,6 +13,7 @@
 #include "tri_kernels.cuh"
 #include "lm_kernels.cuh"
 #include "vp_kernels.cuh"
+#include "merge_kernels.cuh"
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -183,6 +184,9 @@ struct lm_ctx {
   DevBuf d_ba_in, d_ba_blocks, d_ba_out;
   DevBuf d_vp_pts, d_vp_off, d_vp_labels, d_vp_nc, d_vp_ps, d_vp_mat;
   lm_ba_stats ba_stats;
+  // track filters / remerge
+  DevBuf d_mg_in, d_mg_out, d_mg_edges;
+  lm_merge_stats mg_stats;
   // tracks
   std::vector<Track> tracks;
   std::vector<std::pair<int, int>> graph_nodes;
@@ -274,6 +278,7 @@ int lm_ctx_create(int device, lm_ctx **out) {
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   memset(&c->stats, 0, sizeof(c->stats));
   memset(&c->ba_stats, 0, sizeof(c->ba_stats));
+  memset(&c->mg_stats, 0, sizeof(c->mg_stats));
   *out = c;
   return LM_OK;
 }
@@ -316,6 +321,27 @@ int lm_ctx_synchronize(lm_ctx *c) {
   return sync_stream(c);
 }
 
+// Per-view constants (tri_kernels.cuh ViewT) from the reference's camera arrays.
+static void make_view(int model_id, const double *kv, const double *qv, const double *t, lm::ViewD &d) {
+  const double fx = kv[0], fy = kv[1], cx = kv[2], cy = kv[3];
+  // CameraPose(qvec, tvec) normalises qvec (base/camera.h:92-93)
+  M3h R = quat_to_R(qv);
+  // K^-1 (closed form of Eigen's cofactor inverse for the pinhole K)
+  const double ki[9] = {1.0 / fx, 0, -cx / fx, 0, 1.0 / fy, -cy / fy, 0, 0, 1};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) // M = R^T * Kinv
+      d.M[3 * i + j] = R.m[0 * 3 + i] * ki[0 * 3 + j] + R.m[1 * 3 + i] * ki[1 * 3 + j] + R.m[2 * 3 + i] * ki[2 * 3 + j];
+  for (int i = 0; i < 3; ++i) d.C[i] = -(R.m[0 * 3 + i] * t[0] + R.m[1 * 3 + i] * t[1] + R.m[2 * 3 + i] * t[2]);
+  const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      d.P[4 * i + j] = K[3 * i] * R.m[j] + K[3 * i + 1] * R.m[3 + j] + K[3 * i + 2] * R.m[6 + j];
+    d.P[4 * i + 3] = K[3 * i] * t[0] + K[3 * i + 1] * t[1] + K[3 * i + 2] * t[2];
+  }
+  d.fbar = (model_id == 0) ? fx : (fx + fy) / 2.0;
+  d.pad = 0;
+}
+
 static int upload_segs(lm_ctx *c) {
   // add_halfpix (base_line_triangulator.cc:32-43) is applied when both scene and config are known.
   c->h_segs = c->h_segs_raw;
@@ -348,25 +374,7 @@ int lm_scene_upload(lm_ctx *c, int32_t n_views, const int32_t *img_ids, const in
     if (model_ids[v] != 0 && model_ids[v] != 1)
       return fail(LM_ERR_INVALID, "only SIMPLE_PINHOLE / PINHOLE are legal on this path (IsUndistorted check)");
     if (line_off[v + 1] - line_off[v] > 65535) return fail(LM_ERR_INVALID, "more than 65535 lines in one image");
-    const double fx = kvec[4 * v], fy = kvec[4 * v + 1], cx = kvec[4 * v + 2], cy = kvec[4 * v + 3];
-    // CameraPose(qvec, tvec) normalises qvec (base/camera.h:92-93)
-    M3h R = quat_to_R(qvec + 4 * v);
-    const double *t = tvec + 3 * v;
-    lm::ViewD &d = views[v];
-    // K^-1 (closed form of Eigen's cofactor inverse for the pinhole K)
-    const double ki[9] = {1.0 / fx, 0, -cx / fx, 0, 1.0 / fy, -cy / fy, 0, 0, 1};
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) // M = R^T * Kinv
-        d.M[3 * i + j] = R.m[0 * 3 + i] * ki[0 * 3 + j] + R.m[1 * 3 + i] * ki[1 * 3 + j] + R.m[2 * 3 + i] * ki[2 * 3 + j];
-    for (int i = 0; i < 3; ++i) d.C[i] = -(R.m[0 * 3 + i] * t[0] + R.m[1 * 3 + i] * t[1] + R.m[2 * 3 + i] * t[2]);
-    const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
-    for (int i = 0; i < 3; ++i) {
-      for (int j = 0; j < 3; ++j)
-        d.P[4 * i + j] = K[3 * i] * R.m[j] + K[3 * i + 1] * R.m[3 + j] + K[3 * i + 2] * R.m[6 + j];
-      d.P[4 * i + 3] = K[3 * i] * t[0] + K[3 * i + 1] * t[1] + K[3 * i + 2] * t[2];
-    }
-    d.fbar = (model_ids[v] == 0) ? fx : (fx + fy) / 2.0;
-    d.pad = 0;
+    make_view(model_ids[v], kvec + 4 * v, qvec + 4 * v, tvec + 3 * v, views[v]);
     for (int64_t l = line_off[v]; l < line_off[v + 1]; ++l) node_view[l] = (uint16_t)v;
   }
   c->h_segs_raw.assign(segs, segs + 4 * c->n_nodes);
@@ -1139,26 +1147,30 @@ void dominant_eigvec(const double Ain[3][3], double out[3]) {
   for (int k = 0; k < 3; ++k) out[k] = V[k][best];
 }
 
-void aggregate(const std::vector<const lm::NodeRecord *> &recs, int num_outliers, double out[7]) {
-  const int n = (int)recs.size();
+struct AggItem { // one Line3d of a line3d_list: endpoints, uncertainty, score
+  const double *l;
+  double unc, score;
+};
+void aggregate_items(const std::vector<AggItem> &it, int num_outliers, double out[7]) {
+  const int n = (int)it.size();
   double min_unc = 1.7976931348623157e308;
-  for (auto *r : recs) if (r->line[8] < min_unc) min_unc = r->line[8];
+  for (const AggItem &r : it) if (r.unc < min_unc) min_unc = r.unc;
   if (n < 4) { // aggregate_line3d_list_takebest (aggregator.cc:9-29); index 0 when no score > 0
     double best_score = 0.0;
     int best = -1;
-    for (int i = 0; i < n; ++i) if (recs[i]->score > best_score) { best_score = recs[i]->score; best = i; }
+    for (int i = 0; i < n; ++i) if (it[i].score > best_score) { best_score = it[i].score; best = i; }
     if (best < 0) best = 0;
-    for (int k = 0; k < 6; ++k) out[k] = recs[best]->line[k];
+    for (int k = 0; k < 6; ++k) out[k] = it[best].l[k];
     out[6] = min_unc;
     return;
   }
   double ctr[3] = {0, 0, 0};
-  for (auto *r : recs) for (int k = 0; k < 3; ++k) { ctr[k] += r->line[k]; ctr[k] += r->line[3 + k]; }
+  for (const AggItem &r : it) for (int k = 0; k < 3; ++k) { ctr[k] += r.l[k]; ctr[k] += r.l[3 + k]; }
   for (int k = 0; k < 3; ++k) ctr[k] = ctr[k] / (2 * n);
   double S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-  for (auto *r : recs)
+  for (const AggItem &r : it)
     for (int e = 0; e < 2; ++e) {
-      double p[3] = {r->line[3 * e] - ctr[0], r->line[3 * e + 1] - ctr[1], r->line[3 * e + 2] - ctr[2]};
+      double p[3] = {r.l[3 * e] - ctr[0], r.l[3 * e + 1] - ctr[1], r.l[3 * e + 2] - ctr[2]};
       for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) S[a][b] += p[a] * p[b];
     }
   double d[3];
@@ -1166,14 +1178,18 @@ void aggregate(const std::vector<const lm::NodeRecord *> &recs, int num_outliers
   double dn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
   for (int k = 0; k < 3; ++k) d[k] /= dn;
   std::vector<double> proj;
-  for (auto *r : recs)
+  for (const AggItem &r : it)
     for (int e = 0; e < 2; ++e)
-      proj.push_back((r->line[3 * e] - ctr[0]) * d[0] + (r->line[3 * e + 1] - ctr[1]) * d[1] +
-                     (r->line[3 * e + 2] - ctr[2]) * d[2]);
+      proj.push_back((r.l[3 * e] - ctr[0]) * d[0] + (r.l[3 * e + 1] - ctr[1]) * d[1] + (r.l[3 * e + 2] - ctr[2]) * d[2]);
   std::sort(proj.begin(), proj.end());
   const double a = proj[num_outliers], b = proj[2 * n - 1 - num_outliers];
   for (int k = 0; k < 3; ++k) { out[k] = ctr[k] + d[k] * a; out[3 + k] = ctr[k] + d[k] * b; }
   out[6] = min_unc;
+}
+void aggregate(const std::vector<const lm::NodeRecord *> &recs, int num_outliers, double out[7]) {
+  std::vector<AggItem> it(recs.size());
+  for (size_t i = 0; i < recs.size(); ++i) it[i] = AggItem{recs[i]->line, recs[i]->line[8], recs[i]->score};
+  aggregate_items(it, num_outliers, out);
 }
 
 size_t uf_root(size_t i, std::vector<int> &parent) { // base/graph.cc:157-166
@@ -1773,6 +1789,173 @@ int64_t lm_vp_detect(lm_ctx *c, int32_t n_images, const int64_t *line_off, const
   }
   vp_off[n_images] = n_vps;
   return n_vps;
+}
+
+// ---- track filters + remerge (merging/merging_utils.cc, merging/merging.cc:513-645) -------------------
+int lm_tracks_support_flags(lm_ctx *c, int32_t n_views, const int32_t *model_ids, const double *kvec, const double *qvec,
+                            const double *tvec, int64_t T, const int64_t *sup_off, const int32_t *sup_view,
+                            const double *segs, const double *track_line, const lm_filter_config *cfg,
+                            uint8_t *out_flags) {
+  if (!c || !cfg || !sup_off || !kvec || !qvec || !tvec) return fail(LM_ERR_INVALID, "NULL argument");
+  if (T < 0 || n_views <= 0) return fail(LM_ERR_INVALID, "bad sizes");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const int64_t n = sup_off[T];
+  if (n == 0) return LM_OK;
+  if (!sup_view || !segs || !track_line || !out_flags) return fail(LM_ERR_INVALID, "NULL argument");
+  for (int64_t k = 0; k < n; ++k)
+    if (sup_view[k] < 0 || sup_view[k] >= n_views) return fail(LM_ERR_INVALID, "support view index out of range");
+  std::vector<lm::ViewD> views(n_views);
+  for (int v = 0; v < n_views; ++v) {
+    const int mid = model_ids ? model_ids[v] : 1;
+    if (mid != 0 && mid != 1) return fail(LM_ERR_INVALID, "only SIMPLE_PINHOLE / PINHOLE are legal on this path");
+    make_view(mid, kvec + 4 * v, qvec + 4 * v, tvec + 3 * v, views[v]);
+  }
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_v = take(sizeof(lm::ViewD) * n_views), o_s = take(32 * n), o_so = take(8 * (T + 1)), o_sv = take(4 * n),
+               o_tl = take(48 * T);
+  CU(c->d_mg_in.ensure(off + 256));
+  CU(c->d_mg_out.ensure(n + 256));
+  char *in = c->d_mg_in.as<char>();
+  CU(cudaEventRecord(c->ev0, s));
+  CU(cudaMemcpyAsync(in + o_v, views.data(), sizeof(lm::ViewD) * n_views, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(in + o_s, segs, 32 * n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(in + o_so, sup_off, 8 * (T + 1), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(in + o_sv, sup_view, 4 * n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(in + o_tl, track_line, 48 * T, cudaMemcpyHostToDevice, s));
+  lm::SupportParams p;
+  p.views = reinterpret_cast<const lm::ViewD *>(in + o_v);
+  p.sup_off = reinterpret_cast<const int64_t *>(in + o_so);
+  p.sup_view = reinterpret_cast<const int32_t *>(in + o_sv);
+  p.segs = reinterpret_cast<const double4 *>(in + o_s);
+  p.track_line = reinterpret_cast<const double *>(in + o_tl);
+  p.T = T; p.S = n;
+  p.th_angular2d = cfg->th_angular_2d; p.th_perp2d = cfg->th_perp_2d;
+  p.th_sv_angular3d = cfg->th_sv_angular_3d; p.th_overlap = cfg->th_overlap;
+  p.flags = c->d_mg_out.as<uint8_t>();
+  CU(cudaEventRecord(c->evk0, s));
+  lm::launch_support_flags(p, s);
+  CU(cudaEventRecord(c->evk1, s));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out_flags, p.flags, n, cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(c->ev1, s));
+  CU(cudaStreamSynchronize(s));
+  float ms = 0, msk = 0;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  CU(cudaEventElapsedTime(&msk, c->evk0, c->evk1));
+  c->mg_stats.n_supports = n;
+  c->mg_stats.last_flags_ms = ms;
+  c->mg_stats.last_flags_kernel_ms = msk;
+  c->mg_stats.n_kernel_launches += 1;
+  return LM_OK;
+}
+
+int lm_aggregate_lines(int64_t T, const int64_t *off, const double *lines, const double *scores, int32_t num_outliers,
+                       double *out_line) {
+  if (T < 0 || !off || !out_line) return fail(LM_ERR_INVALID, "NULL argument");
+  if (num_outliers < 0) return fail(LM_ERR_INVALID, "num_outliers must be >= 0");
+  std::vector<AggItem> it;
+  for (int64_t t = 0; t < T; ++t) {
+    const int64_t n = off[t + 1] - off[t];
+    double *o = out_line + 7 * t;
+    if (n <= 0) { memset(o, 0, 7 * sizeof(double)); continue; }
+    if (n >= 4 && 2 * n - 1 - num_outliers < num_outliers) return fail(LM_ERR_INVALID, "num_outliers too large for a group");
+    it.resize(n);
+    for (int64_t k = 0; k < n; ++k) it[k] = AggItem{lines + 7 * (off[t] + k), lines[7 * (off[t] + k) + 6], scores[off[t] + k]};
+    aggregate_items(it, num_outliers, o);
+  }
+  return LM_OK;
+}
+
+int64_t lm_remerge_labels(lm_ctx *c, int64_t T, const double *track_line, const uint8_t *active,
+                          const lm_linker_config *linker3d, int32_t *out_labels, int64_t *out_n_edges) {
+  if (!c || !linker3d) return fail(LM_ERR_INVALID, "NULL argument");
+  if (T < 0 || T >= ((int64_t)1 << 31)) return fail(LM_ERR_INVALID, "bad track count");
+  if (out_n_edges) *out_n_edges = 0;
+  if (T == 0) return 0;
+  if (!track_line || !active || !out_labels) return fail(LM_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  lm_linker_config l3 = *linker3d; // set_to_spatial_merging (line_linker.h:123-129)
+  l3.use_angle = 1; l3.use_overlap = 1; l3.use_perp = 0; l3.use_innerseg = 1; l3.use_scaleinv = 0;
+  int64_t n_active = 0;
+  for (int64_t t = 0; t < T; ++t) n_active += active[t] ? 1 : 0;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_l = take(56 * T), o_d = take(16 * T), o_a = take(T), o_c = take(16);
+  CU(c->d_mg_in.ensure(off + 256));
+  char *in = c->d_mg_in.as<char>();
+  CU(cudaEventRecord(c->ev0, s));
+  CU(cudaMemcpyAsync(in + o_l, track_line, 56 * T, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(in + o_a, active, T, cudaMemcpyHostToDevice, s));
+  lm::RemergeParams p;
+  p.lines = reinterpret_cast<const double *>(in + o_l);
+  p.dirf = reinterpret_cast<const float4 *>(in + o_d);
+  p.active = reinterpret_cast<const uint8_t *>(in + o_a);
+  p.T = T;
+  p.all_active = (n_active == T) ? 1 : 0;
+  p.lk = to_dev<double>(l3);
+  p.use_gate = (l3.th_angle > 0.0 && l3.th_angle < 89.0) ? 1 : 0;
+  p.cos_gate = p.use_gate ? (float)(std::cos(l3.th_angle * 3.14159265358979323846 / 180.0) - 1e-5) : -1.0f;
+  p.counter = reinterpret_cast<unsigned long long *>(in + o_c);
+  lm::launch_remerge_dirs(p.lines, T, reinterpret_cast<float4 *>(in + o_d), s);
+  unsigned long long cap = (unsigned long long)std::max<int64_t>(4 * T, 1 << 16);
+  unsigned long long cnt[2] = {0, 0};
+  float msk = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    CU(c->d_mg_edges.ensure(8 * cap));
+    p.edges = c->d_mg_edges.as<uint32_t>();
+    p.capacity = cap;
+    lm::launch_zero_words(reinterpret_cast<unsigned int *>(in + o_c), 4, s);
+    CU(cudaEventRecord(c->evk0, s));
+    if (n_active > 0) lm::launch_remerge_pairs(p, s);
+    CU(cudaEventRecord(c->evk1, s));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(cnt, p.counter, 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaEventElapsedTime(&msk, c->evk0, c->evk1));
+    c->mg_stats.n_kernel_launches += 3;
+    if (cnt[0] <= cap) break;
+    cap = cnt[0]; // the list overflowed: run again with the exact size
+  }
+  const int64_t ne = (int64_t)cnt[0];
+  std::vector<uint32_t> h_edges(2 * std::max<int64_t>(ne, 1));
+  if (ne) CU(cudaMemcpyAsync(h_edges.data(), p.edges, 8 * ne, cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(c->ev1, s));
+  CU(cudaStreamSynchronize(s));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  // std::set<pair> iteration order = lexicographic (merging.cc:558-560)
+  std::vector<uint64_t> keys(ne);
+  for (int64_t e = 0; e < ne; ++e) keys[e] = ((uint64_t)h_edges[2 * e] << 32) | h_edges[2 * e + 1];
+  std::sort(keys.begin(), keys.end());
+  // union-find with the group-size heuristic (merging.cc:562-589)
+  std::vector<int> parent(T, -1);
+  std::vector<int64_t> gsize(T, 1);
+  for (int64_t e = 0; e < ne; ++e) {
+    const size_t r1 = uf_root((size_t)(keys[e] >> 32), parent), r2 = uf_root((size_t)(keys[e] & 0xffffffffu), parent);
+    if (r1 == r2) continue;
+    if (gsize[r1] < gsize[r2]) { parent[r1] = (int)r2; gsize[r2] += gsize[r1]; gsize[r1] = 0; }
+    else { parent[r2] = (int)r1; gsize[r1] += gsize[r2]; gsize[r2] = 0; }
+  }
+  int64_t n_groups = 0;
+  for (int64_t t = 0; t < T; ++t) out_labels[t] = (parent[t] == -1) ? (int32_t)(n_groups++) : -1;
+  for (int64_t t = 0; t < T; ++t)
+    if (out_labels[t] == -1) out_labels[t] = out_labels[uf_root((size_t)t, parent)];
+  if (out_n_edges) *out_n_edges = ne;
+  c->mg_stats.n_tracks = T;
+  c->mg_stats.n_pairs_gated = (int64_t)cnt[1];
+  c->mg_stats.n_edges = ne;
+  c->mg_stats.last_remerge_ms = ms;
+  c->mg_stats.last_remerge_kernel_ms = msk;
+  return n_groups;
+}
+
+int lm_merge_get_stats(lm_ctx *c, lm_merge_stats *out) {
+  if (!c || !out) return fail(LM_ERR_INVALID, "NULL argument");
+  *out = c->mg_stats;
+  return LM_OK;
 }
 
 } // extern "C"

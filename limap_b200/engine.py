@@ -234,3 +234,52 @@ class BAEngine:
         remap[views] = np.arange(len(views), dtype=np.int32)
         return self.solve(ts.kvec[first_idx], ts.qvec[first_idx], ts.tvec[first_idx], ts.sup_off,
                           remap[ts.img_ids], ts.segs, ts.line3d, ts.line_init, **kw)
+
+
+class MergeEngine:
+    """Track filters and remerge on flat arrays (include/limap_b200.h: lm_tracks_support_flags,
+    lm_remerge_labels, lm_aggregate_lines)."""
+
+    def __init__(self, device=0, ctx=None):
+        self.ctx = ctx if ctx is not None else Context(device)
+
+    def support_flags(self, model_ids, kvec, qvec, tvec, sup_off, sup_view, segs, track_line, th_angular_2d=8.0,
+                      th_perp_2d=5.0, th_sv_angular_3d=75.0, th_overlap=0.5):
+        """uint8 per support: bit0 reprojection ok, bit1 sensitivity ok, bit2 overlap ok."""
+        f64 = lambda a: np.ascontiguousarray(a, np.float64)
+        kvec, qvec, tvec, segs, track_line = map(f64, (kvec, qvec, tvec, segs, track_line))
+        model_ids = None if model_ids is None else np.ascontiguousarray(model_ids, np.int32)
+        sup_off = np.ascontiguousarray(sup_off, np.int64)
+        sup_view = np.ascontiguousarray(sup_view, np.int32)
+        T = len(sup_off) - 1
+        flags = np.zeros(int(sup_off[-1]), np.uint8)
+        cfg = _cabi.FilterConfig(th_angular_2d, th_perp_2d, th_sv_angular_3d, th_overlap)
+        check(lib().lm_tracks_support_flags(self.ctx.handle, len(kvec), ptr(model_ids), ptr(kvec), ptr(qvec), ptr(tvec),
+                                            T, ptr(sup_off), ptr(sup_view), ptr(segs), ptr(track_line), C.byref(cfg),
+                                            ptr(flags)))
+        return flags
+
+    def remerge_labels(self, track_line, active, linker3d):
+        """(labels[T], n_groups, n_edges) of one RemergeLineTracks pass; linker3d: config.LinkerConfig."""
+        track_line = np.ascontiguousarray(track_line, np.float64)
+        active = np.ascontiguousarray(active, np.uint8)
+        T = len(track_line)
+        labels = np.zeros(T, np.int32)
+        ne = C.c_int64(0)
+        ng = check(lib().lm_remerge_labels(self.ctx.handle, T, ptr(track_line), ptr(active), C.byref(linker3d),
+                                           ptr(labels), C.byref(ne)))
+        return labels, int(ng), int(ne.value)
+
+    @staticmethod
+    def aggregate(off, lines, scores, num_outliers):
+        off = np.ascontiguousarray(off, np.int64)
+        lines = np.ascontiguousarray(lines, np.float64)
+        scores = np.ascontiguousarray(scores, np.float64)
+        out = np.zeros((len(off) - 1, 7))
+        check(lib().lm_aggregate_lines(len(off) - 1, ptr(off), ptr(lines), ptr(scores), int(num_outliers), ptr(out)))
+        return out
+
+    def stats(self):
+        st = _cabi.MergeStats()
+        check(lib().lm_merge_get_stats(self.ctx.handle, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _cabi.MergeStats._fields_}

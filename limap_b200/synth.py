@@ -279,3 +279,25 @@ def make_tracks(T=100, S=30, V=300, seed=1237, noise_px=0.5, perturb=0.05, scale
                     qvec=np.ascontiguousarray(qs[views]), tvec=np.ascontiguousarray(ts[views]),
                     img_ids=views.astype(np.int32), line3d=np.ascontiguousarray(line3d),
                     line_init=np.ascontiguousarray(line_init), gt=gt)
+
+
+def make_track_lines(T, dup_frac=0.3, seed=0, extent=20.0, unc=0.05, noise=0.002):
+    """Track lines for the remerge pair test: T unit-scale 3D segments (start3, end3, uncertainty) in a cube,
+    a `dup_frac` share of them noisy, partly shifted copies of other tracks (the fragments remerging joins)."""
+    rng = np.random.default_rng(seed)
+    n_base = max(1, int(round(T * (1.0 - dup_frac))))
+    c = rng.uniform(-extent, extent, (n_base, 3))
+    d = rng.normal(size=(n_base, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    half = rng.uniform(0.5, 1.5, (n_base, 1))
+    L = np.concatenate([c - d * half, c + d * half, np.full((n_base, 1), unc)], 1)
+    n_dup = T - n_base
+    if n_dup > 0:
+        src = rng.integers(0, n_base, n_dup)
+        shift = rng.uniform(-0.8, 0.8, (n_dup, 1)) * half[src]
+        D = L[src].copy()
+        D[:, :3] += d[src] * shift + rng.normal(scale=noise, size=(n_dup, 3))
+        D[:, 3:6] += d[src] * shift + rng.normal(scale=noise, size=(n_dup, 3))
+        D[:, 6] = unc * rng.uniform(0.5, 2.0, n_dup)
+        L = np.concatenate([L, D])
+    return np.ascontiguousarray(L[rng.permutation(T)])

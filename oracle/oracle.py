@@ -255,3 +255,57 @@ def detect_vps(line_off, segs, min_length=40.0, inlier_threshold=1.0, min_num_su
     vps = np.zeros((cap, 3))
     tot = L.orc_vp_detect(n, _p(line_off), _p(segs), C.byref(cfg), _p(labels), _p(vp_off), _p(vps), cap)
     return labels, vp_off, vps[:tot]
+
+
+# ---- track filters + remerge (orc_merging.cpp) -----------------------------------------------------------
+class OrcLinkerCfg(C.Structure):  # orc::LinkerConfig
+    _fields_ = [(n, C.c_double) for n in ("score_th", "th_angle", "th_overlap", "th_smartoverlap", "th_smartangle",
+                                           "th_perp", "th_innerseg", "th_scaleinv")] + \
+               [(n, C.c_int) for n in ("use_angle", "use_overlap", "use_smartangle", "use_perp", "use_innerseg",
+                                       "use_scaleinv")]
+
+
+def track_support_flags(model_ids, kvec, qvec, tvec, sup_off, sup_view, segs, track_line, th_angular_2d=8.0,
+                        th_perp_2d=5.0, th_sv_angular_3d=75.0, th_overlap=0.5, threads=None):
+    """CheckReprojection / CheckSensitivity / overlap bits per supporting line (merging_utils.cc:27-155)."""
+    L = lib()
+    L.orc_set_num_threads(int(threads) if threads else min(8, usable_cpus()))
+    L.orc_track_support_flags.argtypes = [C.c_int32, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P] + [C.c_double] * 4 + [_P]
+    sup_off = np.ascontiguousarray(sup_off, np.int64)
+    sup_view = np.ascontiguousarray(sup_view, np.int32)
+    model_ids = None if model_ids is None else np.ascontiguousarray(model_ids, np.int32)
+    kvec, qvec, tvec, segs, track_line = map(_f64, (kvec, qvec, tvec, segs, track_line))
+    flags = np.zeros(int(sup_off[-1]), np.uint8)
+    L.orc_track_support_flags(len(kvec), _p(model_ids), _p(kvec), _p(qvec), _p(tvec), len(sup_off) - 1, _p(sup_off),
+                              _p(sup_view), _p(segs), _p(track_line), th_angular_2d, th_perp_2d, th_sv_angular_3d,
+                              th_overlap, _p(flags))
+    return flags
+
+
+def aggregate_lines(off, lines, scores, num_outliers):
+    L = lib()
+    L.orc_aggregate_lines.argtypes = [C.c_int64, _P, _P, _P, C.c_int32, _P]
+    off = np.ascontiguousarray(off, np.int64)
+    lines, scores = _f64(lines), _f64(scores)
+    out = np.zeros((len(off) - 1, 7))
+    L.orc_aggregate_lines(len(off) - 1, _p(off), _p(lines), _p(scores), int(num_outliers), _p(out))
+    return out
+
+
+def remerge_labels(track_line, active, linker, threads=None):
+    """One RemergeLineTracks pass up to the group labels. linker: dict of LineLinker3dConfig fields."""
+    L = lib()
+    L.orc_set_num_threads(int(threads) if threads else min(8, usable_cpus()))
+    L.orc_remerge_labels.restype = C.c_int64
+    L.orc_remerge_labels.argtypes = [C.c_int64, _P, _P, _P, _P, _P]
+    d = dict(score_th=0.5, th_angle=10.0, th_overlap=0.01, th_smartoverlap=0.1, th_smartangle=1.0, th_perp=0.02,
+             th_innerseg=0.02, th_scaleinv=0.01, use_angle=1, use_overlap=1, use_smartangle=1, use_perp=0,
+             use_innerseg=1, use_scaleinv=0)  # line_linker.h:85-111
+    d.update({k: v for k, v in linker.items() if k in d})
+    cfg = OrcLinkerCfg(*[float(d[n]) if t is C.c_double else int(bool(d[n])) for n, t in OrcLinkerCfg._fields_])
+    track_line = _f64(track_line)
+    active = np.ascontiguousarray(active, np.uint8)
+    labels = np.zeros(len(track_line), np.int32)
+    ne = C.c_int64(0)
+    ng = L.orc_remerge_labels(len(track_line), _p(track_line), _p(active), C.byref(cfg), _p(labels), C.byref(ne))
+    return labels, int(ng), int(ne.value)
