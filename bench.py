@@ -400,6 +400,44 @@ def main():
                                      "sample": "1500 tracks x 30 supports, Ceres-style LM restatement, OpenMP over "
                                                "tracks"}
 
+    # ---- M3: remerge pair test: all-pairs check_connection over 1e5 track lines, rank 0 ----
+    remerge = None
+    if not args.no_lm and rank == 0:
+        from limap_b200.config import LINKER3D_DEFAULTS, make_linker
+        from limap_b200.engine import MergeEngine
+        from limap_b200.synth import make_track_lines
+        lk = dict(score_th=0.5, th_angle=5.0, th_overlap=0.001, th_smartoverlap=0.1, th_smartangle=1.0, th_perp=1.0,
+                  th_innerseg=1.0)  # cfgs/triangulation/default.yaml:99-108
+        Tm = 100000
+        TL = make_track_lines(Tm, dup_frac=0.3, seed=1, extent=60.0)
+        me = MergeEngine(ctx=eng.ctx)
+        act = np.ones(Tm, np.uint8)
+        k_ms, w_ms = [], []
+        for it in range(2 + args.steps):
+            t0 = time.perf_counter()
+            _, ng, ne = me.remerge_labels(TL, act, make_linker(LINKER3D_DEFAULTS, lk))
+            if it >= 2:
+                w_ms.append((time.perf_counter() - t0) * 1e3)
+                k_ms.append(me.stats()["last_remerge_kernel_ms"])
+        pairs = Tm * (Tm - 1) / 2
+        remerge = {"metric": "remerge pair tests/sec", "unit": "track pairs/s",
+                   "config": {"workload": "remerge100k", "tracks": Tm, "groups": ng, "edges": ne,
+                              "pairs_past_fp32_gate": int(me.stats()["n_pairs_gated"])},
+                   "value_kernel": pairs / (float(np.mean(k_ms)) * 1e-3), "kernel_ms": float(np.mean(k_ms)),
+                   "e2e": {"value": pairs / (float(np.mean(w_ms)) * 1e-3),
+                           "note": "lm_remerge_labels from host arrays: H2D, pair kernel, edge list D2H, host union-find"},
+                   "dtype": "f32 gate + f64 check"}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as orc
+            Ts = 20000
+            sub = make_track_lines(Ts, dup_frac=0.3, seed=1, extent=60.0)
+            t0 = time.perf_counter()
+            orc.remerge_labels(sub, np.ones(Ts, np.uint8), lk, threads=orc.usable_cpus())
+            dtc = time.perf_counter() - t0
+            remerge["cpu_baseline"] = {"value": Ts * (Ts - 1) / 2 / dtc, "unit": "track pairs/s",
+                                       "cores": orc.usable_cpus(), "kind": "port",
+                                       "sample": f"{Ts} tracks, all pairs, OpenMP over tracks ({dtc:.2f} s)"}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -411,7 +449,7 @@ def main():
                            "parallelism": f"source-image shards x{world}",
                            "l2": "inputs larger than L2 (match rows + sort buffers > 126 MB per step)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu, "lm_ba": lm_ba}
+                "cpu_baseline": cpu, "lm_ba": lm_ba, "remerge": remerge}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

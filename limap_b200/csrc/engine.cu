@@ -1883,7 +1883,7 @@ int64_t lm_remerge_labels(lm_ctx *c, int64_t T, const double *track_line, const 
   for (int64_t t = 0; t < T; ++t) n_active += active[t] ? 1 : 0;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-  const size_t o_l = take(56 * T), o_d = take(16 * T), o_a = take(T), o_c = take(16);
+  const size_t o_l = take(56 * T), o_d = take(16 * T), o_b = take(16 * T), o_a = take(T), o_c = take(16);
   CU(c->d_mg_in.ensure(off + 256));
   char *in = c->d_mg_in.as<char>();
   CU(cudaEventRecord(c->ev0, s));
@@ -1892,6 +1892,7 @@ int64_t lm_remerge_labels(lm_ctx *c, int64_t T, const double *track_line, const 
   lm::RemergeParams p;
   p.lines = reinterpret_cast<const double *>(in + o_l);
   p.dirf = reinterpret_cast<const float4 *>(in + o_d);
+  p.ballf = reinterpret_cast<const float4 *>(in + o_b);
   p.active = reinterpret_cast<const uint8_t *>(in + o_a);
   p.T = T;
   p.all_active = (n_active == T) ? 1 : 0;
@@ -1899,7 +1900,19 @@ int64_t lm_remerge_labels(lm_ctx *c, int64_t T, const double *track_line, const 
   p.use_gate = (l3.th_angle > 0.0 && l3.th_angle < 89.0) ? 1 : 0;
   p.cos_gate = p.use_gate ? (float)(std::cos(l3.th_angle * 3.14159265358979323846 / 180.0) - 1e-5) : -1.0f;
   p.counter = reinterpret_cast<unsigned long long *>(in + o_c);
-  lm::launch_remerge_dirs(p.lines, T, reinterpret_cast<float4 *>(in + o_d), s);
+  p.use_ball = (l3.use_innerseg && l3.th_innerseg >= 0.0 && l3.score_th > 0.0 && l3.score_th < 1.0) ? 1 : 0;
+  double origin[3] = {0, 0, 0}; // mean midpoint: keeps the fp32 coordinates of the ball gate small
+  {
+    int64_t nfin = 0;
+    for (int64_t t = 0; t < T; ++t) {
+      const double *l = track_line + 7 * t;
+      const double m[3] = {0.5 * (l[0] + l[3]), 0.5 * (l[1] + l[4]), 0.5 * (l[2] + l[5])};
+      if (std::isfinite(m[0]) && std::isfinite(m[1]) && std::isfinite(m[2])) { origin[0] += m[0]; origin[1] += m[1]; origin[2] += m[2]; ++nfin; }
+    }
+    if (nfin) for (int k = 0; k < 3; ++k) origin[k] /= (double)nfin;
+  }
+  lm::launch_remerge_dirs(p.lines, T, origin, l3.th_innerseg, reinterpret_cast<float4 *>(in + o_d),
+                          reinterpret_cast<float4 *>(in + o_b), s);
   unsigned long long cap = (unsigned long long)std::max<int64_t>(4 * T, 1 << 16);
   unsigned long long cnt[2] = {0, 0};
   float msk = 0;

@@ -6,7 +6,8 @@
 //   supporting line, fp64, formulas in the reference's order; 32 B segment + 4 B view id in, 1 B out.
 // remerge_pairs_kernel: RemergeLineTracks tests every pair of track lines with LineLinker3d::check_connection
 //   (merging.cc:527-556, O(T^2)). Tiles of 256 x 256 pairs; the angle test is gated in fp32 on unit directions
-//   (|cos| >= cos(th_angle) - 1e-5: a pair that fails the gate fails the fp64 angle test by > 1e3 ulp of fp32),
+//   (|cos| >= cos(th_angle) - 1e-5: a pair that fails the gate fails the fp64 angle test by > 1e3 ulp of fp32)
+//   and, when the inner-segment test is on, on bounding balls grown by the largest passing distance,
 //   survivors are queued per warp and checked densely in fp64 with the reference's formulas and argument
 //   order. Output: unordered list of connected pairs (a < b); the union-find stays on the host (sequential).
 #include "merge_kernels.cuh"
@@ -93,16 +94,30 @@ void launch_support_flags(const SupportParams &p, cudaStream_t s) {
   support_flags_kernel<<<(unsigned)((p.S + 255) / 256), 256, 0, s>>>(p);
 }
 
-__global__ void remerge_dirs_kernel(const double *lines, int64_t T, float4 *dirf) {
+// fp32 gate records: unit direction, and a ball (midpoint relative to `origin`, radius) that contains the
+// segment grown by the largest inner-segment distance that can still pass: score_innerseg >= score_th
+// <=> dist <= th_innerseg * min(unc) (line_linker.cc:253-262 with multiplier() = 1/sqrt(-2 ln score_th)).
+// Two segments whose inner-segment distance is d have points within d of each other, so their grown balls
+// intersect; w carries the radius with the fp32 error budget (1e-3 relative + 1e-5 of the coordinates).
+__global__ void remerge_dirs_kernel(const double *lines, int64_t T, double ox, double oy, double oz, double th_innerseg,
+                                    float4 *dirf, float4 *ballf) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const double *l = lines + 7 * t;
-  const vec3<double> d = normalized(mk3(l[3] - l[0], l[4] - l[1], l[5] - l[2]));
+  const vec3<double> v = mk3(l[3] - l[0], l[4] - l[1], l[5] - l[2]);
+  const vec3<double> d = normalized(v);
   dirf[t] = make_float4((float)d.x, (float)d.y, (float)d.z, 0.f);
+  const double mx = 0.5 * (l[0] + l[3]) - ox, my = 0.5 * (l[1] + l[4]) - oy, mz = 0.5 * (l[2] + l[5]) - oz;
+  double r = 0.5 * norm(v) + th_innerseg * fabs(l[6]);
+  r = r * 1.001 + 1e-5 * (fabs(mx) + fabs(my) + fabs(mz)) + 1e-30;
+  if (!(r == r) || !(mx == mx) || !(my == my) || !(mz == mz)) r = 3e38; // NaN input: never gate it away
+  ballf[t] = make_float4((float)mx, (float)my, (float)mz, (float)fmin(r, 1e18));
 }
-void launch_remerge_dirs(const double *lines, int64_t T, float4 *dirf, cudaStream_t s) {
+void launch_remerge_dirs(const double *lines, int64_t T, const double origin[3], double th_innerseg, float4 *dirf,
+                         float4 *ballf, cudaStream_t s) {
   if (T <= 0) return;
-  remerge_dirs_kernel<<<(unsigned)((T + 255) / 256), 256, 0, s>>>(lines, T, dirf);
+  remerge_dirs_kernel<<<(unsigned)((T + 255) / 256), 256, 0, s>>>(lines, T, origin[0], origin[1], origin[2],
+                                                                 th_innerseg, dirf, ballf);
 }
 
 constexpr int kTile = 256;
@@ -142,7 +157,7 @@ LM_D void drain(const RemergeParams &p, const uint2 *q, int n, int lane) {
   }
 }
 
-__global__ void __launch_bounds__(kTile) remerge_pairs_kernel(const __grid_constant__ RemergeParams p) {
+__global__ void __launch_bounds__(kTile, 4) remerge_pairs_kernel(const __grid_constant__ RemergeParams p) {
   // upper-triangular tile grid: blockIdx.x enumerates (ta <= tb)
   const int64_t n_tiles = (p.T + kTile - 1) / kTile;
   int64_t ta = 0, rem = blockIdx.x;
@@ -155,7 +170,7 @@ __global__ void __launch_bounds__(kTile) remerge_pairs_kernel(const __grid_const
     rem -= ta * n_tiles - ta * (ta - 1) / 2;
   }
   const int64_t tb = ta + rem;
-  __shared__ float4 sb[kTile];
+  __shared__ float4 sb[kTile], sball[kTile];
   __shared__ uint8_t sact[kTile];
   __shared__ uint2 queue[kTile / 32][kQueue];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -163,33 +178,52 @@ __global__ void __launch_bounds__(kTile) remerge_pairs_kernel(const __grid_const
   const int nb = (int)min((int64_t)kTile, p.T - b0);
   if (tid < nb) {
     sb[tid] = p.dirf[b0 + tid];
+    sball[tid] = p.ballf[b0 + tid];
     sact[tid] = p.active[b0 + tid];
+  } else {
+    sb[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sball[tid] = make_float4(1e30f, 1e30f, 1e30f, 0.f); // never inside a ball
+    sact[tid] = 0;
   }
   __syncthreads();
   const bool a_ok = a < p.T;
-  float4 da = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 da = make_float4(0.f, 0.f, 0.f, 0.f), ba = make_float4(0.f, 0.f, 0.f, 0.f);
   bool a_act = false;
-  if (a_ok) { da = p.dirf[a]; a_act = p.active[a] != 0; }
+  if (a_ok) { da = p.dirf[a]; ba = p.ballf[a]; a_act = p.active[a] != 0; }
   uint2 *q = queue[warp];
   int qn = 0; // warp-uniform
   unsigned long long gated = 0;
-  for (int j = 0; j < nb; ++j) {
-    const int64_t b = b0 + j;
-    bool pass = a_ok && b > a && (p.all_active || a_act || sact[j]);
-    if (pass && p.use_gate) {
-      const float4 db = sb[j];
-      pass = fabsf(da.x * db.x + da.y * db.y + da.z * db.z) >= p.cos_gate;
+  const bool use_ball = p.use_ball != 0;
+  const int jfirst = (ta == tb) ? (tid & ~31) : 0; // diagonal tile: b > a starts in this warp's own column block
+  for (int j0 = jfirst & ~3; j0 < nb; j0 += 4) {
+    bool ps[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 bb = sball[j0 + u];
+      const float dx = ba.x - bb.x, dy = ba.y - bb.y, dz = ba.z - bb.z, rs = ba.w + bb.w;
+      ps[u] = !use_ball || !(dx * dx + dy * dy + dz * dz > rs * rs * 1.0001f); // NaN-safe: only a clear miss drops
     }
-    const unsigned m = __ballot_sync(0xffffffffu, pass);
-    if (m) {
-      if (pass) q[qn + __popc(m & ((1u << lane) - 1))] = make_uint2((uint32_t)a, (uint32_t)b);
-      qn += __popc(m);
-      gated += (lane == 0) ? __popc(m) : 0;
-      __syncwarp();
-      if (qn >= 32) {
-        drain(p, q + (qn - 32), 32, lane);
-        qn -= 32;
+    if (!__any_sync(0xffffffffu, ps[0] | ps[1] | ps[2] | ps[3])) continue;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;
+      const int64_t b = b0 + j;
+      bool pass = ps[u] && a_ok && j < nb && b > a && (p.all_active || a_act || sact[j]);
+      if (pass && p.use_gate) {
+        const float4 db = sb[j];
+        pass = fabsf(da.x * db.x + da.y * db.y + da.z * db.z) >= p.cos_gate;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (m) {
+        if (pass) q[qn + __popc(m & ((1u << lane) - 1))] = make_uint2((uint32_t)a, (uint32_t)b);
+        qn += __popc(m);
+        gated += (lane == 0) ? __popc(m) : 0;
         __syncwarp();
+        if (qn >= 32) {
+          drain(p, q + (qn - 32), 32, lane);
+          qn -= 32;
+          __syncwarp();
+        }
       }
     }
   }

@@ -21,17 +21,20 @@ void launch_support_flags(const SupportParams &p, cudaStream_t s);
 struct RemergeParams {
   const double *lines;       // [T][7] start, end, uncertainty
   const float4 *dirf;        // [T] unit direction in fp32 (gate), w unused
+  const float4 *ballf;       // [T] midpoint - origin, grown radius (gate)
   const uint8_t *active;     // [T]
   int64_t T;
   int all_active;
   LinkerDev<double> lk;      // after set_to_spatial_merging()
   float cos_gate;            // cos(th_angle) - margin; gate used only when use_gate
   int use_gate;
+  int use_ball;              // use_innerseg: the ball gate is a necessary condition
   uint32_t *edges;           // [capacity][2] (a < b), unordered
   unsigned long long *counter; // [2]: edges found, pairs past the gate
   unsigned long long capacity;
 };
-void launch_remerge_dirs(const double *lines, int64_t T, float4 *dirf, cudaStream_t s);
+void launch_remerge_dirs(const double *lines, int64_t T, const double origin[3], double th_innerseg, float4 *dirf,
+                         float4 *ballf, cudaStream_t s);
 void launch_remerge_pairs(const RemergeParams &p, cudaStream_t s);
 
 } // namespace lm
