@@ -4,10 +4,11 @@ Only the hot-path packages exist; everything else of cvg/limap is out of scope (
 import importlib
 import sys
 
-for _name in ("base", "triangulation", "optimize", "vplib", "merging"):
+for _name in ("base", "triangulation", "optimize", "vplib", "merging", "util", "util.io"):
     try:
         _m = importlib.import_module(f"limap_b200.{_name}")
     except ModuleNotFoundError:
         continue
     sys.modules[f"limap.{_name}"] = _m
-    globals()[_name] = _m
+    if "." not in _name:
+        globals()[_name] = _m

@@ -536,6 +536,79 @@ class LineTrack:
     def HasImage(self, image_id):
         return image_id in self.image_id_list
 
+    def Resize(self, n_lines):  # base/linetrack.cc Resize
+        self.image_id_list, self.line_id_list = [0] * n_lines, [0] * n_lines
+        self.line2d_list = [Line2d() for _ in range(n_lines)]
+        self.node_id_list, self.score_list = [0] * n_lines, [0.0] * n_lines
+        self.line3d_list = [Line3d() for _ in range(n_lines)]
+
+    def Write(self, filename):
+        """base/linetrack.cc:133-213 (std::fixed, setprecision(10); NaN endpoints are written as 0)."""
+        ff = lambda v: f"{float(v):.10f}"
+        n_lines = self.count_lines()
+        with open(filename, "w") as f:
+            row = ""
+            for v in list(self.line.start) + list(self.line.end):
+                row += (ff(0.0) if np.isnan(v) else ff(v)) + " "
+            f.write(row + "\n")
+            f.write(f"{n_lines} {self.count_images()}\n")
+            f.write("image_id_list " + "".join(f"{int(i)} " for i in self.image_id_list) + "\n")
+            f.write("line_id_list " + "".join(f"{int(i)} " for i in self.line_id_list) + "\n")
+            f.write("line2d_list\n")
+            for l in self.line2d_list:
+                f.write(f"{ff(l.start[0])} {ff(l.start[1])} {ff(l.end[0])} {ff(l.end[1])} \n")
+            if self.node_id_list:
+                f.write("node_id_list " + "".join(f"{int(i)} " for i in self.node_id_list) + "\n")
+            if self.score_list:
+                f.write("score_list " + "".join(f"{ff(x)} " for x in self.score_list) + "\n")
+            if self.line3d_list:
+                f.write("line3d_list\n")
+                for l in self.line3d_list:
+                    f.write("".join(f"{ff(v)} " for v in list(l.start) + list(l.end)) + "\n")
+            f.write("END\n")
+
+    def Read(self, filename):
+        """base/linetrack.cc:215-270 (token stream like operator>>)."""
+        with open(filename) as f:
+            tok = f.read().split()
+        p = 0
+
+        def take(n, conv):
+            nonlocal p
+            out = [conv(x) for x in tok[p:p + n]]
+            p += n
+            return out
+
+        v = take(6, float)
+        self.line = Line3d(np.array(v[:3]), np.array(v[3:]))
+        n_lines, _ = take(2, int)
+        self.Resize(n_lines)
+        if take(1, str) != ["image_id_list"]:
+            raise RuntimeError("THROW_CHECK_EQ(str, \"image_id_list\")")
+        self.image_id_list = take(n_lines, int)
+        if take(1, str) != ["line_id_list"]:
+            raise RuntimeError("THROW_CHECK_EQ(str, \"line_id_list\")")
+        self.line_id_list = take(n_lines, int)
+        if take(1, str) != ["line2d_list"]:  # files of the previous version stop here
+            return
+        for i in range(n_lines):
+            a = take(4, float)
+            self.line2d_list[i] = Line2d(np.array(a[:2]), np.array(a[2:]))
+        s = take(1, str)
+        if s == ["END"] or not s:
+            return
+        if s != ["node_id_list"]:
+            raise RuntimeError("THROW_CHECK_EQ(str, \"node_id_list\")")
+        self.node_id_list = take(n_lines, int)
+        if take(1, str) != ["score_list"]:
+            raise RuntimeError("THROW_CHECK_EQ(str, \"score_list\")")
+        self.score_list = take(n_lines, float)
+        if take(1, str) != ["line3d_list"]:
+            raise RuntimeError("THROW_CHECK_EQ(str, \"line3d_list\")")
+        for i in range(n_lines):
+            a = take(6, float)
+            self.line3d_list[i] = Line3d(np.array(a[:3]), np.array(a[3:]))
+
     def as_dict(self):
         return {"line": self.line.as_array(), "image_id_list": list(self.image_id_list),
                 "line_id_list": list(self.line_id_list), "line2d_list": [l.as_array() for l in self.line2d_list],

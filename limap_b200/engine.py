@@ -84,6 +84,29 @@ class TriEngine:
         check(lib().lm_tri_add_image_matches_device(self.ctx.handle, int(img_id), len(ng_ids),
                                                     ptr(ng_ids), ptr(row_off), C.c_void_p(int(d_pairs_ptr))))
 
+    def add_image_matches_torch(self, img_id, matches):
+        """matches: {ng_img_id: (M,2) integer torch tensor on this engine's CUDA device} -- the top-k output of a GPU
+        matcher (line2d/endpoints/matcher.py:87-103) goes into the match store device-to-device, no host hop."""
+        import torch
+        ngs = sorted(matches.keys())
+        row_off = np.zeros(len(ngs) + 1, np.int64)
+        parts = []
+        for i, g in enumerate(ngs):
+            m = matches[g]
+            if m.numel() and (m.dim() != 2 or m.shape[1] != 2):
+                raise RuntimeError("match_info.cols() must be 2")
+            if not m.is_cuda or m.device.index != self.ctx.device:
+                raise RuntimeError(f"matches must live on cuda:{self.ctx.device}")
+            parts.append(m.reshape(-1, 2).to(torch.int32))
+            row_off[i + 1] = row_off[i] + parts[-1].shape[0]
+        if parts:
+            pairs = torch.cat(parts, 0).contiguous()
+        else:
+            pairs = torch.zeros((0, 2), dtype=torch.int32, device=f"cuda:{self.ctx.device}")
+        torch.cuda.current_stream(pairs.device).synchronize()  # the engine copies on its own stream
+        self.ctx._keep.append(pairs)
+        self.add_image_matches_device(img_id, np.asarray(ngs, np.int32), row_off, pairs.data_ptr())
+
     def add_image_matches_dict(self, img_id, matches):
         """matches: {ng_img_id: (M,2) int array}; neighbours are visited in ascending id order
         (std::map iteration, base_line_triangulator.cc:74)."""

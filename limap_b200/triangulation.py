@@ -83,6 +83,11 @@ class GlobalLineTriangulator:
 
     def TriangulateImage(self, img_id, matches):
         n_lines = self.CountLines(img_id)
+        if matches and all(type(m).__module__.startswith("torch") and m.is_cuda for m in matches.values()):
+            # device tensors straight from a GPU matcher: out-of-range ids are reported by the engine at run time
+            self._neighbors[int(img_id)] = sorted(int(k) for k in matches)
+            self._eng.add_image_matches_torch(int(img_id), {int(k): v for k, v in matches.items()})
+            return
         for ng, m in matches.items():
             m = np.asarray(m)
             if m.size:

@@ -86,3 +86,53 @@ def test_triangulate_image_index_error_and_model_check():
         tri.TriangulateImage(0, bad)
     with pytest.raises(RuntimeError):
         base.Camera("OPENCV", [1, 1, 0, 0, 0, 0, 0, 0], 0, (10, 10))
+
+
+def test_disk_formats_and_device_tensor_ingress(tmp_path):
+    """§8(f) rank 2: the runner's inputs read back from the reference's file formats, and matches handed over as CUDA
+    tensors (GPU matcher output), give the tracks of the in-memory host path."""
+    import torch
+    import limap.base as base
+    import limap.triangulation as triangulation
+    import limap.util.io as limapio
+    sc = make_scene(V=8, L=120, N=5, K=5, seed=43)
+    cfg = dict(DEFAULT_YAML_TRIANGULATION)
+    imagecols = _imagecols(sc)
+    d = str(tmp_path)
+    os_segs = {int(i): sc.lines_of(v) for v, i in enumerate(sc.img_ids)}
+    for i, s in os_segs.items():
+        limapio.save_txt_segments(d, i, s)
+        limapio.save_match(d, i, sc.matches[i])
+    neighbors = {int(i): sorted(sc.matches[int(i)].keys()) for i in sc.img_ids}
+    limapio.save_txt_metainfos(d + "/metainfos.txt", neighbors, sc.ranges)
+    limapio.save_npy(d + "/imagecols.npy", imagecols.as_dict())
+
+    def run(segs, ranges, ic, matches_of):
+        tri = triangulation.GlobalLineTriangulator(cfg)
+        tri.SetRanges(ranges)
+        tri.Init(base.get_all_lines_2d(segs), ic)
+        for img_id in ic.get_img_ids():
+            tri.TriangulateImage(img_id, matches_of(img_id))
+        return tri.ComputeLineTracks()
+
+    ref = run(os_segs, sc.ranges, imagecols, lambda i: sc.matches[i])
+    # from disk
+    nb2, ranges2 = limapio.read_txt_metainfos(d + "/metainfos.txt")
+    ic2 = base.ImageCollection(limapio.read_npy(d + "/imagecols.npy").item())
+    segs2 = {i: limapio.read_txt_segments(d, i) for i in ic2.get_img_ids()}
+    assert nb2 == neighbors
+    got = run(segs2, ranges2, ic2, lambda i: limapio.read_match(d, i))
+    # from device tensors
+    dev = run(os_segs, sc.ranges, imagecols,
+              lambda i: {g: torch.as_tensor(np.asarray(m), device="cuda") for g, m in sc.matches[i].items()})
+    for other in (got, dev):
+        assert len(other) == len(ref) > 20
+        for a, b in zip(ref, other):
+            assert a.image_id_list == b.image_id_list and a.line_id_list == b.line_id_list
+            assert np.abs(a.line.as_array() - b.line.as_array()).max() <= 1e-9
+    # tracks written and read back
+    limapio.save_folder_linetracks(d + "/finaltracks", ref)
+    back = limapio.read_folder_linetracks(d + "/finaltracks")
+    assert len(back) == len(ref)
+    assert all(x.line_id_list == y.line_id_list and x.node_id_list == y.node_id_list for x, y in zip(ref, back))
+    assert max(np.abs(x.line.as_array() - y.line.as_array()).max() for x, y in zip(ref, back)) <= 1e-9
