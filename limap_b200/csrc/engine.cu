@@ -826,6 +826,10 @@ int lm_tri_run(lm_ctx *c) {
     p.inv_sig_a2 = 1.0 / (p.l2d.th_angle * p.l2d.mult);
     p.inv_sig_p2 = 1.0 / (p.l2d.th_perp * p.l2d.mult);
     p.q_cut3 = -2.0 * std::log(p.l3d.score_th) * (1.0 + 1e-9);
+    p.q_cut3_lo = -2.0 * std::log(p.l3d.score_th) * (1.0 - 1e-9);
+    p.q_cut2 = -2.0 * std::log(p.l2d.score_th) * (1.0 + 1e-9);
+    p.q_cut2_lo = -2.0 * std::log(p.l2d.score_th) * (1.0 - 1e-9);
+    p.inv_smart_den2 = 1.0 / (p.l2d.th_smartoverlap - p.l2d.th_overlap);
   }
   // ---- groups of source images: sort + node kernel of group g overlap the upload of group g+1 -----------
   int nbits = 1;
@@ -904,7 +908,8 @@ int lm_tri_run(lm_ctx *c) {
     if ((int64_t)max_rows * ns > 65535) return fail(LM_ERR_INVALID, "more than 65535 candidates possible for one 2D line");
     int cap = 32;
     while (cap < max_rows * ns) cap += 32;
-    size_t smem = lm::tri_smem_bytes(cap);
+    const bool fast_kernel = p.fast_forms && !p.use_endpoints_triangulation;
+    size_t smem = lm::tri_smem_bytes(cap, fast_kernel);
     int grid;
     const size_t smem_limit = (size_t)std::max(0, c->max_smem_optin - 1024);
     if (smem <= smem_limit) {

@@ -147,7 +147,7 @@ LM_D bool pair_connected(const RemergeParams &p, uint32_t a, uint32_t b) {
   return ok;
 }
 
-LM_D void drain(const RemergeParams &p, const uint2 *q, int n, int lane) {
+__device__ __noinline__ void drain(const RemergeParams &p, const uint2 *q, int n, int lane) {
   if (lane < n) {
     const uint2 e = q[lane];
     if (pair_connected(p, e.x, e.y)) {

@@ -29,8 +29,10 @@ static constexpr int kListExtra = kFlush + 32;
 // meta (3 x uint32); plus per warp two survivor lists (uint32) and one prefilter list (uint16)
 static constexpr int kCandBytes = 17 * 8 + 48 + 12;
 
-size_t tri_smem_bytes(int cap) {
-  return (size_t)cap * kCandBytes + (size_t)kWarps * 2 * (cap + kListExtra) * 4 + (size_t)kWarps * cap * 2;
+// fast layout: one survivor list per warp (no 2d-gate stage) and three more doubles per candidate (reciprocals)
+size_t tri_smem_bytes(int cap, bool fast) {
+  const size_t lists = fast ? 1 : 2, extra = fast ? 24 : 0;
+  return (size_t)cap * (kCandBytes + extra) + (size_t)kWarps * lists * (cap + kListExtra) * 4 + (size_t)kWarps * cap * 2;
 }
 
 // fp32 copy of a candidate for the pruning gates (three 16-byte loads, conflict-free at 48-byte stride):
@@ -44,21 +46,25 @@ struct __align__(16) GateRec {
 
 struct Slab {
   double *sx, *sy, *sz, *ex, *ey, *ez, *dx, *dy, *dz, *zs, *ze, *unc, *q0, *q1, *q2, *q3, *score;
+  double *izs2, *ize2, *inb; // fast layout only: 1/(zs+EPS)^2, 1/(ze+EPS)^2, 1/|q|^2
   GateRec *gate;
   uint32_t *ng, *row, *meta; // meta = view << 16 | direction bucket
   uint32_t *list;            // [kWarps][2][cap + kListExtra]: (row << 16 | j) survivor entries
   uint16_t *list0;           // [kWarps][cap]: j of the bucket prefilter
-  LM_D void carve(char *base, int cap) {
+  LM_D void carve(char *base, int cap, bool fast) {
     double *d = reinterpret_cast<double *>(base);
     sx = d; sy = sx + cap; sz = sy + cap; ex = sz + cap; ey = ex + cap; ez = ey + cap;
     dx = ez + cap; dy = dx + cap; dz = dy + cap; zs = dz + cap; ze = zs + cap; unc = ze + cap;
     q0 = unc + cap; q1 = q0 + cap; q2 = q1 + cap; q3 = q2 + cap; score = q3 + cap;
-    gate = reinterpret_cast<GateRec *>(score + cap);
+    double *nx = score + cap;
+    izs2 = ize2 = inb = nullptr;
+    if (fast) { izs2 = nx; ize2 = izs2 + cap; inb = ize2 + cap; nx = inb + cap; }
+    gate = reinterpret_cast<GateRec *>(nx);
     ng = reinterpret_cast<uint32_t *>(gate + cap);
     row = ng + cap;
     meta = row + cap;
     list = meta + cap;
-    list0 = reinterpret_cast<uint16_t *>(list + (size_t)kWarps * 2 * (cap + kListExtra));
+    list0 = reinterpret_cast<uint16_t *>(list + (size_t)kWarps * (fast ? 1 : 2) * (cap + kListExtra));
   }
 };
 
@@ -132,6 +138,7 @@ LM_D bool sensitivity_exceeds(const TriParams &p, const ViewD &v, vec3<double> X
 // One match row -> candidate. Steps follow triangulateOneNode "Step 3" (base_line_triangulator.cc:290-326).
 // Unit-vector normalisations that do not change a decision or an output beyond rounding are dropped; the
 // angle / sensitivity gates use margin forms with the reference's acos form as the tie fallback.
+template <bool ALLOW_ENDP>
 LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const Src &src, uint32_t ngv, uint32_t ngl, Cand &c,
                         double4 &l2out) {
   const double4 l2 = ld_seg(&p.segs[p.line_off[ngv] + ngl]);
@@ -201,7 +208,7 @@ LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const Src &src, uin
   }
   vec3<double> Xs, Xe;
   const double EPS = consts<double>::eps();
-  if (!p.use_endpoints_triangulation) {
+  if (!ALLOW_ENDP || !p.use_endpoints_triangulation) {
     // line_triangulation (functions.cc:194-233): plane-pair intersection. Only lambda_0 is used, which
     // does not depend on the norms of the second and third column.
     const vec3<double> B = C2 - src.C1;
@@ -329,6 +336,37 @@ LM_D double pair_score(const TriParams &p, const seg<vec3<double>> &Li, vec3<dou
 // sqrt of the max of their squares), directions are never normalised (|cos| = |a.b|/sqrt(|a|^2|b|^2)) and
 // homogeneous divisions use one reciprocal. NaN angles are ignored exactly like std::min ignores a NaN
 // sub-score (line_dists.h:62-66). Polynomial early-outs skip the transcendental part for clear failures.
+// asin(sqrt(t))^2 / t for 0 <= t <= 1/16 (angles up to 14.4 deg): asin^2(x) = sum_n 2^(2n-1) x^(2n) / (n^2 C(2n,n));
+// 14 terms leave a relative remainder below 3e-19.
+LM_D double asin2_over_t(double t) {
+  double r = 0.017069849551821746;
+  r = fma(r, t, 0.019089950090498877);
+  r = fma(r, t, 0.02154247840073658);
+  r = fma(r, t, 0.02456910759753428);
+  r = fma(r, t, 0.028377319275152094);
+  r = fma(r, t, 0.03328204112517838);
+  r = fma(r, t, 0.03978243978243978);
+  r = fma(r, t, 0.04871319157033443);
+  r = fma(r, t, 0.06156806156806157);
+  r = fma(r, t, 0.08126984126984127);
+  r = fma(r, t, 0.11428571428571428);
+  r = fma(r, t, 0.17777777777777778);
+  r = fma(r, t, 0.3333333333333333);
+  r = fma(r, t, 1.0);
+  return r;
+}
+// squared angle in degrees between two directions from sin^2 = t (t <= 1/16) or from |cos| otherwise
+LM_D double angle2_deg(double t, double abs_cos) {
+  const double k = consts<double>::rad2deg();
+  if (t <= 0.0625) return t * asin2_over_t(t) * (k * k);
+  const double a = acos(abs_cos) * k;
+  return a * a;
+}
+
+// Reduced-form pair score: same value as pair_score() up to rounding. min over sub-scores of exp(-(v/sigma)^2/2)
+// == exp(-max (v/sigma)^2 / 2), so the squared normalised deviations are maximised and one exponential is taken;
+// angles come from sin^2 (cross products) through the asin^2 series, distances stay squared, and the divisors
+// that depend on one candidate only (depths of l_i, |q_j|^2) are reciprocals prepared in phase A.
 LM_D double pair_score_fast(const TriParams &p, const Slab &sl, int i, int j, uint32_t vj) {
   const double EPS = consts<double>::eps();
   const LinkerDev<double> &c3 = p.l3d;
@@ -337,13 +375,16 @@ LM_D double pair_score_fast(const TriParams &p, const Slab &sl, int i, int j, ui
   double Q = 0.0; // running maximum of the squared normalised deviations
   // ---- 3d: angle (line_linker.cc:185-192) + scale-invariant endpoint distance (:269-277)
   {
-    const double cs = fabs(sl.dx[i] * sl.dx[j] + sl.dy[i] * sl.dy[j] + sl.dz[i] * sl.dz[j]);
-    const double angle = acos(cs) * consts<double>::rad2deg();
-    const double qa = angle * p.inv_sig_a3;
-    if (angle == angle) Q = qa * qa;
+    const vec3<double> di = mk3(sl.dx[i], sl.dy[i], sl.dz[i]), dj = mk3(sl.dx[j], sl.dy[j], sl.dz[j]);
+    // products rounded separately: cross(di, dj) == -cross(dj, di) bit for bit, so two candidates that support
+    // only each other through the angle term tie exactly, as they do with the reference's symmetric acos(|di.dj|)
+    const vec3<double> cr = mk3(__dmul_rn(di.y, dj.z) - __dmul_rn(di.z, dj.y), __dmul_rn(di.z, dj.x) - __dmul_rn(di.x, dj.z),
+                                __dmul_rn(di.x, dj.y) - __dmul_rn(di.y, dj.x));
+    double a2 = angle2_deg(dot(cr, cr), fabs(dot(di, dj)));
+    if (!(dot(di, di) * dot(dj, dj) > 0.5)) a2 = 8100.0; // zero-length candidate: acos(0) = 90 deg
+    if (a2 == a2) Q = a2 * (p.inv_sig_a3 * p.inv_sig_a3);
     const vec3<double> ds = si - mk3(sl.sx[j], sl.sy[j], sl.sz[j]), de = ei - mk3(sl.ex[j], sl.ey[j], sl.ez[j]);
-    const double zs = sl.zs[i] + EPS, ze = sl.ze[i] + EPS;
-    const double r2 = fmax(dot(ds, ds) / (zs * zs), dot(de, de) / (ze * ze));
+    const double r2 = fmax(dot(ds, ds) * sl.izs2[i], dot(de, de) * sl.ize2[i]);
     Q = fmax(Q, r2 * p.inv_sig_s3 * p.inv_sig_s3);
     if (Q > p.q_cut3) return 0.0; // some 3d sub-score is clearly below score_th
   }
@@ -356,18 +397,22 @@ LM_D double pair_score_fast(const TriParams &p, const Slab &sl, int i, int j, ui
   const vec2<double> va = ae - as, vb = be - bs;
   const double na2 = dot(va, va), nb2 = dot(vb, vb);
   const double dab = dot(va, vb);
+  const double ina = 1.0 / na2, inb = sl.inb[j];
   double Q2 = 0.0;
-  double angle2 = 0.0;
+  double ang2 = 0.0; // squared 2d angle in degrees
   if (c2.use_angle) {
     if (dab * dab < p.cos2_th2d * na2 * nb2 * (1.0 - 1e-9)) return 0.0; // |cos| clearly below cos(th_angle)
-    const double cos2 = (na2 > 0.0 && nb2 > 0.0) ? fabs(dab) / sqrt(na2 * nb2) : 0.0;
-    angle2 = acos(cos2) * consts<double>::rad2deg();
-    const double qa = angle2 * p.inv_sig_a2;
-    if (angle2 == angle2) Q2 = qa * qa;
+    if (na2 > 0.0 && nb2 > 0.0) {
+      const double cr = va.x * vb.y - va.y * vb.x;
+      const double t = cr * cr * (ina * inb);
+      ang2 = angle2_deg(t, (t <= 0.0625) ? 0.0 : fabs(dab) / sqrt(na2 * nb2));
+    } else {
+      ang2 = 8100.0; // acos(0) = 90 deg
+    }
+    if (ang2 == ang2) Q2 = ang2 * (p.inv_sig_a2 * p.inv_sig_a2);
   }
   double bio = 0.0;
   if (c2.use_overlap) { // compute_bioverlap (line_dists.h:190-208)
-    const double inb = 1.0 / nb2, ina = 1.0 / na2;
     double p1 = dot(as - bs, vb) * inb, p2 = dot(ae - bs, vb) * inb;
     if (p1 > p2) { const double t = p1; p1 = p2; p2 = t; }
     const double o1 = smin(p2, 1.0) - smax(p1, 0.0);
@@ -377,27 +422,25 @@ LM_D double pair_score_fast(const TriParams &p, const Slab &sl, int i, int j, ui
     bio = smax(o1, o2);
     if (!(bio > c2.th_overlap)) return 0.0;
   }
-  if (c2.use_angle && c2.use_overlap && c2.use_smartangle) { // line_linker.cc:49-65
-    double th_angle = c2.th_angle;
-    if (bio < c2.th_smartoverlap) {
-      double ratio = (c2.th_smartoverlap - bio) / (c2.th_smartoverlap - c2.th_overlap);
-      ratio = smin(ratio, 1.0);
-      th_angle = c2.th_angle - ratio * (c2.th_angle - c2.th_smartangle);
-    }
-    const double qa = angle2 / (th_angle * c2.mult);
-    if (angle2 == angle2) Q2 = fmax(Q2, qa * qa);
+  if (c2.use_angle && c2.use_overlap && c2.use_smartangle && bio < c2.th_smartoverlap) { // line_linker.cc:49-65
+    double ratio = (c2.th_smartoverlap - bio) * p.inv_smart_den2;
+    ratio = smin(ratio, 1.0);
+    const double sig = (c2.th_angle - ratio * (c2.th_angle - c2.th_smartangle)) * c2.mult;
+    if (ang2 == ang2) Q2 = fmax(Q2, ang2 / (sig * sig));
   }
   if (c2.use_perp) { // max of the four endpoint-to-infinite-line distances, squared (line_dists.h:105-133)
     const vec2<double> d0 = as - bs, d1 = ae - bs, d2 = bs - as, d3 = be - as;
     const double t0 = dot(d0, vb), t1 = dot(d1, vb), t2 = dot(d2, va), t3 = dot(d3, va);
-    const double inb = 1.0 / nb2, ina = 1.0 / na2;
     double m = fmax(dot(d0, d0) - t0 * t0 * inb, 0.0);
     m = fmax(m, dot(d1, d1) - t1 * t1 * inb);
     m = fmax(m, dot(d2, d2) - t2 * t2 * ina);
     m = fmax(m, dot(d3, d3) - t3 * t3 * ina);
     Q2 = fmax(Q2, m * p.inv_sig_p2 * p.inv_sig_p2);
   }
-  // thresholds of the two linkers are applied separately (each has its own score_th)
+  // each linker applies its own score_th: exp(-Q/2) >= th <=> Q <= -2 ln th. Clear of both cuts by 1e-9 relative,
+  // one exponential of the larger deviation is the score; next to a cut the two exponentials decide.
+  if (Q2 > p.q_cut2) return 0.0;
+  if (Q < p.q_cut3_lo && Q2 < p.q_cut2_lo) return exp(-fmax(Q, Q2) * 0.5);
   const double e3 = exp(-Q * 0.5), e2 = exp(-Q2 * 0.5);
   if (e3 < c3.score_th || e2 < c2.score_th) return 0.0;
   return smin(e3, e2);
@@ -461,7 +504,10 @@ LM_D bool gate2d(const TriParams &p, const seg<vec3<double>> &Li, const Slab &sl
   return true;
 }
 
-template <bool SLAB, bool VP>
+// FAST: reduced-form scorer and plane-pair triangulation only (the default configuration); the generic
+// instantiation keeps the reference-structured scorer, the 2d margin gates and endpoint triangulation. Splitting
+// them keeps the hot kernel's code (and instruction-cache footprint) small.
+template <bool SLAB, bool VP, bool FAST>
 __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(const __grid_constant__ TriParams p) {
   constexpr int NS = VP ? 3 : 1; // proposal slots per match row: [vp1, vp2, algebraic] (base_line_triangulator.cc:258-326)
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -471,9 +517,10 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   Slab sl;
-  if (SLAB) sl.carve(p.slab + (int64_t)blockIdx.x * p.slab_stride, p.cap);
-  else sl.carve(reinterpret_cast<char *>(smem_raw), p.cap);
-  uint32_t *list1 = sl.list + (size_t)(warp * 2) * (p.cap + kListExtra), *list2 = list1 + p.cap + kListExtra;
+  if (SLAB) sl.carve(p.slab + (int64_t)blockIdx.x * p.slab_stride, p.cap, FAST);
+  else sl.carve(reinterpret_cast<char *>(smem_raw), p.cap, FAST);
+  uint32_t *list1 = sl.list + (size_t)(warp * (FAST ? 1 : 2)) * (p.cap + kListExtra);
+  uint32_t *list2 = FAST ? list1 : list1 + p.cap + kListExtra;
   uint16_t *list0 = sl.list0 + (size_t)warp * p.cap;
   unsigned long long n1_total = 0, n2_total = 0;
 
@@ -535,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
           }
           l2 = l2v;
         }
-        oks[NS - 1] = gen_candidate(p, v1, src, ngv, ngl, cs[NS - 1], l2);
+        oks[NS - 1] = gen_candidate<!FAST>(p, v1, src, ngv, ngl, cs[NS - 1], l2);
       }
       int cnt = 0;
 #pragma unroll
@@ -571,6 +618,11 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         sl.dx[idx] = d.x; sl.dy[idx] = d.y; sl.dz[idx] = d.z;
         sl.zs[idx] = c.zs; sl.ze[idx] = c.ze; sl.unc[idx] = c.unc;
         sl.q0[idx] = l2.x; sl.q1[idx] = l2.y; sl.q2[idx] = l2.z; sl.q3[idx] = l2.w;
+        if (FAST) {
+          const double zs1 = c.zs + consts<double>::eps(), ze1 = c.ze + consts<double>::eps();
+          const double qx = l2.z - l2.x, qy = l2.w - l2.y;
+          sl.izs2[idx] = 1.0 / (zs1 * zs1); sl.ize2[idx] = 1.0 / (ze1 * ze1); sl.inb[idx] = 1.0 / (qx * qx + qy * qy);
+        }
         sl.ng[idx] = ng;
         sl.row[idx] = (uint32_t)r * NS + k;
         // fp32 gate copy, relative to the source camera centre (keeps |coord| ~ depth)
@@ -661,7 +713,7 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
       // B2 (only with the reference-structured scorer): fp64 margin gates of the 2d tests
       int n2 = n1;
       uint32_t *listS = list1;
-      if (!p.fast_forms) {
+      if (!FAST) {
         n2 = 0;
         for (int kb = 0; kb < n1; kb += 32) {
           const int k = kb + lane;
@@ -697,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
           const uint32_t vj = sl.ng[j] >> 16;
           row = (uint32_t)i;
           key = (row << 16) | vj;
-          if (p.fast_forms) sc = pair_score_fast(p, sl, i, j, vj);
+          if (FAST) sc = pair_score_fast(p, sl, i, j, vj);
           else {
             seg<vec3<double>> Li;
             Li.s = mk3(sl.sx[i], sl.sy[i], sl.sz[i]);
@@ -811,22 +863,23 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
   }
 }
 
-template <bool VP> static void launch_tri_vp(const TriParams &p, int grid, size_t smem, cudaStream_t s) {
+template <bool VP, bool FAST> static void launch_tri_vf(const TriParams &p, int grid, size_t smem, cudaStream_t s) {
   static size_t configured = 0;
   if (p.use_slab) {
-    tri_node_kernel<true, VP><<<grid, kThreads, 0, s>>>(p);
+    tri_node_kernel<true, VP, FAST><<<grid, kThreads, 0, s>>>(p);
     return;
   }
   if (smem > configured) {
-    cudaFuncSetAttribute(tri_node_kernel<false, VP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(tri_node_kernel<false, VP, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  tri_node_kernel<false, VP><<<grid, kThreads, smem, s>>>(p);
+  tri_node_kernel<false, VP, FAST><<<grid, kThreads, smem, s>>>(p);
 }
 void launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem, cudaStream_t s) {
   (void)block;
-  if (p.use_vp) launch_tri_vp<true>(p, grid, smem, s);
-  else launch_tri_vp<false>(p, grid, smem, s);
+  const bool fast = p.fast_forms && !p.use_endpoints_triangulation;
+  if (p.use_vp) { if (fast) launch_tri_vf<true, true>(p, grid, smem, s); else launch_tri_vf<true, false>(p, grid, smem, s); }
+  else { if (fast) launch_tri_vf<false, true>(p, grid, smem, s); else launch_tri_vf<false, false>(p, grid, smem, s); }
 }
 
 // The per-run block tables (match tables ordered by (source view, neighbour), row offsets) are derived on the

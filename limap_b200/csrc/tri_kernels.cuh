@@ -65,6 +65,8 @@ struct TriParams {
   // largest q = (v/sigma)^2 that can still reach score_th (with a 1e-9 margin)
   int fast_forms;
   double inv_sig_a3, inv_sig_s3, inv_sig_a2, inv_sig_p2, q_cut3;
+  double q_cut3_lo, q_cut2, q_cut2_lo; // -2 ln(score_th) * (1 -/+ 1e-9) of the two linkers
+  double inv_smart_den2;               // 1 / (l2d.th_smartoverlap - l2d.th_overlap)
   float bucket_scale;     // n_buckets / pi
 };
 
@@ -76,7 +78,7 @@ struct EdgeParams {
   LinkerDev<double> l3d; // linker3d_config after set_to_spatial_merging()
 };
 
-size_t tri_smem_bytes(int cap);
+size_t tri_smem_bytes(int cap, bool fast);
 void launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem, cudaStream_t s);
 void launch_expand_rows(const int32_t *d_pairs, const int64_t *d_blk_row_off, const int32_t *d_blk_src_view,
                         const int32_t *d_blk_ng_view, const int64_t *d_blk_pair_off, int n_blocks,
