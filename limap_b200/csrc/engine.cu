@@ -812,14 +812,6 @@ int lm_tri_run(lm_ctx *c) {
     p.sens_poly_ok = (tsn > 0.0 && tsn < 90.0);
     p.sin2_tri = std::sin(ta * kPi / 180.0) * std::sin(ta * kPi / 180.0);
     p.sin2_sens = std::sin(tsn * kPi / 180.0) * std::sin(tsn * kPi / 180.0);
-    // direction buckets of width >= th_angle * 1.001 + 0.02 deg (candidates of a node are coplanar when they
-    // come from the plane-pair intersection; endpoint triangulation does not guarantee that)
-    p.n_buckets = 1;
-    if (!g.use_endpoints_triangulation && t3 > 0.0 && t3 < 60.0) {
-      const int nb = (int)std::floor(180.0 / (t3 * 1.001 + 0.02));
-      p.n_buckets = std::max(1, std::min(32, nb));
-    }
-    p.bucket_scale = (float)(p.n_buckets / kPi);
     p.fast_forms = (p.l2d.use_innerseg || getenv("LIMAP_B200_REFERENCE_FORMS")) ? 0 : 1;
     p.inv_sig_a3 = 1.0 / (p.l3d.th_angle * p.l3d.mult);
     p.inv_sig_s3 = 1.0 / (p.l3d.th_scaleinv * p.l3d.mult);

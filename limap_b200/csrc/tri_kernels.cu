@@ -23,11 +23,14 @@ static constexpr int kThreads = 128;
 static constexpr int kWarps = kThreads / 32;
 // per-candidate staging: 17 doubles (exact fp64 data + score), 11 floats (fp32 gate copies), ng + row
 // (2 x uint32); plus two survivor lists per warp
-static constexpr int kFlush = 64;      // a warp flushes its survivor list once it holds this many pairs
+#ifndef LM_KFLUSH
+#define LM_KFLUSH 64
+#endif
+static constexpr int kFlush = LM_KFLUSH;     // a warp flushes its survivor list once it holds this many pairs
 static constexpr int kListExtra = kFlush + 32;
-// per-candidate staging: 17 doubles (exact fp64 data + score), one 48-byte fp32 gate record, ng + row +
-// meta (3 x uint32); plus per warp two survivor lists (uint32) and one prefilter list (uint16)
-static constexpr int kCandBytes = 17 * 8 + 48 + 12;
+// per-candidate staging: 17 doubles (exact fp64 data + score), one 48-byte fp32 gate record, ng + row
+// (2 x uint32); plus per warp two survivor lists (uint32) and one prefilter list (uint16)
+static constexpr int kCandBytes = 17 * 8 + 48 + 8;
 
 // fast layout: one survivor list per warp (no 2d-gate stage) and three more doubles per candidate (reciprocals)
 size_t tri_smem_bytes(int cap, bool fast) {
@@ -48,7 +51,7 @@ struct Slab {
   double *sx, *sy, *sz, *ex, *ey, *ez, *dx, *dy, *dz, *zs, *ze, *unc, *q0, *q1, *q2, *q3, *score;
   double *izs2, *ize2, *inb; // fast layout only: 1/(zs+EPS)^2, 1/(ze+EPS)^2, 1/|q|^2
   GateRec *gate;
-  uint32_t *ng, *row, *meta; // meta = view << 16 | direction bucket
+  uint32_t *ng, *row;
   uint32_t *list;            // [kWarps][2][cap + kListExtra]: (row << 16 | j) survivor entries
   uint16_t *list0;           // [kWarps][cap]: j of the bucket prefilter
   LM_D void carve(char *base, int cap, bool fast) {
@@ -62,8 +65,7 @@ struct Slab {
     gate = reinterpret_cast<GateRec *>(nx);
     ng = reinterpret_cast<uint32_t *>(gate + cap);
     row = ng + cap;
-    meta = row + cap;
-    list = meta + cap;
+    list = row + cap;
     list0 = reinterpret_cast<uint16_t *>(list + (size_t)kWarps * (fast ? 1 : 2) * (cap + kListExtra));
   }
 };
@@ -107,7 +109,6 @@ struct Src {
   vec3<double> w1s, w1e;     // M1 [p;1] (unnormalised world rays)
   vec3<double> ray1s, ray1e; // normalised
   vec3<double> C1;
-  vec3<double> pu, pv;       // orthonormal basis of the back-projection plane of l1
   vec3<double> n1;           // getNormalDirection(l1, view1) (only for VP proposals)
   bool ok;
 };
@@ -466,6 +467,15 @@ LM_D bool gate3d(const GateRec &r, const GateRec *g, float cos_th) {
   return !(bx * bx + by * by + bz * bz > r.lime2);
 }
 
+// gate3d without the start-point test (done by the prefilter)
+LM_D bool gate3d_rest(const GateRec &r, const GateRec *g, float cos_th) {
+  const float4 a = *reinterpret_cast<const float4 *>(&g->dx);
+  if (fabsf(r.dx * a.x + r.dy * a.y + r.dz * a.z) < cos_th) return false;
+  const float4 c = *reinterpret_cast<const float4 *>(&g->ex);
+  const float bx = r.ex - c.x, by = r.ey - c.y, bz = r.ez - c.z;
+  return !(bx * bx + by * by + bz * bz > r.lime2);
+}
+
 // 2d gate, fp64 without transcendentals: angle, overlap and perpendicular tests of
 // LineLinker2d::compute_score (line_linker.cc:139-160) in margin form.
 LM_D bool gate2d(const TriParams &p, const seg<vec3<double>> &Li, const Slab &sl, int j, uint32_t vj) {
@@ -546,8 +556,6 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
       src.ray1s = normalized(src.w1s);
       src.ray1e = normalized(src.w1e);
       src.C1 = mk3(v1.C[0], v1.C[1], v1.C[2]);
-      src.pu = src.ray1s;
-      src.pv = normalized(src.ray1e - src.ray1s * dot(src.ray1e, src.ray1s));
       src.n1 = normalized(cross(src.w1s, src.w1e));
     }
     int count = 0;
@@ -636,23 +644,8 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         g.dx = (float)d.x; g.dy = (float)d.y; g.dz = (float)d.z; g.lims2 = (float)(ls * ls * 1.000001);
         g.sx = (float)rs.x; g.sy = (float)rs.y; g.sz = (float)rs.z; g.lime2 = (float)(le * le * 1.000001);
         g.ex = (float)re.x; g.ey = (float)re.y; g.ez = (float)re.z;
-        // direction bucket: every candidate of the node lies in the back-projection plane of l1, so its
-        // direction is an angle phi in [0, pi) within that plane; the 3d angle test can only pass for
-        // candidates whose buckets (width >= th_angle + margin) are equal or adjacent
-        uint32_t bucket = 0, accept = 0xffffffffu;
-        if (p.n_buckets > 1) {
-          float phi = atan2f((float)dot(d, src.pv), (float)dot(d, src.pu));
-          if (phi < 0.f) phi += 3.14159265358979f;
-          const int bb = (int)(phi * p.bucket_scale);
-          bucket = (uint32_t)min(max(bb, 0), p.n_buckets - 1);
-          if (p.n_buckets > 3) {
-            const int b = (int)bucket, nb = p.n_buckets;
-            accept = (1u << b) | (1u << (b + 1 == nb ? 0 : b + 1)) | (1u << (b == 0 ? nb - 1 : b - 1));
-          }
-        }
-        g.pad = __uint_as_float(accept);
+        g.pad = 0.f;
         sl.gate[idx] = g;
-        sl.meta[idx] = (ng & 0xffff0000u) | bucket;
         ++idx;
       }
       count += tot;
@@ -676,30 +669,33 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= C) { more = false; break; }
         const GateRec rf = sl.gate[i];
-        const uint32_t vi = sl.meta[i] >> 16;
-        const uint32_t accept = __float_as_uint(rf.pad);
-        // B0: bucket / view prefilter on one packed word per candidate
+        const uint32_t vi = sl.ng[i] >> 16;
+        // B0: start-point prefilter. The scale-invariant endpoint test (line_linker.cc:269-277, th_scaleinv of the
+        // depth) is by far the most selective 3d test, so its start-point half runs first on every candidate (one
+        // 16-byte load, 8 flops); the other gates only see the survivors. (A byte-hash of the log distance tested
+        // four candidates per lane was measured slower: more false positives reach B1 than it saves here.)
         int n0 = 0;
         for (int jb = 0; jb < C; jb += 32) {
           const int j = jb + lane;
           bool pass = false;
           if (j < C) {
-            const uint32_t mj = sl.meta[j];
-            pass = ((accept >> (mj & 31u)) & 1u) && (mj >> 16) != vi && j != i;
+            const float4 b = *reinterpret_cast<const float4 *>(&sl.gate[j].sx);
+            const float ax = rf.sx - b.x, ay = rf.sy - b.y, az = rf.sz - b.z;
+            pass = !(ax * ax + ay * ay + az * az > rf.lims2) && j != i;
           }
           const unsigned bal = __ballot_sync(0xffffffffu, pass);
           if (pass) list0[n0 + __popc(bal & lt_mask)] = (uint16_t)j;
           n0 += __popc(bal);
         }
         __syncwarp();
-        // B1: fp32 3d gates on the dense prefilter list
+        // B1: the other fp32 3d gates (angle, end point) and the same-image exclusion on the prefilter list
         for (int kb = 0; kb < n0; kb += 32) {
           const int k = kb + lane;
           bool pass = false;
           int j = 0;
           if (k < n0) {
             j = list0[k];
-            pass = gate3d(rf, &sl.gate[j], p.cos_th3d_f);
+            pass = (sl.ng[j] >> 16) != vi && gate3d_rest(rf, &sl.gate[j], p.cos_th3d_f);
           }
           const unsigned bal = __ballot_sync(0xffffffffu, pass);
           if (pass) list1[n1 + __popc(bal & lt_mask)] = ((uint32_t)i << 16) | (uint32_t)j;

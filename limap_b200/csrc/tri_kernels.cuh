@@ -60,14 +60,12 @@ struct TriParams {
   double sin2_tri;        // sin^2(line_tri_angle_threshold); valid when tri_poly_ok
   double sin2_sens;       // sin^2(sensitivity_threshold); valid when sens_poly_ok
   int tri_poly_ok, sens_poly_ok; // thresholds inside (0, 90): the polynomial forms are equivalent
-  int n_buckets;          // direction buckets over [0, pi) (1 = prefilter off)
   // reduced-form scorer constants: 1/sigma of the angle / scale-invariance / perpendicular tests and the
   // largest q = (v/sigma)^2 that can still reach score_th (with a 1e-9 margin)
   int fast_forms;
   double inv_sig_a3, inv_sig_s3, inv_sig_a2, inv_sig_p2, q_cut3;
   double q_cut3_lo, q_cut2, q_cut2_lo; // -2 ln(score_th) * (1 -/+ 1e-9) of the two linkers
   double inv_smart_den2;               // 1 / (l2d.th_smartoverlap - l2d.th_overlap)
-  float bucket_scale;     // n_buckets / pi
 };
 
 struct EdgeParams {
