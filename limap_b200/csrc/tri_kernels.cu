@@ -659,6 +659,14 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
     // survivors of several rows to a warp-private list until it holds >= kFlush entries, so that the fp64
     // stages B2 (2d margin gates) and B3 (exact reference score) run on dense 32-lane batches.
     for (int i = tid; i < C; i += kThreads) sl.score[i] = 0.0;
+    // records up to the next multiple of 32 can never pass the start-point test: the prefilter loop needs no bounds
+    if (tid < 32 && C + tid < ((C + 31) & ~31)) {
+      GateRec z;
+      z.dx = z.dy = z.dz = 0.f; z.lims2 = 0.f;
+      z.sx = z.sy = z.sz = 3e18f; z.lime2 = 0.f;
+      z.ex = z.ey = z.ez = 3e18f; z.pad = 0.f;
+      sl.gate[C + tid] = z;
+    }
     __syncthreads();
     bool more = true;
     while (more) {
@@ -677,18 +685,15 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         int n0 = 0;
         for (int jb = 0; jb < C; jb += 32) {
           const int j = jb + lane;
-          bool pass = false;
-          if (j < C) {
-            const float4 b = *reinterpret_cast<const float4 *>(&sl.gate[j].sx);
-            const float ax = rf.sx - b.x, ay = rf.sy - b.y, az = rf.sz - b.z;
-            pass = !(ax * ax + ay * ay + az * az > rf.lims2) && j != i;
-          }
+          const float4 b = *reinterpret_cast<const float4 *>(&sl.gate[j].sx);
+          const float ax = rf.sx - b.x, ay = rf.sy - b.y, az = rf.sz - b.z;
+          const bool pass = !(ax * ax + ay * ay + az * az > rf.lims2);
           const unsigned bal = __ballot_sync(0xffffffffu, pass);
           if (pass) list0[n0 + __popc(bal & lt_mask)] = (uint16_t)j;
           n0 += __popc(bal);
         }
         __syncwarp();
-        // B1: the other fp32 3d gates (angle, end point) and the same-image exclusion on the prefilter list
+        // B1: the other fp32 3d gates (angle, end point) and the same-image exclusion (which also drops j == i)
         for (int kb = 0; kb < n0; kb += 32) {
           const int k = kb + lane;
           bool pass = false;
