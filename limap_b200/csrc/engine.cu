@@ -1,5 +1,5 @@
-// engine.cu — host side of the C ABI declared in include/limap_b200.h: context, scene upload,
-// batched TriangulateImage, result getters and ComputeLineTracks.
+// engine.cu — host side of the C ABI declared in include/limap_b200.h: context, scene upload, batched
+// TriangulateImage, result getters, ComputeLineTracks, line BA, VP detection, track filters and remerge.
 //
 // Mirrors (file:line under /root/reference/src/limap/):
 //   BaseLineTriangulator::{Init,TriangulateImage,TriangulateImageExhaustiveMatch}

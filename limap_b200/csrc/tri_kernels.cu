@@ -9,8 +9,9 @@
 //   collect_edges / edge_weights : run_clustering's edge list and 3d scores
 //       (global_line_triangulator.cc:234-291).
 //
-// Arithmetic is fp64 in this first (exact) path: every gate is a hard threshold on a transcendental
-// and the contract is bit-exact candidate indices (see DESIGN.md "precision").
+// Outputs and final decisions are fp64 (every gate of the reference is a hard threshold on a transcendental and
+// the contract is bit-exact candidate indices); fp32 appears only in pruning gates with explicit margins
+// (see DESIGN.md "Precision").
 #include "tri_kernels.cuh"
 #include <cstdio>
 
@@ -53,7 +54,7 @@ struct Slab {
   GateRec *gate;
   uint32_t *ng, *row;
   uint32_t *list;            // [kWarps][2][cap + kListExtra]: (row << 16 | j) survivor entries
-  uint16_t *list0;           // [kWarps][cap]: j of the bucket prefilter
+  uint16_t *list0;           // [kWarps][cap]: j of the start-point prefilter
   LM_D void carve(char *base, int cap, bool fast) {
     double *d = reinterpret_cast<double *>(base);
     sx = d; sy = sx + cap; sz = sy + cap; ex = sz + cap; ey = ex + cap; ez = ey + cap;
