@@ -156,6 +156,8 @@ struct lm_ctx {
   bool any_exhaustive = false, any_matches = false;
   int shard_begin = 0, shard_end = -1;
   int pipeline_groups = 1; // lm_tri_set_pipeline_groups
+  // pinned landing pad of the small device->host reads inside a run (no staging through pageable memory)
+  unsigned int *h_pin = nullptr;
   // run buffers
   DevBuf d_blk_row_off, d_blk_src, d_blk_ng, d_blk_pair_off;
   DevBuf d_key, d_key2, d_val, d_val2, d_sort_tmp;
@@ -274,6 +276,7 @@ int lm_ctx_create(int device, lm_ctx **out) {
   CU(cudaEventCreate(&c->evk0));
   CU(cudaEventCreate(&c->evk1));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_pin), 256, cudaHostAllocDefault));
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   memset(&c->stats, 0, sizeof(c->stats));
@@ -291,7 +294,7 @@ void lm_ctx_destroy(lm_ctx *c) {
                     &c->d_blk_src, &c->d_blk_ng, &c->d_blk_pair_off, &c->d_key, &c->d_key2, &c->d_val, &c->d_val2,
                     &c->d_sort_tmp, &c->d_node_row_off, &c->d_scalars, &c->d_nodes, &c->d_row_state, &c->d_row_cand,
                     &c->d_slab, &c->d_edges, &c->d_edges2, &c->d_edge_keys, &c->d_edge_keys2, &c->d_edge_w,
-                    &c->d_edge_cnt, &c->d_nvalid, &c->d_edge_off, &c->d_edge_ng, &c->d_ba_in, &c->d_ba_blocks, &c->d_ba_out, &c->d_raw_blocks, &c->d_bkey, &c->d_bkey2, &c->d_bval, &c->d_bval2, &c->d_blk_rows, &c->d_vp_label, &c->d_vp_voff, &c->d_vp_vps, &c->d_vp_pts, &c->d_vp_off, &c->d_vp_labels, &c->d_vp_nc, &c->d_vp_ps, &c->d_vp_mat};
+                    &c->d_edge_cnt, &c->d_nvalid, &c->d_edge_off, &c->d_edge_ng, &c->d_ba_in, &c->d_ba_blocks, &c->d_ba_out, &c->d_raw_blocks, &c->d_bkey, &c->d_bkey2, &c->d_bval, &c->d_bval2, &c->d_blk_rows, &c->d_vp_label, &c->d_vp_voff, &c->d_vp_vps, &c->d_vp_pts, &c->d_vp_off, &c->d_vp_labels, &c->d_vp_nc, &c->d_vp_ps, &c->d_vp_mat, &c->d_mg_in, &c->d_mg_out, &c->d_mg_edges};
   for (DevBuf *b : bufs) b->release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -301,6 +304,7 @@ void lm_ctx_destroy(lm_ctx *c) {
   for (auto &ch : c->chunks) cudaEventDestroy(ch.ev);
   for (auto e : c->event_pool) cudaEventDestroy(e);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -885,7 +889,8 @@ int lm_tri_run(lm_ctx *c) {
                             d_max_rows, s);
     ++launches;
     // the shared-memory staging area is sized from the largest node of the group (one 8-byte read-back)
-    unsigned int hs[2] = {0, 0};
+    unsigned int *hs = c->h_pin;
+    hs[0] = hs[1] = 0;
     CU(cudaMemcpyAsync(hs, c->d_scalars.p, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     if (hs[1] == 1)
@@ -959,8 +964,9 @@ int lm_tri_run(lm_ctx *c) {
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->stats.last_node_kernel_ms = c->node_kernel_ms_acc;
-  unsigned long long cnt[4];
-  CU(cudaMemcpy(cnt, d_counters, 32, cudaMemcpyDeviceToHost));
+  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(c->h_pin + 8);
+  CU(cudaMemcpyAsync(cnt, d_counters, 32, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
   c->stats.n_rows = n_rows;
   c->stats.n_candidates = (int64_t)cnt[0];
   c->stats.n_valid_edges = (int64_t)cnt[1];
