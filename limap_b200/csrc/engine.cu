@@ -15,6 +15,9 @@
 #include "vp_kernels.cuh"
 #include "merge_kernels.cuh"
 #include <algorithm>
+#ifdef LM_TRACE
+#include <chrono>
+#endif
 #include <array>
 #include <cmath>
 #include <cstdio>
@@ -742,7 +745,15 @@ int lm_tri_run(lm_ctx *c) {
   CU(c->d_row_state.ensure(std::max<int64_t>(n_rows * ns, 1)));
   if (c->cfg.debug_mode) CU(c->d_row_cand.ensure(80 * std::max<int64_t>(n_rows * ns, 1)));
 
+#ifdef LM_TRACE
+  const auto lm_t0 = std::chrono::steady_clock::now();
+  auto lm_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - lm_t0).count(); };
+#endif
   CU(cudaEventRecord(c->ev0, s));
+#ifdef LM_TRACE
+  cudaEventSynchronize(c->ev0);
+  fprintf(stderr, "[lm trace] ev0 executed %.3f ms after run entry\n", lm_ms());
+#endif
   lm::launch_zero_words(c->d_scalars.p, 16, s);
   // block tables, derived on the device from the descriptors uploaded with the matches (no transfer now)
   {
@@ -960,7 +971,13 @@ int lm_tri_run(lm_ctx *c) {
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev1, s));
   CU(cudaStreamSynchronize(s));
+#ifdef LM_TRACE
+  fprintf(stderr, "[lm trace] compute stream drained %.3f ms after run entry\n", lm_ms());
+#endif
   CU(cudaStreamSynchronize(c->copy_stream)); // uploads of images outside this shard may still be in flight
+#ifdef LM_TRACE
+  fprintf(stderr, "[lm trace] copy stream drained %.3f ms after run entry\n", lm_ms());
+#endif
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->stats.last_node_kernel_ms = c->node_kernel_ms_acc;
