@@ -106,3 +106,40 @@ def test_segments_metainfos_matches(tmp_path):
     assert os.path.basename(limapio.get_match_filename(d, 0)) == "matches_0.npy"
     back = limapio.read_match(d, 0)
     assert sorted(back) == [1, 5] and np.array_equal(back[1], m[1]) and back[5].shape == (0, 2)
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "io")
+
+
+def test_golden_files_written_by_the_reference(tmp_path):
+    """tests/golden/io/* were written by the reference's own util/io.py (tests/golden/make_io_golden.py): this
+    repository's writers reproduce them byte for byte from the same inputs, and its readers parse them."""
+    z = np.load(os.path.join(GOLDEN, "inputs.npz"), allow_pickle=True)
+    d = str(tmp_path)
+    for i in z["seg_ids"]:
+        i = int(i)
+        limapio.save_txt_segments(d, i, z[f"segs_{i}"])
+        assert open(os.path.join(d, f"segments_{i}.txt")).read() == open(os.path.join(GOLDEN, f"segments_{i}.txt")).read()
+        got = limapio.read_txt_segments(GOLDEN, i)
+        if len(z[f"segs_{i}"]):
+            assert np.array_equal(got, z[f"segs_{i}"])
+    nb, rg = limapio.read_txt_metainfos(os.path.join(GOLDEN, "metainfos.txt"))
+    assert nb == {3: [11, 12], 11: [3], 12: []}
+    assert np.array_equal(rg[0], z["range_lo"]) and np.array_equal(rg[1], z["range_hi"])
+    limapio.save_txt_metainfos(os.path.join(d, "metainfos.txt"), nb, rg)
+    assert open(os.path.join(d, "metainfos.txt")).read() == open(os.path.join(GOLDEN, "metainfos.txt")).read()
+    tracks = []
+    for L, img, lid in zip(z["track_lines"], z["track_img"], z["track_lid"]):
+        t = base.LineTrack()
+        t.line = base.Line3d(L[:3], L[3:])
+        t.image_id_list, t.line_id_list = list(img), list(lid)
+        t.line2d_list = [base.Line2d() for _ in img]
+        tracks.append(t)
+    for nv in (1, 3):
+        f = os.path.join(d, f"alltracks_nv{nv}.txt")
+        limapio.save_txt_linetracks(f, tracks, n_visible_views=nv)
+        assert open(f).read() == open(os.path.join(GOLDEN, f"alltracks_nv{nv}.txt")).read()
+    back = limapio.read_txt_linetracks(os.path.join(GOLDEN, "alltracks_nv1.txt"))
+    assert len(back) == 3 and back[2][1] == list(z["track_img"][2])
+    m = limapio.read_match(GOLDEN, 3)
+    assert sorted(m) == [11, 12] and m[11].shape == (7, 2) and m[12].shape == (0, 2)

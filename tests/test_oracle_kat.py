@@ -104,3 +104,24 @@ def test_oracle_recovers_ground_truth_tracks():
             close += dist < 0.05
     assert pure > 0.5 * T
     assert close > 0.9 * pure
+
+
+def test_pose_rotation_against_reference_python_golden(oracle_lib):
+    """tests/golden/io/quaternion_rotation.npz holds rotation matrices computed by the reference's own pure-Python
+    rotation_from_quaternion (util/geometry.py:40-58) on unnormalised quaternions (tests/golden/make_io_golden.py).
+    Pins CameraPose::R() of the Python value types and the pose math inside the oracle's projection."""
+    import os
+    from limap_b200 import base
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "io", "quaternion_rotation.npz"))
+    rng = np.random.default_rng(1)
+    K = np.array([[500.0, 0, 320.0], [0, 480.0, 240.0], [0, 0, 1.0]])
+    for q, R in zip(z["qvec"], z["R"]):
+        assert np.abs(base.CameraPose(q, np.zeros(3)).R() - R).max() <= 2e-15
+        T = rng.normal(size=3)
+        X = R.T @ (np.array([0.3, -0.2, 4.0]) - T)  # in front of the camera
+        h = K @ (R @ X + T)
+        exp = h[:2] / (h[2] + 1e-12)
+        cam = orc.cam_array(1, [500.0, 480.0, 320.0, 240.0], q, T)
+        p = np.zeros(2)
+        oracle_lib.orc_project_point(orc._p(cam), orc._p(X), orc._p(p))
+        assert np.abs(p - exp).max() <= 1e-9
