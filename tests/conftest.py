@@ -17,3 +17,13 @@ def oracle_lib():
     from oracle import oracle
     oracle.build()
     return oracle.lib()
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _engine_library():
+    """The C-ABI library is built in-tree (it travels with the repository snapshot); a checkout without it builds it
+    once per session. Nothing is skipped when the build fails: the product path has no fallback."""
+    from limap_b200 import _build
+    if not os.path.exists(_build.LIB):
+        _build.build_native()
+    yield
