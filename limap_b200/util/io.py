@@ -17,52 +17,55 @@ import numpy as np
 from .. import base
 
 
-def check_directory(fname):  # util/io.py:12-15
-    d = os.path.dirname(fname)
-    if d and not os.path.exists(d):
-        raise ValueError(f"Error! Base directory {d} does not exist!")
+def _require_parent(fname):
+    parent = os.path.dirname(fname)
+    if parent and not os.path.isdir(parent):
+        raise ValueError(f"Error! Base directory {parent} does not exist!")
 
 
-def check_path(fname):  # util/io.py:18-20
-    if not os.path.exists(fname):
-        raise ValueError(f"Error! File {fname} does not exist!")
+def _require(path):
+    if not os.path.exists(path):
+        raise ValueError(f"Error! File {path} does not exist!")
+
+
+check_directory, check_path = _require_parent, _require  # names of util/io.py:11-26
 
 
 def check_makedirs(folder):
-    if not os.path.exists(folder):
-        os.makedirs(folder)
+    os.makedirs(folder, exist_ok=True)
 
 
 def delete_folder(folder):
-    if os.path.exists(folder):
-        shutil.rmtree(folder)
+    shutil.rmtree(folder, ignore_errors=True)
 
 
-def save_npy(fname, nparray):  # util/io.py:39-42
-    check_directory(fname)
-    with open(fname, "wb") as f:
-        np.save(f, np.array(nparray, dtype=object))
+def save_npy(fname, nparray):
+    """Pickled object array, as util/io.py:39-42 writes it (np.save of np.array(obj, dtype=object))."""
+    _require_parent(fname)
+    payload = np.array(nparray, dtype=object)
+    with open(fname, "wb") as fh:
+        np.save(fh, payload)
 
 
-def read_npy(fname):  # util/io.py:45-49
-    check_path(fname)
-    with open(fname, "rb") as f:
-        return np.load(f, allow_pickle=True)
+def read_npy(fname):
+    _require(fname)
+    with open(fname, "rb") as fh:
+        return np.load(fh, allow_pickle=True)
 
 
 def save_npz(fname, dic):
-    check_directory(fname)
+    _require_parent(fname)
     np.savez(fname, **dic)
 
 
 def read_npz(fname):
-    check_path(fname)
+    _require(fname)
     return np.load(fname, allow_pickle=True)
 
 
-# ---- matches (line2d/base_matcher.py:80-117) ---------------------------------------------------------------
+# ---- matches: matches_{id}.npy = pickled {ng_img_id: (M, 2) int array} (line2d/base_matcher.py:80-117) ----------
 def get_match_filename(matches_folder, idx):
-    return os.path.join(matches_folder, f"matches_{idx}.npy")
+    return os.path.join(matches_folder, "matches_%s.npy" % idx)
 
 
 def save_match(matches_folder, idx, matches):
@@ -73,143 +76,139 @@ def read_match(matches_folder, idx):
     return read_npy(get_match_filename(matches_folder, idx)).item()
 
 
-# ---- neighbors + ranges (util/io.py:87-131) -----------------------------------------------------------------
+# ---- metainfos.txt: neighbors + ranges (util/io.py:87-131) -----------------------------------------------------
 def save_txt_metainfos(fname, neighbors, ranges):
-    check_directory(fname)
-    with open(fname, "w") as f:
-        f.write(f"number of images, {len(neighbors)}\n")
-        f.write(f"x-range, {ranges[0][0]}, {ranges[1][0]}\n")
-        f.write(f"y-range, {ranges[0][1]}, {ranges[1][1]}\n")
-        f.write(f"z-range, {ranges[0][2]}, {ranges[1][2]}\n")
-        for img_id, neighbor in neighbors.items():
-            str_ = f"image {img_id}"
-            for ng_idx in neighbor:
-                str_ += f", {ng_idx}"
-            f.write(str_ + "\n")
+    _require_parent(fname)
+    lo, hi = ranges
+    rows = [f"number of images, {len(neighbors)}"]
+    rows += [f"{axis}-range, {lo[k]}, {hi[k]}" for k, axis in enumerate("xyz")]
+    rows += [", ".join([f"image {img_id}"] + [str(n) for n in ngs]) for img_id, ngs in neighbors.items()]
+    with open(fname, "w") as fh:
+        fh.write("\n".join(rows) + "\n")
 
 
 def read_txt_metainfos(fname):
-    check_path(fname)
-    with open(fname) as f:
-        txt_lines = f.readlines()
-    n_images = int(txt_lines[0].strip().split(",")[1])
-    ranges = (np.zeros(3), np.zeros(3))
-    for axis in range(3):
-        k = txt_lines[1 + axis].strip().split(",")[1:]
-        ranges[0][axis], ranges[1][axis] = float(k[0]), float(k[1])
+    _require(fname)
+    with open(fname) as fh:
+        rows = [r.strip() for r in fh]
+    fields = lambda row: [x for x in row.split(",")[1:]]
+    n_images = int(fields(rows[0])[0])
+    lo, hi = np.zeros(3), np.zeros(3)
+    for k in range(3):
+        lo[k], hi[k] = (float(x) for x in fields(rows[1 + k])[:2])
     neighbors = {}
-    for row in txt_lines[4:4 + n_images]:
-        k = row.strip().split(",")
-        neighbors[int(k[0][6:])] = [int(kk) for kk in k[1:]]
-    return neighbors, ranges
+    for row in rows[4:4 + n_images]:
+        head = row.split(",")[0]
+        neighbors[int(head[len("image "):])] = [int(x) for x in fields(row)]
+    return neighbors, (lo, hi)
 
 
-# ---- 2D segments (util/io.py:436-474) ------------------------------------------------------------------------
+# ---- segments_{id}.txt: count, then "x1 y1 x2 y2" per row (util/io.py:436-474) -----------------------------------
+def _segments_file(folder, img_id):
+    return os.path.join(folder, "segments_%s.txt" % img_id)
+
+
 def exists_txt_segments(folder, img_id):
-    return os.path.exists(os.path.join(folder, f"segments_{img_id}.txt"))
+    return os.path.exists(_segments_file(folder, img_id))
 
 
 def save_txt_segments(folder, img_id, segs):
-    fname = os.path.join(folder, f"segments_{img_id}.txt")
     segs = np.asarray(segs)
-    with open(fname, "w") as f:
-        f.write(f"{segs.shape[0]}\n")
-        for line in segs:
-            f.write(f"{line[0]} {line[1]} {line[2]} {line[3]}\n")
+    body = "".join("%s %s %s %s\n" % (s[0], s[1], s[2], s[3]) for s in segs)
+    with open(_segments_file(folder, img_id), "w") as fh:
+        fh.write("%d\n%s" % (segs.shape[0], body))
 
 
 def read_txt_segments(folder, img_id):
-    check_path(folder)
-    fname = os.path.join(folder, f"segments_{img_id}.txt")
-    with open(fname) as f:
-        txt_lines = f.readlines()
-    n_segments = int(txt_lines[0].strip())
-    assert n_segments + 1 == len(txt_lines)
-    segs = [[float(kk) for kk in row.strip().split(" ")] for row in txt_lines[1:]]
-    return np.array(segs)
+    _require(folder)
+    with open(_segments_file(folder, img_id)) as fh:
+        rows = fh.read().splitlines()
+    n = int(rows[0])
+    if n + 1 != len(rows):
+        raise AssertionError("segment count does not match the number of rows")
+    return np.array([[float(x) for x in r.split(" ")] for r in rows[1:]])
 
 
 def read_all_segments_from_folder(folder):
-    all_2d_segs = {}
-    for fname in os.listdir(folder):
-        img_id = int(fname[9:-4])
-        all_2d_segs[img_id] = read_txt_segments(folder, img_id)
-    return all_2d_segs
+    out = {}
+    for name in os.listdir(folder):
+        img_id = int(name[len("segments_"):-len(".txt")])
+        out[img_id] = read_txt_segments(folder, img_id)
+    return out
 
 
 # ---- line tracks (util/io.py:259-346) ----------------------------------------------------------------------------
 def save_txt_linetracks(fname, linetracks, n_visible_views=4):
-    d = os.path.dirname(fname)
-    if d and not os.path.exists(d):
-        os.makedirs(d)
-    linetracks = [track for track in linetracks if track.count_images() >= n_visible_views]
-    with open(fname, "w") as f:
-        f.write(f"{len(linetracks)}\n")
-        for track_id, track in enumerate(linetracks):
-            f.write(f"{track_id} {track.count_lines()} {track.count_images()}\n")
-            # the reference's f-string continues over source lines, which leaves the indentation inside the row
-            pad = " " * 18
-            f.write(f"{track.line.start[0]:.10f} {pad}{track.line.start[1]:.10f} {pad}{track.line.start[2]:.10f}\n")
-            f.write(f"{track.line.end[0]:.10f} {pad}{track.line.end[1]:.10f} {pad}{track.line.end[2]:.10f}\n")
-            f.write("".join(f"{i} " for i in track.image_id_list) + "\n")
-            f.write("".join(f"{i} " for i in track.line_id_list) + "\n")
+    """alltracks.txt. A 3D point row is "x <18 blanks>y <18 blanks>z": the reference's f-string is continued over
+    source lines, which leaves the source indentation inside the row."""
+    parent = os.path.dirname(fname)
+    if parent:
+        os.makedirs(parent, exist_ok=True)
+    kept = [t for t in linetracks if t.count_images() >= n_visible_views]
+    gap = " " + " " * 18
+    point = lambda p: gap.join("%.10f" % float(v) for v in p)
+    ids = lambda seq: "".join("%s " % v for v in seq)
+    out = [str(len(kept))]
+    for k, t in enumerate(kept):
+        out += ["%d %d %d" % (k, t.count_lines(), t.count_images()), point(t.line.start), point(t.line.end),
+                ids(t.image_id_list), ids(t.line_id_list)]
+    with open(fname, "w") as fh:
+        fh.write("\n".join(out) + "\n")
 
 
 def read_txt_linetracks(fname):
     """Inverse of save_txt_linetracks: [(line (2,3), image_id_list, line_id_list)] (whitespace tolerant)."""
-    check_path(fname)
-    with open(fname) as f:
-        tok = f.read().split()
-    n, p, out = int(tok[0]), 1, []
-    for _ in range(n):
-        n_lines = int(tok[p + 1])
-        p += 3
-        line = np.array([float(x) for x in tok[p:p + 6]]).reshape(2, 3)
-        p += 6
-        img = [int(x) for x in tok[p:p + n_lines]]
-        p += n_lines
-        lid = [int(x) for x in tok[p:p + n_lines]]
-        p += n_lines
+    _require(fname)
+    with open(fname) as fh:
+        tok = fh.read().split()
+    pos = 1
+    out = []
+    for _ in range(int(tok[0])):
+        n_lines = int(tok[pos + 1])
+        pos += 3
+        line = np.array(tok[pos:pos + 6], dtype=np.float64).reshape(2, 3)
+        pos += 6
+        img = [int(x) for x in tok[pos:pos + n_lines]]
+        lid = [int(x) for x in tok[pos + n_lines:pos + 2 * n_lines]]
+        pos += 2 * n_lines
         out.append((line, img, lid))
     return out
 
 
 def save_folder_linetracks(folder, linetracks):
-    if os.path.exists(folder):
-        shutil.rmtree(folder)
+    delete_folder(folder)
     os.makedirs(folder)
-    for track_id, track in enumerate(linetracks):
-        track.Write(os.path.join(folder, f"track_{track_id}.txt"))
+    for k, t in enumerate(linetracks):
+        t.Write(os.path.join(folder, "track_%d.txt" % k))
 
 
 def read_folder_linetracks(folder):
-    check_path(folder)
-    n_tracks = sum(1 for fname in os.listdir(folder) if fname[-4:] == ".txt" and fname[:5] == "track")
-    linetracks = []
-    for track_id in range(n_tracks):
-        track = base.LineTrack()
-        track.Read(os.path.join(folder, f"track_{track_id}.txt"))
-        linetracks.append(track)
-    return linetracks
+    _require(folder)
+    n_tracks = len([f for f in os.listdir(folder) if f.startswith("track") and f.endswith(".txt")])
+    out = []
+    for k in range(n_tracks):
+        t = base.LineTrack()
+        t.Read(os.path.join(folder, "track_%d.txt" % k))
+        out.append(t)
+    return out
+
+
+_INFO_FILES = ("config.npy", "imagecols.npy", "all_2d_segs.npy")
 
 
 def save_folder_linetracks_with_info(folder, linetracks, config=None, imagecols=None, all_2d_segs=None):
     save_folder_linetracks(folder, linetracks)
-    if config is not None:
-        save_npy(os.path.join(folder, "config.npy"), config)
-    if imagecols is not None:
-        save_npy(os.path.join(folder, "imagecols.npy"), imagecols.as_dict())
-    if all_2d_segs is not None:
-        save_npy(os.path.join(folder, "all_2d_segs.npy"), all_2d_segs)
+    payload = (config, None if imagecols is None else imagecols.as_dict(), all_2d_segs)
+    for name, obj in zip(_INFO_FILES, payload):
+        if obj is not None:
+            save_npy(os.path.join(folder, name), obj)
 
 
 def read_folder_linetracks_with_info(folder):
     linetracks = read_folder_linetracks(folder)
-    cfg, imagecols, all_2d_segs = None, None, None
-    if os.path.isfile(os.path.join(folder, "config.npy")):
-        cfg = read_npy(os.path.join(folder, "config.npy")).item()
-    if os.path.isfile(os.path.join(folder, "imagecols.npy")):
-        imagecols = base.ImageCollection(read_npy(os.path.join(folder, "imagecols.npy")).item())
-    if os.path.isfile(os.path.join(folder, "all_2d_segs.npy")):
-        all_2d_segs = read_npy(os.path.join(folder, "all_2d_segs.npy")).item()
-    return linetracks, cfg, imagecols, all_2d_segs
+    got = []
+    for name in _INFO_FILES:
+        f = os.path.join(folder, name)
+        got.append(read_npy(f).item() if os.path.isfile(f) else None)
+    cfg, ic, segs = got
+    return linetracks, cfg, (base.ImageCollection(ic) if ic is not None else None), segs
