@@ -186,3 +186,56 @@ def test_bulk_add_and_pipeline_groups_match_per_image_adds():
         assert eng.get_nodes().tobytes() == nodes_ref.tobytes()
         o2, e2 = eng.get_all_valid_edges()
         assert np.array_equal(o2, off_ref) and np.array_equal(e2[: o2[-1]], edges_ref[: off_ref[-1]])
+
+
+def test_full_size_hypersim100_properties():
+    """BASELINE.json configs[1] at full size (V=100, L=1000, N=20, K=10: 2e7 match rows, the bench workload), through
+    properties that do not need the oracle: counters are consistent with the node records, a second run and a
+    pipelined run (5 groups) reproduce every node record and valid connection bit for bit, two half shards reproduce
+    the full run, and the best candidate of every node is one of its valid connections' peers or scoreless."""
+    from limap_b200.engine import TriEngine
+    from limap_b200.synth import CONFIGS
+    sc = make_scene(**CONFIGS["hypersim100"])
+    src, ng, off, pairs = sc.bulk_matches()
+    assert len(pairs) == 20_000_000
+
+    def run(groups, shard=None):
+        eng = TriEngine(_cfg())
+        eng.upload(sc)
+        eng.set_ranges(*sc.ranges)
+        eng.set_pipeline_groups(groups)
+        eng.add_matches_bulk(src, ng, off, pairs)
+        if shard is not None:
+            eng.set_shard(*shard)
+        st = eng.run()
+        nodes = eng.get_nodes().copy()
+        if shard is not None:
+            return eng, st, nodes, None, None
+        eoff, edges = eng.get_all_valid_edges()
+        return eng, st, nodes, eoff.copy(), edges[: int(eoff[-1])].copy()
+
+    eng, st, nodes, eoff, edges = run(1)
+    assert st["n_rows"] == 20_000_000 and st["n_nodes"] == 100_000
+    assert int(nodes["n_cand"].sum()) == st["n_candidates"] > 5_000_000
+    assert int(nodes["n_valid"].sum()) == st["n_valid_edges"] == int(eoff[-1]) > 500_000
+    assert np.array_equal(np.diff(eoff), nodes["n_valid"])
+    has = nodes["n_cand"] > 0
+    assert np.isfinite(nodes["line"][has]).all() and (nodes["score"][has] >= 0).all()
+    assert (nodes["score"][~has] == 0).all()
+    assert (nodes["n_valid"] <= nodes["n_cand"]).all()
+    assert edges[:, 1].min() >= 0 and edges[:, 1].max() < 1000 and set(np.unique(edges[:, 0])) <= set(sc.img_ids.tolist())
+    # idempotence
+    st2 = eng.run()
+    assert st2["n_candidates"] == st["n_candidates"] and st2["n_valid_edges"] == st["n_valid_edges"]
+    assert eng.get_nodes().tobytes() == nodes.tobytes()
+    # pipelined groups
+    _, st5, nodes5, eoff5, edges5 = run(5)
+    assert nodes5.tobytes() == nodes.tobytes() and np.array_equal(eoff5, eoff) and np.array_equal(edges5, edges)
+    # two half shards
+    tot = 0
+    for lo, hi in ((0, 50), (50, 100)):
+        e2, s2, n2, _, _ = run(1, shard=(lo, hi))
+        a, b = int(sc.line_off[lo]), int(sc.line_off[hi])
+        assert n2[a:b].tobytes() == nodes[a:b].tobytes()
+        tot += s2["n_candidates"]
+    assert tot == st["n_candidates"]
