@@ -94,3 +94,61 @@ class NodeGather:
                 p = p.contiguous()
                 check(self.lib.lm_tri_import_edges(h, p.numel() // 2, C.c_void_p(p.data_ptr()), 1))
         torch.cuda.current_stream().synchronize()
+
+
+# ---- track-sharded stages (LM refinement with constant cameras, J-Linkage per image) -------------
+def partition_by_cost(costs, world):
+    """Units (tracks by #supports, images by #segments) dealt to `world` ranks: sorted by cost descending and dealt
+    in snake order, so every rank gets the same count (+-1) and nearly the same total cost. Returns a list of
+    ascending index arrays; deterministic on every rank."""
+    c = np.asarray(costs, dtype=np.float64)
+    order = np.argsort(-c, kind="stable")
+    out = [[] for _ in range(max(world, 1))]
+    for k, idx in enumerate(order):
+        r = k % world
+        if (k // world) % 2 == 1:
+            r = world - 1 - r
+        out[r].append(int(idx))
+    return [np.asarray(sorted(x), dtype=np.int64) for x in out]
+
+
+def gather_rows(local_index, local_rows, total, group=None):
+    """Every rank holds rows of a [total, k] table for its own indices; returns the full table on every rank (one
+    padded all-gather of the indices and one of the rows)."""
+    import torch
+    idx = torch.as_tensor(local_index, dtype=torch.int64, device=local_rows.device).reshape(-1)
+    rows = local_rows.reshape(idx.numel(), -1) if idx.numel() else local_rows.reshape(0, local_rows.shape[-1])
+    k = rows.shape[1]
+    parts_i = all_gather_padded(idx, group)
+    parts_r = all_gather_padded(rows.reshape(-1).contiguous(), group)
+    out = torch.zeros((int(total), k), dtype=local_rows.dtype, device=local_rows.device)
+    for pi, pr in zip(parts_i, parts_r):
+        if pi.numel():
+            out[pi] = pr.reshape(pi.numel(), k)
+    return out
+
+
+def slice_tracks(index, sup_off, *per_support):
+    """Sub-problem of the tracks in `index`: (sup_off', per-support arrays restricted and re-packed)."""
+    sup_off = np.asarray(sup_off, dtype=np.int64)
+    counts = (sup_off[1:] - sup_off[:-1])[index]
+    new_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    sel = np.concatenate([np.arange(sup_off[t], sup_off[t + 1]) for t in index]) if len(index) else np.zeros(0, np.int64)
+    return new_off, [np.ascontiguousarray(np.asarray(a)[sel]) for a in per_support]
+
+
+def solve_line_ba_sharded(solve, kvec, qvec, tvec, sup_off, sup_view, segs, line3d, line_init, rank, world, group=None,
+                          device="cuda", **kw):
+    """Line BA with constant cameras is block-separable per track (hybrid_bundle_adjustment.cc:106-123,156-197):
+    tracks are dealt by #supports, every rank solves its share with `solve` (BAEngine.solve) and the refined lines
+    (+ iteration counts and costs) are all-gathered. Returns dict(line[T,6], iters[T,2], cost[T,2]) on every rank."""
+    import torch
+    sup_off = np.asarray(sup_off, dtype=np.int64)
+    T = len(sup_off) - 1
+    mine = partition_by_cost(sup_off[1:] - sup_off[:-1], world)[rank]
+    off, (sv, sg, l3) = slice_tracks(mine, sup_off, sup_view, segs, line3d)
+    res = solve(kvec, qvec, tvec, off, sv, sg, l3, np.ascontiguousarray(np.asarray(line_init)[mine]), **kw)
+    table = np.concatenate([res["line"], res["iters"].astype(np.float64), res["cost"]], axis=1) if len(mine) else \
+        np.zeros((0, 10))
+    full = gather_rows(mine, torch.as_tensor(table, dtype=torch.float64, device=device), T, group).cpu().numpy()
+    return dict(line=full[:, :6], iters=full[:, 6:8].astype(np.int32), cost=full[:, 8:10])

@@ -52,3 +52,69 @@ def test_all_gather_padded_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_partition_by_cost_is_balanced_and_complete():
+    from limap_b200.dist import partition_by_cost, slice_tracks
+    rng = np.random.default_rng(0)
+    cost = rng.integers(2, 60, 1001)
+    for world in (1, 2, 3, 8):
+        parts = partition_by_cost(cost, world)
+        allidx = np.concatenate(parts)
+        assert len(parts) == world and np.array_equal(np.sort(allidx), np.arange(1001))
+        sizes = [len(p) for p in parts]
+        assert max(sizes) - min(sizes) <= 1
+        tot = [cost[p].sum() for p in parts]
+        assert max(tot) - min(tot) <= 60
+        assert all(np.all(np.diff(p) > 0) for p in parts)
+    sup_off = np.concatenate([[0], np.cumsum(cost)])
+    flat = np.arange(sup_off[-1])
+    off, (sub,) = slice_tracks(np.array([3, 10]), sup_off, flat)
+    assert off.tolist() == [0, cost[3], cost[3] + cost[10]]
+    assert np.array_equal(sub, np.concatenate([flat[sup_off[3]:sup_off[4]], flat[sup_off[10]:sup_off[11]]]))
+
+
+def _ba_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from limap_b200.dist import solve_line_ba_sharded
+    rng = np.random.default_rng(5)
+    T = 37
+    cnt = rng.integers(2, 9, T)
+    sup_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    S = int(sup_off[-1])
+    sup_view = rng.integers(0, 5, S).astype(np.int32)
+    segs = rng.uniform(0, 100, (S, 4))
+    line3d = rng.normal(size=(S, 6))
+    init = rng.normal(size=(T, 6))
+    seen = {}
+
+    def fake_solve(kvec, qvec, tvec, off, sv, sg, l3, li, **kw):  # stands in for BAEngine.solve (needs a GPU)
+        n = len(off) - 1
+        seen["n"] = n
+        # a function of the track's own data only: line = init + sum of its segments' first coordinate
+        s = np.array([sg[off[t]:off[t + 1], 0].sum() for t in range(n)])
+        return dict(line=li + s[:, None], iters=np.stack([off[1:] - off[:-1], np.zeros(n, np.int64)], 1).astype(np.int32),
+                    cost=np.stack([s, 0.5 * s], 1))
+    out = solve_line_ba_sharded(fake_solve, None, None, None, sup_off, sup_view, segs, line3d, init, rank, world,
+                                device="cpu")
+    s_all = np.array([segs[sup_off[t]:sup_off[t + 1], 0].sum() for t in range(T)])
+    ok = np.allclose(out["line"], init + s_all[:, None]) and np.array_equal(out["iters"][:, 0], cnt)
+    ok &= np.allclose(out["cost"][:, 1], 0.5 * s_all) and abs(seen["n"] - T / world) <= 1
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_sharded_line_ba_gather_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ba_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
