@@ -61,6 +61,9 @@ void orc_set_num_threads(int n) {
 #endif
 }
 
+// 0: the reference's OpenMP schedule (inside one node); 1: OpenMP over the 2D lines of the image (same results).
+void orc_tri_set_node_parallel(void *h, int flag);
+
 void *orc_tri_create(const orc_tri_cfg *c) {
   TriConfig cfg;
   cfg.debug_mode = c->debug_mode; cfg.add_halfpix = c->add_halfpix; cfg.use_vp = c->use_vp;
@@ -81,6 +84,7 @@ void *orc_tri_create(const orc_tri_cfg *c) {
   return h;
 }
 void orc_tri_destroy(void *hp) { delete (OrcTri *)hp; }
+void orc_tri_set_node_parallel(void *hp, int flag) { ((OrcTri *)hp)->tri->node_parallel_ = flag != 0; }
 
 int orc_tri_init(void *hp, int n_views, const int32_t *img_ids, const int32_t *model_ids,
                  const double *kvec, const double *qvec, const double *tvec,

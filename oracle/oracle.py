@@ -48,6 +48,7 @@ def lib():
         L.orc_tri_create.restype = _P
         L.orc_tri_create.argtypes = [_P]
         L.orc_tri_destroy.argtypes = [_P]
+        L.orc_tri_set_node_parallel.argtypes = [_P, C.c_int]
         L.orc_tri_init.argtypes = [_P, C.c_int] + [_P] * 7
         L.orc_tri_set_ranges.argtypes = [_P, _P, _P]
         L.orc_tri_unset_ranges.argtypes = [_P]
@@ -91,7 +92,9 @@ class OracleTri:
     """fp64 CPU restatement of GlobalLineTriangulator, same array-level interface as
     limap_b200.engine.TriEngine."""
 
-    def __init__(self, cfg=None, threads=None):
+    def __init__(self, cfg=None, threads=None, node_parallel=False):
+        """node_parallel=False keeps the reference's OpenMP schedule (inside one node); True moves the OpenMP loop out to
+        the 2D lines of the image -- same results, the schedule a throughput-tuned CPU implementation would use."""
         from limap_b200.config import make_tri_config
         self.cfg = make_tri_config(cfg) if not hasattr(cfg, "_fields_") else cfg
         L = lib()
@@ -100,6 +103,8 @@ class OracleTri:
         self._h = L.orc_tri_create(C.byref(self.cfg))
         if not self._h:
             raise RuntimeError(L.orc_last_error().decode())
+        if node_parallel:
+            L.orc_tri_set_node_parallel(self._h, 1)
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -363,6 +363,10 @@ class GlobalLineTriangulator {
 public:
   TriConfig config_;
   bool faithful_ = true; // true: per-call camview() copies, R()/K_inv() recomputation as in the reference
+  // false: the reference's schedule (OpenMP inside one node: over the connections / candidates of a 2D line).
+  // true: the same arithmetic with the OpenMP loop moved out to the 2D lines of the image (nodes are independent), the
+  // schedule a CPU implementation tuned for throughput would use; results are identical.
+  bool node_parallel_ = false;
 
   explicit GlobalLineTriangulator(const TriConfig &cfg) : config_(cfg) {
     linker2d_.config = cfg.linker2d;
@@ -389,7 +393,7 @@ public:
       valid_edges_[img_id].assign(n_lines, {});
       valid_tris_[img_id].assign(n_lines, {});
       tris_best_[img_id].assign(n_lines, TriTuple());
-      already_scored_[img_id].assign(n_lines, false);
+      already_scored_[img_id].assign(n_lines, 0);
     }
   }
   void InitVPResults(const std::map<int, VPResult> &v) { vpresults_ = v; }
@@ -411,7 +415,9 @@ public:
                                    std::to_string(ng_img_id) + ").");
         edges_[img_id][line_id].push_back(std::make_pair(ng_img_id, ng_line_id));
       }
-      for (size_t line_id = 0; line_id < CountLines(img_id); ++line_id) {
+      const long long n_lines = (long long)CountLines(img_id);
+#pragma omp parallel for schedule(dynamic, 8) if (node_parallel_)
+      for (long long line_id = 0; line_id < n_lines; ++line_id) {
         triangulateOneNode(img_id, (int)line_id);
         edges_[img_id][line_id].clear();
       }
@@ -464,6 +470,7 @@ private:
   void triangulateOneNode(int img_id, int line_id) {
     auto &connections = edges_[img_id][line_id];
     const Line2d &l1 = all_lines_2d_[img_id][line_id];
+#pragma omp atomic
     n_match_rows_tested_ += (long long)connections.size();
     if (l1.length() <= config_.min_length_2d) return;
     const CameraView view1 = camview(img_id);
@@ -533,7 +540,9 @@ private:
     LineLinker3d linker3d_scoring = linker3d_;
     linker3d_scoring.config.set_to_shared_parent_scoring();
     n_tris_[img_id].assign(CountLines(img_id), 0);
-    for (size_t line_id = 0; line_id < CountLines(img_id); ++line_id)
+    const long long n_lines = (long long)CountLines(img_id);
+#pragma omp parallel for schedule(dynamic, 8) if (node_parallel_)
+    for (long long line_id = 0; line_id < n_lines; ++line_id)
       scoreOneNode(img_id, (int)line_id, linker2d_, linker3d_scoring);
     if (!config_.debug_mode) valid_tris_[img_id].assign(CountLines(img_id), {});
   }
@@ -597,7 +606,7 @@ private:
       tris_[img_id][line_id].clear();
       valid_tris_[img_id][line_id].clear();
     }
-    already_scored_[img_id][line_id] = true;
+    already_scored_[img_id][line_id] = 1;
   }
 
   // global_line_triangulator.cc:168-232
@@ -711,7 +720,7 @@ private:
   std::map<int, CameraView> views_;
   std::map<int, VPResult> vpresults_;
   std::map<int, std::vector<std::vector<std::pair<int, int>>>> edges_;
-  std::map<int, std::vector<bool>> already_scored_;
+  std::map<int, std::vector<char>> already_scored_; // bytes, not bits: lines are scored concurrently in node-parallel mode
   std::map<int, std::vector<bool>> valid_flags_;
   bool ranges_flag_ = false;
   V3 ranges_lo_, ranges_hi_;

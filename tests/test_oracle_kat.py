@@ -125,3 +125,30 @@ def test_pose_rotation_against_reference_python_golden(oracle_lib):
         p = np.zeros(2)
         oracle_lib.orc_project_point(orc._p(cam), orc._p(X), orc._p(p))
         assert np.abs(p - exp).max() <= 1e-9
+
+
+def test_node_parallel_schedule_gives_identical_results():
+    """The oracle's throughput schedule (OpenMP over the 2D lines of an image) is the reference-structured restatement
+    with the loop moved outwards: every output is bit-identical for any thread count."""
+    from limap_b200.config import DEFAULT_YAML_TRIANGULATION
+    from limap_b200.synth import make_scene
+    sc = make_scene(V=8, L=120, N=5, K=6, seed=77)
+    outs = []
+    for mode, th in ((False, 1), (True, 1), (True, 4)):
+        o = orc.OracleTri(dict(DEFAULT_YAML_TRIANGULATION), threads=th, node_parallel=mode)
+        o.upload(sc)
+        o.set_ranges(*sc.ranges)
+        for i in sc.img_ids:
+            o.add_image_matches(int(i), *sc.flat_matches(int(i)))
+        tr = o.build_tracks()
+        outs.append(([o.get_best(int(i)) for i in sc.img_ids], [o.get_valid_edges(int(i)) for i in sc.img_ids], tr,
+                     o.rows_tested()))
+    ref = outs[0]
+    for other in outs[1:]:
+        assert other[3] == ref[3]
+        for a, b in zip(ref[0], other[0]):
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        for a, b in zip(ref[1], other[1]):
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        assert np.array_equal(ref[2]["track_off"], other[2]["track_off"])
+        assert np.array_equal(ref[2]["track_line"], other[2]["track_line"])
