@@ -374,7 +374,7 @@ int lm_scene_upload(lm_ctx *c, int32_t n_views, const int32_t *img_ids, const in
   for (int v = 0; v < n_views; ++v) c->id2view[img_ids[v]] = v;
   c->line_off.assign(line_off, line_off + n_views + 1);
   c->n_nodes = line_off[n_views];
-  if (c->n_nodes >= (int64_t)1 << 32) return fail(LM_ERR_INVALID, "too many 2D lines");
+  if (c->n_nodes >= ((int64_t)1 << 31) - 64) return fail(LM_ERR_INVALID, "more than 2^31 2D lines in one scene");
   std::vector<lm::ViewD> views(n_views);
   std::vector<uint16_t> node_view(c->n_nodes);
   for (int v = 0; v < n_views; ++v) {
@@ -721,7 +721,8 @@ int lm_tri_run(lm_ctx *c) {
     bng[i] = blk[i].ng_view;
   }
   const int64_t n_rows = row_off[nb];
-  if (n_rows >= ((int64_t)1 << 32) - 64) return fail(LM_ERR_INVALID, "more than 2^32 match rows in one run");
+  // the sort and scan item counts are 32-bit signed
+  if (n_rows >= ((int64_t)1 << 31) - 64) return fail(LM_ERR_INVALID, "more than 2^31 match rows in one run (shard the scene by source image)");
   c->n_rows = n_rows;
   c->node_begin = c->line_off[vb];
   c->node_end = c->line_off[ve];
