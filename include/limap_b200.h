@@ -148,6 +148,19 @@ int lm_tri_import_nodes(lm_ctx *ctx, int64_t node_begin, int64_t node_end, const
 int64_t lm_tri_num_valid_edges(lm_ctx *ctx);
 int lm_tri_export_edges(lm_ctx *ctx, void *d_out /* int64[n][2] */);
 int lm_tri_import_edges(lm_ctx *ctx, int64_t n, const void *d_in /* int64[n][2] */, int32_t append);
+/* The same exchange as one fixed-size message per rank, so that a multi-GPU step is pack -> ONE all-gather ->
+ * unpack with no host synchronisation (replaces nothing in the reference, which is single-process).
+ * Message: [int64 n_edges, int64 n_nodes] | lm_node_record[max_nodes] | (uint32 src_node, uint32 dst_node)[cap_edges].
+ * pack: this context's shard -> d_msg (device, asynchronous on the ctx stream). unpack: `world` messages laid out
+ * back to back (the all-gather output) -> node records of every rank in place and the directed valid connections of
+ * all ranks, in rank order, ready for lm_tri_build_tracks; rank_node_begin[r] = first node of rank r's shard.
+ * lm_tri_gather_status synchronises and returns 1 when some rank had more than cap_edges connections (repeat the
+ * exchange with a larger message), 0 otherwise; *n_edges_total = directed edges now held. */
+int64_t lm_tri_gather_message_bytes(int64_t max_nodes, int64_t cap_edges);
+int lm_tri_pack_message(lm_ctx *ctx, int64_t max_nodes, int64_t cap_edges, void *d_msg);
+int lm_tri_unpack_messages(lm_ctx *ctx, int32_t world, const int64_t *rank_node_begin, int64_t max_nodes,
+                           int64_t cap_edges, const void *d_msgs);
+int64_t lm_tri_gather_status(lm_ctx *ctx, int64_t *n_edges_total);
 /* first node index of a view (ascending img_id order) */
 int64_t lm_scene_node_offset(lm_ctx *ctx, int32_t view_index);
 
@@ -269,6 +282,18 @@ typedef struct lm_vp_config {
  * if it exceeds vp_cap) or <0. */
 int64_t lm_vp_detect(lm_ctx *ctx, int32_t n_images, const int64_t *line_off, const double *segs,
                      const lm_vp_config *cfg, int32_t *labels, int64_t *vp_off, double *vps, int64_t vp_cap);
+
+/* Same, with image_index[n_images] (NULL = 0..n_images-1): the index that seeds the hypotheses of each image. A
+ * rank that detects a subset of a scene's images (vplib/base_vp_detector.py:46-78 fans images out over processes)
+ * passes their positions in the full list and gets exactly the labels the single call on all images returns. */
+int64_t lm_vp_detect_indexed(lm_ctx *ctx, int32_t n_images, const int64_t *line_off, const double *segs,
+                             const lm_vp_config *cfg, const int64_t *image_index, int32_t *labels, int64_t *vp_off,
+                             double *vps, int64_t vp_cap);
+typedef struct lm_vp_stats {
+  int64_t n_images, n_segments, n_vps; /* of the last lm_vp_detect: images, segments of min_length, VPs returned */
+  double kernel_ms;                    /* device time of the clustering kernel (CUDA events on the ctx stream) */
+} lm_vp_stats;
+int lm_vp_get_stats(lm_ctx *ctx, lm_vp_stats *out);
 
 #ifdef __cplusplus
 }

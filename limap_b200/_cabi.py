@@ -35,6 +35,10 @@ class VPConfig(C.Structure):
                 ("min_num_supports", C.c_int32), ("n_models", C.c_int32), ("seed", C.c_uint64)]
 
 
+class VPStats(C.Structure):
+    _fields_ = [("n_images", C.c_int64), ("n_segments", C.c_int64), ("n_vps", C.c_int64), ("kernel_ms", C.c_double)]
+
+
 class BAStats(C.Structure):
     _fields_ = [("n_tracks", C.c_int64), ("n_blocks", C.c_int64), ("total_iterations", C.c_int64),
                 ("total_successful", C.c_int64), ("solve_ms", C.c_double), ("prepare_ms", C.c_double)]
@@ -86,6 +90,10 @@ _SIGS = {
     "lm_tri_export_edges": (C.c_int, [_P, _P]),
     "lm_tri_import_edges": (C.c_int, [_P, C.c_int64, _P, C.c_int32]),
     "lm_scene_node_offset": (C.c_int64, [_P, C.c_int32]),
+    "lm_tri_gather_message_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "lm_tri_pack_message": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
+    "lm_tri_unpack_messages": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_int64, _P]),
+    "lm_tri_gather_status": (C.c_int64, [_P, C.POINTER(C.c_int64)]),
     "lm_tri_build_tracks": (C.c_int64, [_P, C.POINTER(C.c_int64)]),
     "lm_tri_get_tracks": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "lm_tri_add_matches_bulk": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
@@ -94,6 +102,8 @@ _SIGS = {
     "lm_ba_solve": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lm_ba_get_stats": (C.c_int, [_P, _P]),
     "lm_vp_detect": (C.c_int64, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64]),
+    "lm_vp_detect_indexed": (C.c_int64, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int64]),
+    "lm_vp_get_stats": (C.c_int, [_P, _P]),
     "lm_tracks_support_flags": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "lm_aggregate_lines": (C.c_int, [C.c_int64, _P, _P, _P, C.c_int32, _P]),
     "lm_remerge_labels": (C.c_int64, [_P, C.c_int64, _P, _P, _P, _P, _P]),

@@ -129,6 +129,21 @@ struct lm_ctx {
   DevBuf d_raw_blocks, d_bkey, d_bkey2, d_bval, d_bval2, d_blk_rows; // device mirror of `blocks` + sort scratch
   int64_t raw_uploaded = 0;
   cudaEvent_t ev_raw = nullptr; // recorded on the copy stream after the latest descriptor upload
+  // Every host->device transfer (scene, VPs, matches) travels on the copy stream; the compute stream only waits
+  // for events. A compute stream whose latest operation is itself a host->device copy has its next operations
+  // (event records, kernel launches) ordered behind whatever the H2D copy engine is working on -- i.e. behind a
+  // bulk match upload issued in between (measured in round 1: ~3 ms per hypersim100 step).
+  cudaEvent_t ev_scene = nullptr;
+  std::vector<lm::ViewD> h_views;    // staging of the scene tables (kept alive: the copies are asynchronous)
+  std::vector<uint16_t> h_node_view;
+  std::vector<cudaEvent_t> evk;      // per pipeline group: node-kernel begin/end (read after the run's only sync)
+  DevBuf d_gather;                   // [0] total edges, [1] overflow flag of the last unpack; +64: rank node table
+  int64_t gather_tab[64] = {0};
+  int gather_world = 0;
+  bool edges_count_on_device = false; // n_edges_dev is still on the device (lm_tri_unpack_messages)
+  int cap_hint = 0;                  // staging capacity of the node kernel, from the previous run (0: default)
+  bool outside_shard_clean = false;  // node records / row offsets outside the shard were zero-filled
+  int run_retry = 0;
   int sm_count = 148;
   int max_smem_optin = 0;
   // scene
@@ -189,6 +204,8 @@ struct lm_ctx {
   DevBuf d_ba_in, d_ba_blocks, d_ba_out;
   DevBuf d_vp_pts, d_vp_off, d_vp_labels, d_vp_nc, d_vp_ps, d_vp_mat;
   lm_ba_stats ba_stats;
+  lm_vp_stats vp_stats;
+  DevBuf d_vp_idx;
   // track filters / remerge
   DevBuf d_mg_in, d_mg_out, d_mg_edges;
   lm_merge_stats mg_stats;
@@ -279,11 +296,13 @@ int lm_ctx_create(int device, lm_ctx **out) {
   CU(cudaEventCreate(&c->evk0));
   CU(cudaEventCreate(&c->evk1));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_pin), 256, cudaHostAllocDefault));
+  CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_pin), 2048, cudaHostAllocDefault));
+  CU(cudaEventCreateWithFlags(&c->ev_scene, cudaEventDisableTiming));
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   memset(&c->stats, 0, sizeof(c->stats));
   memset(&c->ba_stats, 0, sizeof(c->ba_stats));
+  memset(&c->vp_stats, 0, sizeof(c->vp_stats));
   memset(&c->mg_stats, 0, sizeof(c->mg_stats));
   *out = c;
   return LM_OK;
@@ -297,13 +316,15 @@ void lm_ctx_destroy(lm_ctx *c) {
                     &c->d_blk_src, &c->d_blk_ng, &c->d_blk_pair_off, &c->d_key, &c->d_key2, &c->d_val, &c->d_val2,
                     &c->d_sort_tmp, &c->d_node_row_off, &c->d_scalars, &c->d_nodes, &c->d_row_state, &c->d_row_cand,
                     &c->d_slab, &c->d_edges, &c->d_edges2, &c->d_edge_keys, &c->d_edge_keys2, &c->d_edge_w,
-                    &c->d_edge_cnt, &c->d_nvalid, &c->d_edge_off, &c->d_edge_ng, &c->d_ba_in, &c->d_ba_blocks, &c->d_ba_out, &c->d_raw_blocks, &c->d_bkey, &c->d_bkey2, &c->d_bval, &c->d_bval2, &c->d_blk_rows, &c->d_vp_label, &c->d_vp_voff, &c->d_vp_vps, &c->d_vp_pts, &c->d_vp_off, &c->d_vp_labels, &c->d_vp_nc, &c->d_vp_ps, &c->d_vp_mat, &c->d_mg_in, &c->d_mg_out, &c->d_mg_edges};
+                    &c->d_edge_cnt, &c->d_nvalid, &c->d_edge_off, &c->d_edge_ng, &c->d_ba_in, &c->d_ba_blocks, &c->d_ba_out, &c->d_raw_blocks, &c->d_bkey, &c->d_bkey2, &c->d_bval, &c->d_bval2, &c->d_blk_rows, &c->d_vp_label, &c->d_vp_voff, &c->d_vp_vps, &c->d_vp_pts, &c->d_vp_off, &c->d_vp_labels, &c->d_vp_nc, &c->d_vp_ps, &c->d_vp_mat, &c->d_mg_in, &c->d_mg_out, &c->d_mg_edges, &c->d_gather, &c->d_vp_idx};
   for (DevBuf *b : bufs) b->release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->evk0) cudaEventDestroy(c->evk0);
   if (c->evk1) cudaEventDestroy(c->evk1);
   if (c->ev_raw) cudaEventDestroy(c->ev_raw);
+  if (c->ev_scene) cudaEventDestroy(c->ev_scene);
+  for (auto e : c->evk) cudaEventDestroy(e);
   for (auto &ch : c->chunks) cudaEventDestroy(ch.ev);
   for (auto e : c->event_pool) cudaEventDestroy(e);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -351,13 +372,16 @@ static void make_view(int model_id, const double *kv, const double *qv, const do
 
 static int upload_segs(lm_ctx *c) {
   // add_halfpix (base_line_triangulator.cc:32-43) is applied when both scene and config are known.
+  CU(cudaStreamSynchronize(c->copy_stream)); // no copy from h_segs may still be in flight
   c->h_segs = c->h_segs_raw;
   if (c->have_cfg && c->cfg.add_halfpix)
     for (double &v : c->h_segs) v += 0.5;
+  if (std::max<size_t>(32, c->h_segs.size() * 8) > c->d_segs.cap) CU(cudaStreamSynchronize(c->stream)); // readers of the old buffer
+  CU(cudaStreamSynchronize(c->copy_stream)); // h_segs is rewritten below: no copy from it may be in flight
   CU(c->d_segs.ensure(std::max<size_t>(32, c->h_segs.size() * 8)));
   if (!c->h_segs.empty())
-    CU(cudaMemcpyAsync(c->d_segs.p, c->h_segs.data(), c->h_segs.size() * 8, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyAsync(c->d_segs.p, c->h_segs.data(), c->h_segs.size() * 8, cudaMemcpyHostToDevice, c->copy_stream));
+  CU(cudaEventRecord(c->ev_scene, c->copy_stream));
   return LM_OK;
 }
 
@@ -368,6 +392,8 @@ int lm_scene_upload(lm_ctx *c, int32_t n_views, const int32_t *img_ids, const in
   CU(cudaSetDevice(c->device));
   for (int v = 1; v < n_views; ++v)
     if (img_ids[v] <= img_ids[v - 1]) return fail(LM_ERR_INVALID, "img_ids must be strictly ascending");
+  CU(cudaStreamSynchronize(c->copy_stream)); // the host staging tables below may still feed a previous upload
+  CU(cudaStreamSynchronize(c->stream));      // ... and a previous run may still read buffers that get re-allocated
   c->V = n_views;
   c->img_ids.assign(img_ids, img_ids + n_views);
   c->id2view.clear();
@@ -375,8 +401,10 @@ int lm_scene_upload(lm_ctx *c, int32_t n_views, const int32_t *img_ids, const in
   c->line_off.assign(line_off, line_off + n_views + 1);
   c->n_nodes = line_off[n_views];
   if (c->n_nodes >= ((int64_t)1 << 31) - 64) return fail(LM_ERR_INVALID, "more than 2^31 2D lines in one scene");
-  std::vector<lm::ViewD> views(n_views);
-  std::vector<uint16_t> node_view(c->n_nodes);
+  std::vector<lm::ViewD> &views = c->h_views;
+  std::vector<uint16_t> &node_view = c->h_node_view;
+  views.resize(n_views);
+  node_view.resize(c->n_nodes);
   for (int v = 0; v < n_views; ++v) {
     if (model_ids[v] != 0 && model_ids[v] != 1)
       return fail(LM_ERR_INVALID, "only SIMPLE_PINHOLE / PINHOLE are legal on this path (IsUndistorted check)");
@@ -388,14 +416,14 @@ int lm_scene_upload(lm_ctx *c, int32_t n_views, const int32_t *img_ids, const in
   CU(c->d_views.ensure(sizeof(lm::ViewD) * n_views));
   CU(c->d_node_view.ensure(std::max<size_t>(2, 2 * c->n_nodes)));
   CU(c->d_line_off.ensure(8 * (n_views + 1)));
-  CU(cudaMemcpyAsync(c->d_views.p, views.data(), sizeof(lm::ViewD) * n_views, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_views.p, views.data(), sizeof(lm::ViewD) * n_views, cudaMemcpyHostToDevice, c->copy_stream));
   if (c->n_nodes)
-    CU(cudaMemcpyAsync(c->d_node_view.p, node_view.data(), 2 * c->n_nodes, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_line_off.p, c->line_off.data(), 8 * (n_views + 1), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_node_view.p, node_view.data(), 2 * c->n_nodes, cudaMemcpyHostToDevice, c->copy_stream));
+  CU(cudaMemcpyAsync(c->d_line_off.p, c->line_off.data(), 8 * (n_views + 1), cudaMemcpyHostToDevice, c->copy_stream));
   CU(c->d_img_ids.ensure(4 * n_views));
-  CU(cudaMemcpyAsync(c->d_img_ids.p, c->img_ids.data(), 4 * n_views, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream)); // host vectors above go out of scope
+  CU(cudaMemcpyAsync(c->d_img_ids.p, c->img_ids.data(), 4 * n_views, cudaMemcpyHostToDevice, c->copy_stream));
   c->have_scene = true;
+  c->outside_shard_clean = false;
   int rc = upload_segs(c);
   if (rc) return rc;
   c->image_added.assign(n_views, 0);
@@ -456,13 +484,15 @@ int lm_tri_set_vps(lm_ctx *c, int32_t n_images, const int32_t *img_ids, const in
   for (int v = 0; v < c->V; ++v)
     if (src[v] >= 0)
       memcpy(&vv[3 * voff[v]], vps + 3 * vp_off[src[v]], 24 * cnt[v]);
+  CU(cudaStreamSynchronize(c->stream)); // a previous run may still read the tables that are re-allocated
   CU(c->d_vp_label.ensure(4 * lab.size()));
   CU(c->d_vp_voff.ensure(8 * voff.size()));
   CU(c->d_vp_vps.ensure(8 * vv.size()));
-  CU(cudaMemcpyAsync(c->d_vp_label.p, lab.data(), 4 * lab.size(), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_vp_voff.p, voff.data(), 8 * voff.size(), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_vp_vps.p, vv.data(), 8 * vv.size(), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpyAsync(c->d_vp_label.p, lab.data(), 4 * lab.size(), cudaMemcpyHostToDevice, c->copy_stream));
+  CU(cudaMemcpyAsync(c->d_vp_voff.p, voff.data(), 8 * voff.size(), cudaMemcpyHostToDevice, c->copy_stream));
+  CU(cudaMemcpyAsync(c->d_vp_vps.p, vv.data(), 8 * vv.size(), cudaMemcpyHostToDevice, c->copy_stream));
+  CU(cudaEventRecord(c->ev_scene, c->copy_stream));
+  CU(cudaStreamSynchronize(c->copy_stream)); // the staging vectors die here
   c->have_vps = true;
   c->ran = false;
   return LM_OK;
@@ -495,6 +525,7 @@ int lm_tri_set_pipeline_groups(lm_ctx *c, int32_t n) {
 
 int lm_tri_set_shard(lm_ctx *c, int32_t b, int32_t e) {
   if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  if (b != c->shard_begin || e != c->shard_end) c->outside_shard_clean = false;
   c->shard_begin = b;
   c->shard_end = e;
   c->ran = false;
@@ -655,6 +686,10 @@ int64_t lm_tri_get_all_valid_edges(lm_ctx *c, int64_t *node_off, int32_t *edges)
   if (!node_off && !edges) return ne;
   // converted on the device and copied straight into the caller's buffers (pinned buffers avoid staging)
   const int64_t nsh = c->node_end - c->node_begin;
+  if (nsh <= 0) { // empty shard: nothing on the device to convert
+    if (node_off) memset(node_off, 0, 8 * (size_t)(c->n_nodes + 1));
+    return 0;
+  }
   const size_t off_bytes = 8 * (size_t)(c->n_nodes + 1), pair_bytes = 8 * (size_t)std::max<int64_t>(ne, 1);
   CU(c->d_host_edges.ensure(off_bytes + pair_bytes + 256));
   int64_t *d_off = c->d_host_edges.as<int64_t>();
@@ -728,6 +763,7 @@ int lm_tri_run(lm_ctx *c) {
   c->node_end = c->line_off[ve];
   c->h_nodes_valid = c->h_rows_valid = c->h_edges_valid = false;
   c->edges_collected = false;
+  c->edges_count_on_device = false;
   c->tracks.clear();
 
   CU(c->d_blk_row_off.ensure(8 * (nb + 1)));
@@ -739,7 +775,7 @@ int lm_tri_run(lm_ctx *c) {
   CU(c->d_val.ensure(4 * std::max<int64_t>(n_rows, 1)));
   CU(c->d_val2.ensure(4 * std::max<int64_t>(n_rows, 1)));
   CU(c->d_node_row_off.ensure(4 * (c->n_nodes + 2)));
-  CU(c->d_scalars.ensure(64));
+  CU(c->d_scalars.ensure(1024));
   CU(c->d_nodes.ensure(sizeof(lm::NodeRecord) * std::max<int64_t>(c->n_nodes, 1)));
   const int ns = (c->cfg.use_vp && !c->cfg.disable_vp_triangulation && c->have_vps) ? 3 : 1;
   c->ns = ns;
@@ -755,7 +791,9 @@ int lm_tri_run(lm_ctx *c) {
   cudaEventSynchronize(c->ev0);
   fprintf(stderr, "[lm trace] ev0 executed %.3f ms after run entry\n", lm_ms());
 #endif
-  lm::launch_zero_words(c->d_scalars.p, 16, s);
+  // scene tables / VP tables travel on the copy stream (see lm_ctx::ev_scene)
+  CU(cudaStreamWaitEvent(s, c->ev_scene, 0));
+  lm::launch_zero_words(c->d_scalars.p, 128, s);
   // block tables, derived on the device from the descriptors uploaded with the matches (no transfer now)
   {
     const int n_all = (int)c->blocks.size();
@@ -784,7 +822,7 @@ int lm_tri_run(lm_ctx *c) {
     CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmps, c->d_blk_rows.as<int64_t>(), c->d_blk_row_off.as<int64_t>(),
                                      nb + 1, s));
   }
-  unsigned int *d_max_rows = c->d_scalars.as<unsigned int>();
+  // d_scalars words: [1] index error, [2] staging overflow, bytes 16..47 counters, words [16 + g] largest node of group g
   int *d_err = c->d_scalars.as<int>() + 1;
   unsigned long long *d_counters = reinterpret_cast<unsigned long long *>(c->d_scalars.as<char>() + 16);
   int launches = 0;
@@ -799,6 +837,7 @@ int lm_tri_run(lm_ctx *c) {
   p.row_state = c->d_row_state.as<uint8_t>();
   p.row_cand = c->cfg.debug_mode ? c->d_row_cand.as<double>() : nullptr;
   p.counters = d_counters;
+  p.overflow = c->d_scalars.as<int>() + 2;
   p.node_begin = c->node_begin;
   p.node_end = c->node_end;
   const lm_tri_config &g = c->cfg;
@@ -847,15 +886,52 @@ int lm_tri_run(lm_ctx *c) {
   c->sorted_val = c->d_val2.as<uint32_t>();
   p.row_ng = c->sorted_val;
   const int n_groups = exhaustive ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(c->pipeline_groups, n_rows >> 16));
-  int max_rows_all = 0;
   c->node_kernel_ms_acc = 0;
   int bg0 = 0, gv0 = vb;
   const int64_t n_shard_nodes = c->node_end - c->node_begin;
+  // Results outside the shard (filled by lm_tri_import_nodes in a multi-GPU run) start from the empty record, so a
+  // getter never sees uninitialised memory; done once per scene/shard, imports survive later runs.
+  if (!c->outside_shard_clean && (c->node_begin > 0 || c->node_end < c->n_nodes)) {
+    if (c->node_begin > 0) {
+      CU(cudaMemsetAsync(c->d_nodes.p, 0, sizeof(lm::NodeRecord) * c->node_begin, s));
+      CU(cudaMemsetAsync(c->d_node_row_off.p, 0, 4 * c->node_begin, s));
+    }
+    if (c->node_end < c->n_nodes) {
+      CU(cudaMemsetAsync(c->d_nodes.as<lm::NodeRecord>() + c->node_end, 0, sizeof(lm::NodeRecord) * (c->n_nodes - c->node_end), s));
+      CU(cudaMemsetAsync(c->d_node_row_off.as<uint32_t>() + c->node_end + 1, 0, 4 * (c->n_nodes - c->node_end), s));
+    }
+    c->outside_shard_clean = true;
+  }
+  // The staging capacity of the node kernel (candidates per node held in shared memory) comes from the previous run
+  // (default: what four CTAs per SM allow); the kernel flags nodes that do not fit and the run is repeated once with
+  // the exact size. No read-back, no host synchronisation until everything of this run is queued.
+  const bool fast_kernel = p.fast_forms && !p.use_endpoints_triangulation;
+  const size_t smem_limit = (size_t)std::max(0, c->max_smem_optin - 1024);
+  int cap = c->cap_hint > 0 ? c->cap_hint : 224;
+  if (exhaustive && c->cap_hint == 0) { // every node sees all lines of every neighbour: known on the host
+    int64_t mr = 0, cur = 0;
+    int cur_src = -1;
+    for (int i = 0; i < nb; ++i) {
+      if (blk[i].src_view != cur_src) { cur_src = blk[i].src_view; cur = 0; }
+      cur += c->line_off[blk[i].ng_view + 1] - c->line_off[blk[i].ng_view];
+      mr = std::max(mr, cur);
+    }
+    if (mr * ns > 65535) return fail(LM_ERR_INVALID, "more than 65535 candidates possible for one 2D line");
+    cap = 32;
+    while (cap < mr * ns) cap += 32;
+  }
+  while ((int)c->evk.size() < 2 * n_groups) {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    c->evk.push_back(e);
+  }
+  std::vector<int> group_has_kernel(n_groups, 0);
   for (int g = 0; g < n_groups; ++g) {
     // blocks [bg0, bg1) with whole source images, views [gv0, gv1)
     int bg1 = nb, gv1 = ve;
     if (g + 1 < n_groups) {
-      const int64_t target = n_rows * (g + 1) / n_groups;
+      // the first group is the smallest: it is the only one whose matches nothing else can hide
+      const int64_t target = (int64_t)((double)n_rows * std::pow((g + 1.0) / n_groups, 1.6));
       bg1 = bg0;
       while (bg1 < nb && row_off[bg1] < target) ++bg1;
       while (bg1 < nb && bg1 > 0 && blk[bg1].src_view == blk[bg1 - 1].src_view) ++bg1; // finish the image
@@ -866,13 +942,10 @@ int lm_tri_run(lm_ctx *c) {
     if (!exhaustive && re > rb) {
       int64_t need = 0;
       for (int b2 = bg0; b2 < bg1; ++b2) need = std::max(need, pair_off[b2] + blk[b2].n_rows);
-      size_t ci = 0;
-      for (const auto &ch : c->chunks) { // chunks complete in order: wait for the first one that covers `need`
+      for (const auto &ch : c->chunks) // chunks complete in order: wait for the first one that covers `need`
         if (ch.row_end >= need) { CU(cudaStreamWaitEvent(s, ch.ev, 0)); break; }
-        ++ci;
-      }
     }
-    lm::launch_zero_words(c->d_scalars.p, 2, s);
+    unsigned int *d_max_rows = c->d_scalars.as<unsigned int>() + 16 + g;
     if (re > rb) {
       if (exhaustive)
         lm::launch_expand_exhaustive(c->d_blk_row_off.as<int64_t>(), c->d_blk_src.as<int32_t>(), c->d_blk_ng.as<int32_t>(),
@@ -900,27 +973,11 @@ int lm_tri_run(lm_ctx *c) {
     lm::launch_node_offsets(c->sorted_key + rb, re - rb, rb, node_lo, node_hi, c->d_node_row_off.as<uint32_t>(),
                             d_max_rows, s);
     ++launches;
-    // the shared-memory staging area is sized from the largest node of the group (one 8-byte read-back)
-    unsigned int *hs = c->h_pin;
-    hs[0] = hs[1] = 0;
-    CU(cudaMemcpyAsync(hs, c->d_scalars.p, 8, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    if (hs[1] == 1)
-      return fail(LM_ERR_INVALID, "IndexError! Out-of-index matches exist (line_id >= number of lines of the image). "
-                                  "Please make sure you are reusing the correct descriptors and matches.");
-    if (hs[1] == 2) return fail(LM_ERR_INVALID, "IndexError! Out-of-index neighbor line id in matches.");
-    const int max_rows = (int)hs[0];
-    max_rows_all = std::max(max_rows_all, max_rows);
     p.node_begin = node_lo;
     p.node_end = node_hi;
     const int64_t n_group_nodes = node_hi - node_lo;
-    if ((int64_t)max_rows * ns > 65535) return fail(LM_ERR_INVALID, "more than 65535 candidates possible for one 2D line");
-    int cap = 32;
-    while (cap < max_rows * ns) cap += 32;
-    const bool fast_kernel = p.fast_forms && !p.use_endpoints_triangulation;
     size_t smem = lm::tri_smem_bytes(cap, fast_kernel);
     int grid;
-    const size_t smem_limit = (size_t)std::max(0, c->max_smem_optin - 1024);
     if (smem <= smem_limit) {
       p.use_slab = 0;
       p.cap = cap;
@@ -931,26 +988,20 @@ int lm_tri_run(lm_ctx *c) {
       p.cap = cap;
       grid = (int)std::min<int64_t>(n_group_nodes, (int64_t)c->sm_count * 4);
       p.slab_stride = (int64_t)((smem + 255) / 256 * 256);
-      CU(c->d_slab.ensure((size_t)p.slab_stride * grid));
+      CU(c->d_slab.ensure((size_t)p.slab_stride * std::max(grid, 1)));
       p.slab = c->d_slab.as<char>();
       smem = 0;
     }
-    CU(cudaEventRecord(c->evk0, s));
     if (n_group_nodes > 0) {
-      lm::launch_tri_node_kernel(p, grid, 128, smem, s);
+      CU(cudaEventRecord(c->evk[2 * g], s));
+      CU(lm::launch_tri_node_kernel(p, grid, 128, smem, s));
+      CU(cudaEventRecord(c->evk[2 * g + 1], s));
+      group_has_kernel[g] = 1;
       ++launches;
-    }
-    CU(cudaEventRecord(c->evk1, s));
-    if (n_group_nodes > 0) {
-      float msk = 0;
-      CU(cudaEventSynchronize(c->evk1));
-      CU(cudaEventElapsedTime(&msk, c->evk0, c->evk1));
-      c->node_kernel_ms_acc += msk;
     }
     bg0 = bg1;
     gv0 = gv1;
   }
-  c->stats.max_rows_per_node = max_rows_all;
   p.node_begin = c->node_begin;
   p.node_end = c->node_end;
   // valid_edges_ in compact form: per-node counts -> exclusive scan -> ordered scatter
@@ -971,6 +1022,9 @@ int lm_tri_run(lm_ctx *c) {
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev1, s));
+  // one read-back for the whole run: error / overflow flags, counters, largest node per group
+  unsigned int *hs = c->h_pin;
+  CU(cudaMemcpyAsync(hs, c->d_scalars.p, 512, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
 #ifdef LM_TRACE
   fprintf(stderr, "[lm trace] compute stream drained %.3f ms after run entry\n", lm_ms());
@@ -979,18 +1033,40 @@ int lm_tri_run(lm_ctx *c) {
 #ifdef LM_TRACE
   fprintf(stderr, "[lm trace] copy stream drained %.3f ms after run entry\n", lm_ms());
 #endif
+  c->stats.n_kernel_launches += launches;
+  if (hs[1] == 1)
+    return fail(LM_ERR_INVALID, "IndexError! Out-of-index matches exist (line_id >= number of lines of the image). "
+                                "Please make sure you are reusing the correct descriptors and matches.");
+  if (hs[1] == 2) return fail(LM_ERR_INVALID, "IndexError! Out-of-index neighbor line id in matches.");
+  int max_rows_all = 0;
+  for (int g = 0; g < n_groups; ++g) max_rows_all = std::max(max_rows_all, (int)hs[16 + g]);
+  if ((int64_t)max_rows_all * ns > 65535) return fail(LM_ERR_INVALID, "more than 65535 candidates possible for one 2D line");
+  int need_cap = 32;
+  while (need_cap < max_rows_all * ns) need_cap += 32;
+  c->cap_hint = need_cap;
+  if (hs[2] != 0) { // some node did not fit the staging area sized from the hint: repeat with the exact size
+    if (c->run_retry) { c->run_retry = 0; return fail(LM_ERR_STATE, "node staging overflow after resizing"); }
+    c->run_retry = 1;
+    const int rc2 = lm_tri_run(c);
+    c->run_retry = 0;
+    return rc2;
+  }
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  for (int g = 0; g < n_groups; ++g)
+    if (group_has_kernel[g]) {
+      float msk = 0;
+      CU(cudaEventElapsedTime(&msk, c->evk[2 * g], c->evk[2 * g + 1]));
+      c->node_kernel_ms_acc += msk;
+    }
+  c->stats.max_rows_per_node = max_rows_all;
   c->stats.last_node_kernel_ms = c->node_kernel_ms_acc;
-  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(c->h_pin + 8);
-  CU(cudaMemcpyAsync(cnt, d_counters, 32, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
+  const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(hs + 4);
   c->stats.n_rows = n_rows;
   c->stats.n_candidates = (int64_t)cnt[0];
   c->stats.n_valid_edges = (int64_t)cnt[1];
   c->stats.n_pairs_gated = (int64_t)cnt[2];
   c->stats.n_pairs_exact = (int64_t)cnt[3];
-  c->stats.n_kernel_launches += launches;
   c->stats.last_run_ms = ms;
   c->ran = true;
   return LM_OK;
@@ -1096,7 +1172,14 @@ int lm_tri_import_nodes(lm_ctx *c, int64_t b, int64_t e, const void *d_in) {
 }
 
 static int collect_edges(lm_ctx *c) {
-  if (c->edges_collected) return LM_OK;
+  if (c->edges_collected) {
+    if (c->edges_count_on_device) {
+      const int64_t over = lm_tri_gather_status(c, nullptr);
+      if (over < 0) return (int)over;
+      if (over) return fail(LM_ERR_STATE, "the last multi-GPU exchange overflowed its edge capacity: repeat it with a larger message");
+    }
+    return LM_OK;
+  }
   const int64_t ne = c->stats.n_valid_edges;
   CU(c->d_edges.ensure(16 * std::max<int64_t>(ne, 1)));
   lm::launch_edge_pairs(c->d_edge_off.as<uint32_t>(), c->d_edge_ng.as<uint32_t>(), c->d_line_off.as<int64_t>(),
@@ -1137,6 +1220,67 @@ int lm_tri_import_edges(lm_ctx *c, int64_t n, const void *d_in, int32_t append) 
   c->n_edges_dev = base + n;
   c->edges_collected = true;
   return LM_OK;
+}
+
+int64_t lm_tri_gather_message_bytes(int64_t max_nodes, int64_t cap_edges) {
+  if (max_nodes < 0 || cap_edges < 0) return fail(LM_ERR_INVALID, "bad sizes");
+  return (16 + max_nodes * (int64_t)sizeof(lm::NodeRecord) + cap_edges * 8 + 15) / 16 * 16;
+}
+int lm_tri_pack_message(lm_ctx *c, int64_t max_nodes, int64_t cap_edges, void *d_msg) {
+  if (!c || !d_msg) return fail(LM_ERR_INVALID, "NULL argument");
+  int rc = ensure_ran(c);
+  if (rc) return rc;
+  const int64_t n = c->node_end - c->node_begin;
+  if (n > max_nodes) return fail(LM_ERR_INVALID, "shard has more nodes than the message holds");
+  lm::launch_gather_pack(c->d_nodes.as<lm::NodeRecord>(), c->node_begin, n, max_nodes, c->d_edge_off.as<uint32_t>(),
+                         c->d_edge_ng.as<uint32_t>(), c->d_line_off.as<int64_t>(), cap_edges, static_cast<char *>(d_msg),
+                         c->stream);
+  CU(cudaGetLastError());
+  c->stats.n_kernel_launches += 1;
+  return LM_OK;
+}
+int lm_tri_unpack_messages(lm_ctx *c, int32_t world, const int64_t *rank_node_begin, int64_t max_nodes, int64_t cap_edges,
+                           const void *d_msgs) {
+  if (!c || !d_msgs || !rank_node_begin || world <= 0 || world > 64) return fail(LM_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(c->device));
+  for (int r = 0; r < world; ++r)
+    if (rank_node_begin[r] < 0 || rank_node_begin[r] > c->n_nodes) return fail(LM_ERR_INVALID, "bad node range");
+  CU(c->d_nodes.ensure(sizeof(lm::NodeRecord) * std::max<int64_t>(c->n_nodes, 1)));
+  if ((size_t)world * cap_edges * 16 + 16 > c->d_edges.cap) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(c->d_edges.ensure((size_t)world * cap_edges * 16 + 16));
+  }
+  CU(c->d_gather.ensure(8 * 64 + 64));
+  // rank table as kernel-readable memory: tiny, written through pinned memory on the compute stream's own order
+  int64_t *h = reinterpret_cast<int64_t *>(c->h_pin + 128); // bytes 512.. of the pinned pad
+  for (int r = 0; r < world; ++r) h[r] = rank_node_begin[r];
+  if (memcmp(c->gather_tab, h, 8 * world) != 0 || c->gather_world != world) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyAsync(c->d_gather.as<char>() + 64, h, 8 * world, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    memcpy(c->gather_tab, h, 8 * world);
+    c->gather_world = world;
+  }
+  lm::launch_gather_unpack(static_cast<const char *>(d_msgs), world, reinterpret_cast<const int64_t *>(c->d_gather.as<char>() + 64),
+                           max_nodes, cap_edges, lm_tri_gather_message_bytes(max_nodes, cap_edges),
+                           c->d_nodes.as<lm::NodeRecord>(), c->d_edges.as<int64_t>(), c->d_gather.as<int64_t>(), c->stream);
+  CU(cudaGetLastError());
+  c->stats.n_kernel_launches += 1;
+  c->h_nodes_valid = false;
+  c->edges_collected = true;
+  c->edges_count_on_device = true;
+  return LM_OK;
+}
+int64_t lm_tri_gather_status(lm_ctx *c, int64_t *n_edges_total) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  if (!c->edges_count_on_device) { if (n_edges_total) *n_edges_total = c->n_edges_dev; return 0; }
+  int64_t *h = reinterpret_cast<int64_t *>(c->h_pin + 256);
+  CU(cudaMemcpyAsync(h, c->d_gather.p, 16, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->n_edges_dev = h[0];
+  c->edges_count_on_device = false;
+  if (n_edges_total) *n_edges_total = h[0];
+  return h[1]; // 1: some rank had more valid connections than cap_edges -- repeat the exchange with a larger message
 }
 
 // ---- ComputeLineTracks ---------------------------------------------------------------------------
@@ -1712,6 +1856,16 @@ extern "C" {
 
 int64_t lm_vp_detect(lm_ctx *c, int32_t n_images, const int64_t *line_off, const double *segs, const lm_vp_config *cfg,
                      int32_t *labels, int64_t *vp_off, double *vps, int64_t vp_cap) {
+  return lm_vp_detect_indexed(c, n_images, line_off, segs, cfg, nullptr, labels, vp_off, vps, vp_cap);
+}
+int lm_vp_get_stats(lm_ctx *c, lm_vp_stats *out) {
+  if (!c || !out) return fail(LM_ERR_INVALID, "NULL argument");
+  *out = c->vp_stats;
+  return LM_OK;
+}
+int64_t lm_vp_detect_indexed(lm_ctx *c, int32_t n_images, const int64_t *line_off, const double *segs,
+                             const lm_vp_config *cfg, const int64_t *image_index, int32_t *labels, int64_t *vp_off,
+                             double *vps, int64_t vp_cap) {
   if (!c || !cfg || !line_off || !labels || !vp_off) return fail(LM_ERR_INVALID, "NULL argument");
   if (n_images < 0) return fail(LM_ERR_INVALID, "bad sizes");
   if (cfg->n_models <= 0 || cfg->n_models > 65535) return fail(LM_ERR_INVALID, "n_models must be in [1, 65535]");
@@ -1737,6 +1891,7 @@ int64_t lm_vp_detect(lm_ctx *c, int32_t n_images, const int64_t *line_off, const
   const int64_t nv = (int64_t)valid_ids.size();
   std::vector<int32_t> raw(std::max<int64_t>(nv, 1), -1), ncl(std::max(n_images, 1), 0);
   const int min_lines = 2 * std::max(cfg->min_num_supports, 10);
+  bool vp_kernel_ran = false;
   if (nv > 0 && max_n >= min_lines) {
     const int W = (cfg->n_models + 31) / 32;
     int grid = std::min(n_images, c->sm_count * 2);
@@ -1746,11 +1901,14 @@ int64_t lm_vp_detect(lm_ctx *c, int32_t n_images, const int64_t *line_off, const
     CU(c->d_vp_nc.ensure(4 * n_images));
     CU(c->d_vp_ps.ensure((size_t)grid * max_n * W * 4));
     CU(c->d_vp_mat.ensure((size_t)grid * max_n * max_n * 4));
+    CU(c->d_vp_idx.ensure(8 * std::max(n_images, 1)));
     CU(cudaMemcpyAsync(c->d_vp_pts.p, pts.data(), 16 * nv, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(c->d_vp_off.p, valid_off.data(), 8 * (n_images + 1), cudaMemcpyHostToDevice, s));
+    if (image_index) CU(cudaMemcpyAsync(c->d_vp_idx.p, image_index, 8 * n_images, cudaMemcpyHostToDevice, s));
     lm::VPParams p;
     p.pts = c->d_vp_pts.as<float4>();
     p.valid_off = c->d_vp_off.as<int64_t>();
+    p.image_index = image_index ? c->d_vp_idx.as<int64_t>() : nullptr;
     p.labels = c->d_vp_labels.as<int32_t>();
     p.n_clusters = c->d_vp_nc.as<int32_t>();
     p.ps_slab = c->d_vp_ps.as<uint32_t>();
@@ -1760,8 +1918,11 @@ int64_t lm_vp_detect(lm_ctx *c, int32_t n_images, const int64_t *line_off, const
     p.seed = cfg->seed;
     if (lm::vp_smem_bytes(p.n_models, p.max_n) > (size_t)c->max_smem_optin)
       return fail(LM_ERR_INVALID, "n_models too large for shared memory");
+    CU(cudaEventRecord(c->evk0, s));
     lm::launch_jlinkage(p, grid, s);
+    CU(cudaEventRecord(c->evk1, s));
     CU(cudaGetLastError());
+    vp_kernel_ran = true;
     c->stats.n_kernel_launches += 1;
     CU(cudaMemcpyAsync(raw.data(), c->d_vp_labels.p, 4 * nv, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(ncl.data(), c->d_vp_nc.p, 4 * n_images, cudaMemcpyDeviceToHost, s));
@@ -1809,6 +1970,11 @@ int64_t lm_vp_detect(lm_ctx *c, int32_t n_images, const int64_t *line_off, const
     }
   }
   vp_off[n_images] = n_vps;
+  c->vp_stats.n_images = n_images;
+  c->vp_stats.n_segments = nv;
+  c->vp_stats.n_vps = n_vps;
+  c->vp_stats.kernel_ms = 0;
+  if (vp_kernel_ran) { float ms = 0; CU(cudaEventElapsedTime(&ms, c->evk0, c->evk1)); c->vp_stats.kernel_ms = ms; }
   return n_vps;
 }
 

@@ -539,9 +539,10 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
     const uint32_t r0 = p.node_row_off[node], r1 = p.node_row_off[node + 1];
     const int nrows = (int)(r1 - r0);
     NodeRecord *rec = &p.nodes[node];
-    if (nrows == 0) {
+    if (nrows == 0 || nrows * NS > p.cap) {
       if (tid < 9) rec->line[tid] = (tid == 8) ? -1.0 : 0.0;
       if (tid == 9) { rec->score = 0.0; rec->ng_view = 0; rec->ng_line = 0; rec->n_cand = 0; rec->n_valid = 0; }
+      if (nrows != 0 && tid == 10) *p.overflow = 1; // staging area sized from a stale hint: the host repeats the run
       continue;
     }
     // ---------------- phase A: candidate generation with stable compaction -----------------
@@ -865,23 +866,24 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
   }
 }
 
-template <bool VP, bool FAST> static void launch_tri_vf(const TriParams &p, int grid, size_t smem, cudaStream_t s) {
-  static size_t configured = 0;
+template <bool VP, bool FAST> static cudaError_t launch_tri_vf(const TriParams &p, int grid, size_t smem, cudaStream_t s) {
   if (p.use_slab) {
     tri_node_kernel<true, VP, FAST><<<grid, kThreads, 0, s>>>(p);
-    return;
+    return cudaGetLastError();
   }
-  if (smem > configured) {
-    cudaFuncSetAttribute(tri_node_kernel<false, VP, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
+  // the opt-in is per device (and per function): set it on every launch above the default limit
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(tri_node_kernel<false, VP, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
   }
   tri_node_kernel<false, VP, FAST><<<grid, kThreads, smem, s>>>(p);
+  return cudaGetLastError();
 }
-void launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem, cudaStream_t s) {
+cudaError_t launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem, cudaStream_t s) {
   (void)block;
   const bool fast = p.fast_forms && !p.use_endpoints_triangulation;
-  if (p.use_vp) { if (fast) launch_tri_vf<true, true>(p, grid, smem, s); else launch_tri_vf<true, false>(p, grid, smem, s); }
-  else { if (fast) launch_tri_vf<false, true>(p, grid, smem, s); else launch_tri_vf<false, false>(p, grid, smem, s); }
+  if (p.use_vp) return fast ? launch_tri_vf<true, true>(p, grid, smem, s) : launch_tri_vf<true, false>(p, grid, smem, s);
+  return fast ? launch_tri_vf<false, true>(p, grid, smem, s) : launch_tri_vf<false, false>(p, grid, smem, s);
 }
 
 // The per-run block tables (match tables ordered by (source view, neighbour), row offsets) are derived on the
@@ -1106,6 +1108,69 @@ void launch_edges_for_host(const uint32_t *edge_off, const uint32_t *edge_ng, co
   const int64_t n = (n_edges > n_nodes_total + 1) ? n_edges : n_nodes_total + 1;
   edges_for_host_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(edge_off, edge_ng, img_ids, n_nodes_shard, n_edges,
                                                                node_begin, n_nodes_total, node_off, pairs);
+}
+
+// ---- multi-GPU exchange: one fixed-size message per rank ("one all-gather of per-node results") ----
+// message = [int64 n_edges, int64 n_nodes] | NodeRecord[max_nodes] | (uint32 src_node, uint32 dst_node)[cap_edges]
+__global__ void gather_pack_kernel(const NodeRecord *__restrict__ nodes, int64_t node_begin, int64_t n_nodes,
+                                   int64_t max_nodes, const uint32_t *__restrict__ edge_off,
+                                   const uint32_t *__restrict__ edge_ng, const int64_t *__restrict__ line_off,
+                                   int64_t cap_edges, char *__restrict__ msg) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t ne = n_nodes > 0 ? (int64_t)edge_off[n_nodes] : 0;
+  if (tid == 0) { reinterpret_cast<int64_t *>(msg)[0] = ne; reinterpret_cast<int64_t *>(msg)[1] = n_nodes; }
+  const uint4 *src = reinterpret_cast<const uint4 *>(nodes + node_begin);
+  uint4 *dst = reinterpret_cast<uint4 *>(msg + 16);
+  const int64_t nv = n_nodes * (int64_t)(sizeof(NodeRecord) / 16);
+  for (int64_t i = tid; i < nv; i += nth) dst[i] = src[i];
+  uint2 *ed = reinterpret_cast<uint2 *>(msg + 16 + max_nodes * (int64_t)sizeof(NodeRecord));
+  const int64_t nc = ne < cap_edges ? ne : cap_edges;
+  for (int64_t e = tid; e < nc; e += nth) {
+    int64_t lo = 0, hi = n_nodes; // largest i with edge_off[i] <= e
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (edge_off[mid] <= (uint32_t)e) lo = mid; else hi = mid;
+    }
+    const uint32_t ng = edge_ng[e];
+    ed[e] = make_uint2((uint32_t)(node_begin + lo), (uint32_t)(line_off[ng >> 16] + (ng & 0xffffu)));
+  }
+}
+// all ranks' messages -> node records in place, directed edges appended in rank order as int64 pairs;
+// scal[0] = total edges, scal[1] = 1 when some rank had more edges than the message holds
+__global__ void gather_unpack_kernel(const char *__restrict__ msgs, int world, const int64_t *__restrict__ rank_node_begin,
+                                     int64_t max_nodes, int64_t cap_edges, int64_t msg_bytes,
+                                     NodeRecord *__restrict__ nodes, int64_t *__restrict__ edges,
+                                     int64_t *__restrict__ scal) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  int64_t ebase = 0;
+  bool over = false;
+  for (int r = 0; r < world; ++r) {
+    const char *m = msgs + r * msg_bytes;
+    int64_t ne = reinterpret_cast<const int64_t *>(m)[0];
+    const int64_t nn = reinterpret_cast<const int64_t *>(m)[1];
+    if (ne > cap_edges) { over = true; ne = cap_edges; }
+    const uint4 *src = reinterpret_cast<const uint4 *>(m + 16);
+    uint4 *dst = reinterpret_cast<uint4 *>(nodes + rank_node_begin[r]);
+    const int64_t nv = nn * (int64_t)(sizeof(NodeRecord) / 16);
+    for (int64_t i = tid; i < nv; i += nth) dst[i] = src[i];
+    const uint2 *ed = reinterpret_cast<const uint2 *>(m + 16 + max_nodes * (int64_t)sizeof(NodeRecord));
+    for (int64_t e = tid; e < ne; e += nth) {
+      const uint2 v = ed[e];
+      edges[2 * (ebase + e)] = (int64_t)v.x;
+      edges[2 * (ebase + e) + 1] = (int64_t)v.y;
+    }
+    ebase += ne;
+  }
+  if (tid == 0) { scal[0] = ebase; scal[1] = over ? 1 : 0; }
+}
+void launch_gather_pack(const NodeRecord *nodes, int64_t node_begin, int64_t n_nodes, int64_t max_nodes,
+                        const uint32_t *edge_off, const uint32_t *edge_ng, const int64_t *line_off, int64_t cap_edges,
+                        char *msg, cudaStream_t s) {
+  gather_pack_kernel<<<148 * 4, 256, 0, s>>>(nodes, node_begin, n_nodes, max_nodes, edge_off, edge_ng, line_off, cap_edges, msg);
+}
+void launch_gather_unpack(const char *msgs, int world, const int64_t *rank_node_begin, int64_t max_nodes, int64_t cap_edges,
+                          int64_t msg_bytes, NodeRecord *nodes, int64_t *edges, int64_t *scal, cudaStream_t s) {
+  gather_unpack_kernel<<<148 * 4, 256, 0, s>>>(msgs, world, rank_node_begin, max_nodes, cap_edges, msg_bytes, nodes, edges, scal);
 }
 
 // run_clustering edge weight (global_line_triangulator.cc:263-288): LineLinker3d::compute_score of the

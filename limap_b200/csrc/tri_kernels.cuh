@@ -41,6 +41,7 @@ struct TriParams {
   uint8_t *row_state;          // [rows][ns] out: 0 rejected, 1 candidate, 2 valid connection (ns = 3 with VPs)
   double *row_cand;            // [rows][ns][10] out (debug_mode only, else NULL)
   unsigned long long *counters; // [4] n_candidates, n_valid, pairs past the 3d gates, pairs scored exactly
+  int *overflow;               // set when a node has more candidate slots than `cap` (the host re-runs with the exact size)
   char *slab;                  // global scratch for nodes whose rows exceed the smem capacity (or NULL)
   int64_t slab_stride;         // bytes per CTA
   int64_t node_begin, node_end;
@@ -77,7 +78,7 @@ struct EdgeParams {
 };
 
 size_t tri_smem_bytes(int cap, bool fast);
-void launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem, cudaStream_t s);
+cudaError_t launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem, cudaStream_t s);
 void launch_expand_rows(const int32_t *d_pairs, const int64_t *d_blk_row_off, const int32_t *d_blk_src_view,
                         const int32_t *d_blk_ng_view, const int64_t *d_blk_pair_off, int n_blocks,
                         const int64_t *d_line_off, int64_t r_begin, int64_t r_end, uint32_t *d_key, uint32_t *d_val,
@@ -109,5 +110,10 @@ void launch_block_keys(const RawBlock *raw, int n_all, int vb, int ve, int exhau
 void launch_block_gather(const RawBlock *raw, const uint32_t *sorted_idx, int nb, int32_t *blk_src, int32_t *blk_ng,
                          int64_t *blk_pair_off, int64_t *blk_rows, cudaStream_t s);
 void launch_edge_weights(const EdgeParams &p, cudaStream_t s);
+void launch_gather_pack(const NodeRecord *nodes, int64_t node_begin, int64_t n_nodes, int64_t max_nodes,
+                        const uint32_t *edge_off, const uint32_t *edge_ng, const int64_t *line_off, int64_t cap_edges,
+                        char *msg, cudaStream_t s);
+void launch_gather_unpack(const char *msgs, int world, const int64_t *rank_node_begin, int64_t max_nodes, int64_t cap_edges,
+                          int64_t msg_bytes, NodeRecord *nodes, int64_t *edges, int64_t *scal, cudaStream_t s);
 
 } // namespace lm

@@ -85,8 +85,9 @@ __global__ void __launch_bounds__(256) jlinkage_kernel(const __grid_constant__ V
       continue;
     }
     // stage 1: models
+    const uint64_t gim = p.image_index ? (uint64_t)p.image_index[im] : (uint64_t)im;
     for (int m = tid; m < p.n_models; m += blockDim.x) {
-      const uint64_t z = splitmix64(p.seed, (uint64_t)im * (uint64_t)p.n_models + (uint64_t)m);
+      const uint64_t z = splitmix64(p.seed, gim * (uint64_t)p.n_models + (uint64_t)m);
       int i = (int)((uint32_t)(z & 0xffffffffu) % (uint32_t)n);
       int j = (int)((uint32_t)(z >> 32) % (uint32_t)(n - 1));
       if (j >= i) ++j;
@@ -195,11 +196,8 @@ size_t vp_smem_bytes(int n_models, int max_n) { return (size_t)n_models * sizeof
 
 void launch_jlinkage(const VPParams &p, int grid, cudaStream_t s) {
   const size_t smem = vp_smem_bytes(p.n_models, p.max_n);
-  static size_t configured = 0;
-  if (smem > configured) {
+  if (smem > 48 * 1024) // per device: set on every launch above the default limit
     cudaFuncSetAttribute(jlinkage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
   jlinkage_kernel<<<grid, 256, smem, s>>>(p);
 }
 

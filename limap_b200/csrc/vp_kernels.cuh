@@ -7,6 +7,7 @@ namespace lm {
 struct VPParams {
   const float4 *pts;        // [sum n] valid segments (x1,y1,x2,y2) as float
   const int64_t *valid_off; // [n_images+1]
+  const int64_t *image_index; // [n_images] index seeding the hypotheses of each image, or NULL (= position in the call)
   int32_t *labels;          // [sum n] out: raw cluster id of every valid segment
   int32_t *n_clusters;      // [n_images] out
   uint32_t *ps_slab;        // [grid][max_n][W] preference bit matrices

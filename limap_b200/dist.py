@@ -49,51 +49,70 @@ def all_gather_padded(t, group=None):
 
 
 class NodeGather:
-    """All-gather of the per-node records (96 B each) and of the valid-connection pairs of every rank's
-    shard, imported into the local engine so that ComputeLineTracks can run replicated (or on rank 0)."""
+    """Exchange of every rank's per-node results (96-byte node records + valid connections) so that ComputeLineTracks
+    can run replicated (or on rank 0): pack (one kernel) -> ONE all_gather_into_tensor of a fixed-size message ->
+    unpack (one kernel). The message capacity for valid connections is agreed once (a counts all-reduce on the first
+    call, with head-room) and reused; steady-state calls do not synchronise the host. `check()` (called by
+    lm_tri_build_tracks too) reports an overflow, in which case the exchange is repeated with a larger message."""
 
-    def __init__(self, eng, world, rank, shards=None):
+    def __init__(self, eng, world, rank, shards=None, group=None):
         import torch
-        from ._cabi import NODE_RECORD_DTYPE, lib
-        self.eng, self.world, self.rank = eng, world, rank
+        from ._cabi import lib
+        self.eng, self.world, self.rank, self.group = eng, world, rank, group
         self.lib = lib()
+        # pack / unpack kernels are enqueued on the engine's stream and the collective on torch's current stream:
+        # make them the same stream so that stream order is the only synchronisation needed
+        eng.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         V = len(eng.img_ids)
         if shards is None:
             per = V // world
             shards = [(r * per, (r + 1) * per if r < world - 1 else V) for r in range(world)]
         self.shards = shards
         self.node_rng = [(int(eng.line_off[b]), int(eng.line_off[e])) for b, e in shards]
-        self.rec = NODE_RECORD_DTYPE.itemsize
+        self.node_begin = np.ascontiguousarray([b for b, _ in self.node_rng], np.int64)
         self.max_nodes = max(e - b for b, e in self.node_rng)
-        self.send = torch.zeros(self.max_nodes * self.rec, dtype=torch.uint8, device="cuda")
-        self.recv = torch.zeros(world * self.max_nodes * self.rec, dtype=torch.uint8, device="cuda")
+        self.cap_edges = 0
+        self.send = self.recv = None
 
-    def all_gather(self, with_edges=True):
+    def _size(self, cap_edges):
         import torch
+        self.cap_edges = int(cap_edges)
+        self.msg_bytes = int(self.lib.lm_tri_gather_message_bytes(self.max_nodes, self.cap_edges))
+        self.send = torch.zeros(self.msg_bytes, dtype=torch.uint8, device="cuda")
+        self.recv = torch.zeros(self.world * self.msg_bytes, dtype=torch.uint8, device="cuda")
+
+    def _agree_capacity(self):
+        """Largest valid-connection count over ranks (one tiny all-reduce + host read, first call only)."""
+        import torch
+        import torch.distributed as dist
+        n = int(self.eng.stats()["n_valid_edges"])
+        t = torch.tensor([n], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
+    def all_gather(self):
         import torch.distributed as dist
         from ._cabi import check
         h = self.eng.ctx.handle
-        b, e = self.node_rng[self.rank]
-        check(self.lib.lm_tri_export_nodes(h, b, e, C.c_void_p(self.send.data_ptr())))
-        dist.all_gather_into_tensor(self.recv, self.send)
-        for r in range(self.world):
-            if r == self.rank:
-                continue
-            rb, re_ = self.node_rng[r]
-            off = r * self.max_nodes * self.rec
-            check(self.lib.lm_tri_import_nodes(h, rb, re_, C.c_void_p(self.recv.data_ptr() + off)))
-        if with_edges:
-            n = check(self.lib.lm_tri_num_valid_edges(h))
-            mine = torch.empty(max(2 * n, 1), dtype=torch.int64, device="cuda")
-            if n:
-                check(self.lib.lm_tri_export_edges(h, C.c_void_p(mine.data_ptr())))
-            parts = all_gather_padded(mine[: 2 * n])
-            for r, p in enumerate(parts):
-                if r == self.rank or p.numel() == 0:
-                    continue
-                p = p.contiguous()
-                check(self.lib.lm_tri_import_edges(h, p.numel() // 2, C.c_void_p(p.data_ptr()), 1))
-        torch.cuda.current_stream().synchronize()
+        if self.send is None:
+            self._size(max(1024, int(self._agree_capacity() * 1.25) + 1024))
+        check(self.lib.lm_tri_pack_message(h, self.max_nodes, self.cap_edges, C.c_void_p(self.send.data_ptr())))
+        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        check(self.lib.lm_tri_unpack_messages(h, self.world, self.node_begin.ctypes.data_as(C.c_void_p), self.max_nodes,
+                                              self.cap_edges, C.c_void_p(self.recv.data_ptr())))
+
+    def check(self):
+        """Synchronise; if some rank held more valid connections than the message capacity, grow it and repeat the
+        exchange. Returns the number of directed valid connections now held by the engine."""
+        from ._cabi import check
+        tot = C.c_int64(0)
+        over = check(self.lib.lm_tri_gather_status(self.eng.ctx.handle, C.byref(tot)))
+        if over:
+            self._size(max(self.cap_edges * 2, int(self._agree_capacity() * 1.25) + 1024))
+            self.all_gather()
+            over = check(self.lib.lm_tri_gather_status(self.eng.ctx.handle, C.byref(tot)))
+            assert not over
+        return int(tot.value)
 
 
 # ---- track-sharded stages (SURVEY.md §8e: LM refinement with constant cameras, J-Linkage per image) -------------
@@ -152,3 +171,34 @@ def solve_line_ba_sharded(solve, kvec, qvec, tvec, sup_off, sup_view, segs, line
         np.zeros((0, 10))
     full = gather_rows(mine, torch.as_tensor(table, dtype=torch.float64, device=device), T, group).cpu().numpy()
     return dict(line=full[:, :6], iters=full[:, 6:8].astype(np.int32), cost=full[:, 8:10])
+
+
+def detect_vps_sharded(detect_batch, segs_list, rank, world, group=None, device="cuda"):
+    """J-Linkage over the images of a scene, sharded per image (vplib/base_vp_detector.py:46-78 fans images out with
+    joblib): images are dealt by segment count, every rank clusters its share with `detect_batch(images,
+    image_index=...)` -- the index seeds each image's hypotheses, so the labels are those of the single-rank call --
+    and labels + VPs are all-gathered. Returns (labels[n_images] int32 arrays, vps[n_images] (k,3) arrays) on every rank."""
+    import torch
+    n = len(segs_list)
+    counts = np.asarray([len(s) for s in segs_list], np.int64)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    mine = partition_by_cost(counts, world)[rank]
+    res = detect_batch([segs_list[i] for i in mine], image_index=mine) if len(mine) else []
+    lab = np.concatenate([np.asarray(r.labels, np.int64) for r in res]) if len(res) else np.zeros(0, np.int64)
+    nv = np.asarray([len(np.asarray(r.vps).reshape(-1, 3)) for r in res], np.int64)
+    vps = np.concatenate([np.asarray(r.vps, np.float64).reshape(-1, 3) for r in res]) if len(res) else np.zeros((0, 3))
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=device)
+    parts_i = all_gather_padded(t(mine, torch.int64), group)
+    parts_l = all_gather_padded(t(lab, torch.int64), group)
+    parts_n = all_gather_padded(t(nv, torch.int64), group)
+    parts_v = all_gather_padded(t(vps.reshape(-1), torch.float64), group)
+    labels, out_vps = [None] * n, [None] * n
+    for pi, pl, pn, pv in zip(parts_i, parts_l, parts_n, parts_v):
+        pi, pl, pn, pv = pi.cpu().numpy(), pl.cpu().numpy(), pn.cpu().numpy(), pv.cpu().numpy().reshape(-1, 3)
+        lo = vo = 0
+        for k, i in enumerate(pi):
+            labels[i] = pl[lo:lo + counts[i]].astype(np.int32)
+            out_vps[i] = pv[vo:vo + pn[k]].copy()
+            lo += counts[i]
+            vo += pn[k]
+    return labels, out_vps

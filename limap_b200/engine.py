@@ -145,10 +145,15 @@ class TriEngine:
         """(node_off[n_nodes+1], edges[n,2] = (ng_img_id, ng_line_id)); pass preallocated (pinned) arrays to
         avoid staging copies."""
         n = int(self.line_off[-1])
-        ne = int(self.ctx.stats()["n_valid_edges"])
+        # the count call runs the pending work first (ensure_ran), so `ne` is never stale
+        ne = int(check(lib().lm_tri_get_all_valid_edges(self.ctx.handle, None, None)))
+        if edges is not None and len(edges) < ne:
+            raise ValueError(f"edges buffer holds {len(edges)} rows, {ne} valid connections to return")
+        if off is not None and len(off) < n + 1:
+            raise ValueError(f"off buffer holds {len(off)} entries, {n + 1} needed")
         if off is None:
             off = np.zeros(n + 1, np.int64)
-        if edges is None or len(edges) < ne:
+        if edges is None:
             edges = np.zeros((max(ne, 1), 2), np.int32)
         check(lib().lm_tri_get_all_valid_edges(self.ctx.handle, ptr(off), ptr(edges)))
         return off, edges[:ne]

@@ -88,7 +88,7 @@ def _rot_to_quat(R):
 
 
 def make_scene(V=10, L=100, N=5, K=4, seed=1234, scale=1.0, noise_px=0.5, G=None, id_stride=1,
-               width=800, height=600, focal=692.82, shuffle_rows=False, match_views=None):
+               width=800, height=600, focal=692.82, shuffle_rows=False, match_views=None, camera_mix=False):
     rng = np.random.default_rng(seed)
     G = int(L * 1.3) if G is None else G
     # ground-truth 3D segments
@@ -105,6 +105,14 @@ def make_scene(V=10, L=100, N=5, K=4, seed=1234, scale=1.0, noise_px=0.5, G=None
     rad = 12.0 * scale * rng.uniform(0.95, 1.05, V)
     Cs = np.stack([rad * np.cos(el) * np.cos(az), rad * np.cos(el) * np.sin(az), rad * np.sin(el)], 1)
     kvec = np.tile(np.array([focal, focal, width / 2.0, height / 2.0]), (V, 1))
+    model_ids = np.zeros(V, np.int32)
+    if camera_mix:
+        # one camera per view: odd views PINHOLE with fx != fy, even views SIMPLE_PINHOLE, principal points off-centre
+        crng = np.random.default_rng(seed + 7919)
+        fx = focal * crng.uniform(0.85, 1.15, V)
+        fy = np.where(np.arange(V) % 2 == 1, fx * crng.uniform(0.9, 1.1, V), fx)
+        kvec = np.stack([fx, fy, width / 2.0 + crng.uniform(-20, 20, V), height / 2.0 + crng.uniform(-20, 20, V)], 1)
+        model_ids = (np.arange(V) % 2).astype(np.int32)
     qvec = np.zeros((V, 4))
     tvec = np.zeros((V, 3))
     Rs = np.zeros((V, 3, 3))
@@ -127,8 +135,8 @@ def make_scene(V=10, L=100, N=5, K=4, seed=1234, scale=1.0, noise_px=0.5, G=None
         Xc0 = P0 @ R.T + t
         Xc1 = P1 @ R.T + t
         ok = (Xc0[:, 2] > 0.5 * scale) & (Xc1[:, 2] > 0.5 * scale)
-        p0 = Xc0[:, :2] / Xc0[:, 2:3] * focal + kvec[v, 2:4]
-        p1 = Xc1[:, :2] / Xc1[:, 2:3] * focal + kvec[v, 2:4]
+        p0 = Xc0[:, :2] / Xc0[:, 2:3] * kvec[v, 0:2] + kvec[v, 2:4]
+        p1 = Xc1[:, :2] / Xc1[:, 2:3] * kvec[v, 0:2] + kvec[v, 2:4]
         inside = lambda p: (p[:, 0] >= 0) & (p[:, 0] <= width) & (p[:, 1] >= 0) & (p[:, 1] <= height)
         ok &= inside(p0) & inside(p1) & (np.linalg.norm(p1 - p0, axis=1) > 8.0)
         vis = np.flatnonzero(ok)
@@ -198,11 +206,39 @@ def make_scene(V=10, L=100, N=5, K=4, seed=1234, scale=1.0, noise_px=0.5, G=None
         matches[int(img_ids[v])] = mv
     lo = np.array([-5.0, -5.0, -5.0]) * scale * 1.25
     hi = np.array([5.0, 5.0, 5.0]) * scale * 1.25
-    return Scene(img_ids=img_ids, model_ids=np.zeros(V, np.int32), kvec=np.ascontiguousarray(kvec),
+    return Scene(img_ids=img_ids, model_ids=model_ids, kvec=np.ascontiguousarray(kvec),
                  qvec=np.ascontiguousarray(qvec), tvec=np.ascontiguousarray(tvec), line_off=line_off,
                  segs=segs, gt_id=gt_id, neighbors=neighbors, matches=matches, ranges=(lo, hi),
                  gt_lines=gt_lines, meta=dict(V=V, L=L, N=N, K=K, seed=seed, scale=scale,
                                               noise_px=noise_px))
+
+
+def concat_scenes(scenes):
+    """One scene out of several independent blocks: views, lines and matches of block b keep their content and get
+    image ids offset by the views of the blocks before it (neighbours stay inside a block). Used for equal-work weak
+    scaling: N blocks of the same shape = N times the work of one block, one block per GPU."""
+    img_ids, model_ids, kvec, qvec, tvec, segs, gt_id, line_off = [], [], [], [], [], [], [], [0]
+    neighbors, matches = {}, {}
+    lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+    id0 = 0
+    for sc in scenes:
+        ids = sc.img_ids.astype(np.int64) + id0
+        img_ids.append(ids.astype(np.int32))
+        model_ids.append(sc.model_ids); kvec.append(sc.kvec); qvec.append(sc.qvec); tvec.append(sc.tvec)
+        segs.append(sc.segs); gt_id.append(sc.gt_id)
+        line_off.extend((sc.line_off[1:] + line_off[-1]).tolist())
+        for i, nb in sc.neighbors.items():
+            neighbors[int(i) + id0] = [int(j) + id0 for j in nb]
+        for i, m in sc.matches.items():
+            matches[int(i) + id0] = {int(g) + id0: v for g, v in m.items()}
+        lo, hi = np.minimum(lo, sc.ranges[0]), np.maximum(hi, sc.ranges[1])
+        id0 = int(ids[-1]) + 1
+    return Scene(img_ids=np.concatenate(img_ids), model_ids=np.concatenate(model_ids),
+                 kvec=np.ascontiguousarray(np.concatenate(kvec)), qvec=np.ascontiguousarray(np.concatenate(qvec)),
+                 tvec=np.ascontiguousarray(np.concatenate(tvec)), line_off=np.asarray(line_off, np.int64),
+                 segs=np.ascontiguousarray(np.concatenate(segs)), gt_id=np.concatenate(gt_id), neighbors=neighbors,
+                 matches=matches, ranges=(lo, hi), gt_lines=None,
+                 meta=dict(blocks=[sc.meta for sc in scenes]))
 
 
 # BASELINE.json `configs` -> generator arguments (SURVEY.md §8d)
@@ -301,3 +337,33 @@ def make_track_lines(T, dup_frac=0.3, seed=0, extent=20.0, unc=0.05, noise=0.002
         D[:, 6] = unc * rng.uniform(0.5, 2.0, n_dup)
         L = np.concatenate([L, D])
     return np.ascontiguousarray(L[rng.permutation(T)])
+
+
+def make_vp_images(n_images, n_segments=300, seed=0, width=800, height=600, noise=0.3, clutter_frac=0.15):
+    """Images of 2D segments with three dominant vanishing points (two far ones, one near the image centre) plus
+    clutter -- the Manhattan-like structure J-Linkage is run on (vplib/JLinkage/JLinkage.cc:14-127). Every segment
+    is at least 45 px long, so all pass the detector's min_length of 40. Returns a list of [n_segments, 4] arrays."""
+    rng = np.random.default_rng(seed)
+    out = []
+    n_cl = int(round(n_segments * clutter_frac))
+    base = n_segments - n_cl
+    counts = [base - 2 * (base // 3), base // 3, base // 3]
+    for _ in range(n_images):
+        vps = [np.array([rng.uniform(1500, 4000) * rng.choice([-1, 1]), rng.uniform(200, 400), 1.0]),
+               np.array([rng.uniform(300, 500), rng.uniform(2500, 5000) * rng.choice([-1, 1]), 1.0]),
+               np.array([rng.uniform(350, 450), rng.uniform(250, 350), 1.0])]
+        segs = []
+        for vp, n in zip(vps, counts):
+            p = rng.uniform([0, 0], [width, height], (n, 2))
+            d = vp[:2] / vp[2] - p
+            d /= np.linalg.norm(d, axis=1, keepdims=True)
+            L = rng.uniform(45, 160, (n, 1))
+            segs.append(np.concatenate([p + rng.normal(scale=noise, size=(n, 2)),
+                                        p + d * L + rng.normal(scale=noise, size=(n, 2))], 1))
+        a = rng.uniform([0, 0], [width, height], (n_cl, 2))
+        ang = rng.uniform(0, np.pi, n_cl)
+        ln = rng.uniform(45, 150, (n_cl, 1))
+        segs.append(np.concatenate([a, a + ln * np.stack([np.cos(ang), np.sin(ang)], 1)], 1))
+        segs = np.concatenate(segs, 0)
+        out.append(np.ascontiguousarray(segs[rng.permutation(len(segs))]))
+    return out

@@ -157,8 +157,9 @@ class GlobalLineTriangulator:
         line, ng = self._eng.get_cands_node(int(img_id), int(line_id))  # needs debug_mode, like the reference
         out = [(_line3d(r), float(r[9]), (int(g[0]), int(g[1]))) for r, g in zip(line, ng)]
         if valid_only:
-            out.sort(key=lambda t: (-t[1], -out.index(t)))
-            out = [t for t in out[: self.config_.max_valid_conns] if t[1] >= self.config_.fullscore_th]
+            # valid_tris_ is filled in std::greater<pair<score, tri_id>> order (global_line_triangulator.cc:124-142)
+            order = sorted(range(len(out)), key=lambda i: (-out[i][1], -i))
+            out = [out[i] for i in order[: self.config_.max_valid_conns] if out[i][1] >= self.config_.fullscore_th]
         return out
 
     def CountAllTris(self):

@@ -73,7 +73,15 @@ class JLinkageDetector:
     def as_dict(self):
         return dict(self.config_)
 
-    def detect_batch(self, segs_list):
+    def stats(self):
+        st = _cabi.VPStats()
+        check(lib().lm_vp_get_stats(self._ctx.handle, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _cabi.VPStats._fields_}
+
+    def detect_batch(self, segs_list, image_index=None):
+        """image_index[i]: position of image i in the full image list of the scene (seeds its hypotheses); a rank
+        detecting a share of the images passes it to get the labels of the single-call run."""
+        idx = None if image_index is None else np.ascontiguousarray(image_index, np.int64)
         off = np.zeros(len(segs_list) + 1, np.int64)
         for i, s in enumerate(segs_list):
             off[i + 1] = off[i] + len(s)
@@ -85,12 +93,12 @@ class JLinkageDetector:
         vp_off = np.zeros(len(segs_list) + 1, np.int64)
         cap = 64 * max(len(segs_list), 1)
         vps = np.zeros((cap, 3))
-        n = check(lib().lm_vp_detect(self._ctx.handle, len(segs_list), ptr(off), ptr(segs), C.byref(cfg), ptr(labels),
-                                     ptr(vp_off), ptr(vps), cap))
+        n = check(lib().lm_vp_detect_indexed(self._ctx.handle, len(segs_list), ptr(off), ptr(segs), C.byref(cfg), ptr(idx),
+                                             ptr(labels), ptr(vp_off), ptr(vps), cap))
         if n > cap:
             vps = np.zeros((n, 3))
-            check(lib().lm_vp_detect(self._ctx.handle, len(segs_list), ptr(off), ptr(segs), C.byref(cfg), ptr(labels),
-                                     ptr(vp_off), ptr(vps), n))
+            check(lib().lm_vp_detect_indexed(self._ctx.handle, len(segs_list), ptr(off), ptr(segs), C.byref(cfg), ptr(idx),
+                                             ptr(labels), ptr(vp_off), ptr(vps), n))
         return [VPResult(labels[off[i]:off[i + 1]], vps[vp_off[i]:vp_off[i + 1]]) for i in range(len(segs_list))]
 
     def ComputeVPLabels(self, lines):

@@ -244,12 +244,13 @@ class VPCfg(C.Structure):
 
 
 def detect_vps(line_off, segs, min_length=40.0, inlier_threshold=1.0, min_num_supports=5, th_perp_supports=3.0,
-               n_models=5000, seed=0, threads=None):
+               n_models=5000, seed=0, threads=None, image_index=None):
     """CPU restatement of JLinkage::AssociateVPs over a batch of images (flat segments)."""
     L = lib()
     L.orc_set_num_threads(int(threads) if threads else min(8, usable_cpus()))
-    L.orc_vp_detect.restype = C.c_longlong
-    L.orc_vp_detect.argtypes = [C.c_int, _P, _P, _P, _P, _P, _P, C.c_longlong]
+    L.orc_vp_detect_indexed.restype = C.c_longlong
+    L.orc_vp_detect_indexed.argtypes = [C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_longlong]
+    idx = None if image_index is None else np.ascontiguousarray(image_index, np.int64)
     line_off = np.ascontiguousarray(line_off, np.int64)
     segs = _f64(segs)
     n = len(line_off) - 1
@@ -258,7 +259,8 @@ def detect_vps(line_off, segs, min_length=40.0, inlier_threshold=1.0, min_num_su
     vp_off = np.zeros(n + 1, np.int64)
     cap = 64 * max(n, 1)
     vps = np.zeros((cap, 3))
-    tot = L.orc_vp_detect(n, _p(line_off), _p(segs), C.byref(cfg), _p(labels), _p(vp_off), _p(vps), cap)
+    tot = L.orc_vp_detect_indexed(n, _p(line_off), _p(segs), C.byref(cfg), None if idx is None else _p(idx), _p(labels),
+                                  _p(vp_off), _p(vps), cap)
     return labels, vp_off, vps[:tot]
 
 

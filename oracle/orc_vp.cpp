@@ -14,8 +14,10 @@ struct orc_vp_cfg {
 };
 
 // labels[sum L] out; vps_out[cap][3]; vp_off[n_images+1] out. Returns total number of VPs (may exceed cap).
-long long orc_vp_detect(int n_images, const int64_t *line_off, const double *segs, const orc_vp_cfg *c,
-                        int32_t *labels, int64_t *vp_off, double *vps_out, long long cap) {
+// image_index[im] (may be NULL = im): the index that seeds the hypotheses of image im, so that a call on a subset of
+// the images (one rank's share) draws what the call on all images draws for them.
+long long orc_vp_detect_indexed(int n_images, const int64_t *line_off, const double *segs, const orc_vp_cfg *c,
+                                const int64_t *image_index, int32_t *labels, int64_t *vp_off, double *vps_out, long long cap) {
   VPConfig cfg;
   cfg.min_length = c->min_length; cfg.inlier_threshold = c->inlier_threshold; cfg.th_perp_supports = c->th_perp_supports;
   cfg.min_num_supports = c->min_num_supports; cfg.n_models = c->n_models; cfg.seed = c->seed;
@@ -26,7 +28,7 @@ long long orc_vp_detect(int n_images, const int64_t *line_off, const double *seg
     std::vector<Line2d> lines;
     for (int64_t l = line_off[im]; l < line_off[im + 1]; ++l)
       lines.push_back(Line2d(V2(segs[4 * l], segs[4 * l + 1]), V2(segs[4 * l + 2], segs[4 * l + 3])));
-    detect_vp_image(lines, cfg, (uint64_t)im, all_labels[im], all_vps[im]);
+    detect_vp_image(lines, cfg, image_index ? (uint64_t)image_index[im] : (uint64_t)im, all_labels[im], all_vps[im]);
   }
   long long n = 0;
   for (int im = 0; im < n_images; ++im) {
@@ -39,6 +41,11 @@ long long orc_vp_detect(int n_images, const int64_t *line_off, const double *seg
   }
   vp_off[n_images] = n;
   return n;
+}
+
+long long orc_vp_detect(int n_images, const int64_t *line_off, const double *segs, const orc_vp_cfg *c,
+                        int32_t *labels, int64_t *vp_off, double *vps_out, long long cap) {
+  return orc_vp_detect_indexed(n_images, line_off, segs, c, nullptr, labels, vp_off, vps_out, cap);
 }
 
 } // extern "C"

@@ -40,22 +40,18 @@ for k, v in acc.items():
     print(f"{k:28s} {np.median(v[2:]):8.3f} ms")
 print("device run ms", st["last_run_ms"], "kernel", st["last_node_kernel_ms"])
 
-# ---- does a kernel on another stream run while the match upload is in flight (same process, same context)? ----
-probe = torch.zeros(1 << 10, device="cuda")
-s2 = torch.cuda.Stream()
-for groups in (1, 5):
+# ---- full public-API step (scene up, matches up, run, results down) for several pipeline group counts ----
+for groups in (1, 2, 4, 8):
     eng.set_pipeline_groups(groups)
-    lat, tot = [], []
-    for it in range(5):
-        eng.upload(sc); eng.set_ranges(*sc.ranges); torch.cuda.synchronize()
-        t = time.perf_counter()
-        eng.add_matches_bulk(bsrc, bng, boff, pp)
-        with torch.cuda.stream(s2):
-            probe.add_(1.0)
-        s2.synchronize()
-        lat.append((time.perf_counter() - t) * 1e3)
-        st = eng.run()
+    tot, dev, ker = [], [], []
+    for it in range(7):
         torch.cuda.synchronize()
+        t = time.perf_counter()
+        eng.upload(sc); eng.set_ranges(*sc.ranges)
+        eng.add_matches_bulk(bsrc, bng, boff, pp)
+        st = eng.run()
+        eng.get_nodes(nodes_out)
+        eng.get_all_valid_edges(off_out, edges_out)
         tot.append((time.perf_counter() - t) * 1e3)
-    print(f"groups={groups}: probe kernel on a side stream done {np.median(lat[2:]):.3f} ms after the bulk add was issued; "
-          f"add+run {np.median(tot[2:]):.3f} ms; device run {st['last_run_ms']:.3f} ms")
+        dev.append(st["last_run_ms"]); ker.append(st["last_node_kernel_ms"])
+    print(f"groups={groups}: e2e step {np.median(tot[2:]):.3f} ms; device run {np.median(dev[2:]):.3f} ms; node kernel {np.median(ker[2:]):.3f} ms")

@@ -100,3 +100,35 @@ def compare_tracks(eng, orc):
         assert abs(a[6] - b[6]) <= ENDPOINT_TOL
     assert worst <= ENDPOINT_TOL, f"track endpoints differ by {worst}"
     return dict(tracks=len(gs), exact_order=exact_order, worst=worst, score_ties=n_ties)
+
+
+def compare_nodes_fast(img_ids, eng, orc):
+    """compare_nodes without per-node Python loops (for scenes of 1e5 nodes): candidate counts, best-candidate ids
+    and per-node valid-connection sets bit-exact; endpoints / depths / uncertainty within 1e-4, scores within 1e-6."""
+    n_nodes = n_cand = n_edges = 0
+    worst = 0.0
+    for i in img_ids:
+        i = int(i)
+        gl, gng, gnc = eng.get_best(i)
+        ol, ong, onc = orc.get_best(i)
+        assert np.array_equal(gnc, onc), f"candidate counts differ in image {i}"
+        has = onc > 0
+        assert np.array_equal(gng[has], ong[has]), f"best candidate index differs in image {i}"
+        if has.any():
+            worst = max(worst, float(np.abs(gl[has, :9] - ol[has, :9]).max()))
+            assert np.abs(gl[has, 9] - ol[has, 9]).max() <= SCORE_TOL
+        goff, ge = eng.get_valid_edges(i)
+        ooff, oe = orc.get_valid_edges(i)
+        assert np.array_equal(goff, ooff), f"valid connection counts differ in image {i}"
+        node_of = np.repeat(np.arange(len(goff) - 1), np.diff(goff))
+        if len(ge):
+            ga = np.stack([node_of, ge[:, 0], ge[:, 1]], 1)
+            oa = np.stack([node_of, oe[:, 0], oe[:, 1]], 1)
+            ga = ga[np.lexsort((ga[:, 2], ga[:, 1], ga[:, 0]))]
+            oa = oa[np.lexsort((oa[:, 2], oa[:, 1], oa[:, 0]))]
+            assert np.array_equal(ga, oa), f"valid connections differ in image {i}"
+        n_nodes += len(onc)
+        n_cand += int(onc.sum())
+        n_edges += len(oe)
+    assert worst <= ENDPOINT_TOL, worst
+    return dict(nodes=n_nodes, candidates=n_cand, valid_edges=n_edges, worst=worst)

@@ -1,0 +1,94 @@
+"""GPU parity against the oracle AT THE SIZES bench.py reports (round-1 verdict, "parity only on toy sizes"):
+  * full hypersim100 (BASELINE.json configs[1]: V=100, L=1000, N=20, K=10 = 2e7 match rows) -- node records, valid
+    connections and track membership against the oracle (node-parallel schedule: identical results, all cores);
+  * a 60-source-image shard of sweep500 (configs[2]: V=500, L=400, N=40, K=10; 400 rows per node);
+  * line BA at 10k tracks x 30 supports (configs[3]) with max_num_iterations 100 and 200;
+  * an asset-unit (x100) scene of > 1e6 rows and a multi-camera scene mixing PINHOLE (fx != fy) and SIMPLE_PINHOLE.
+Bar: candidate / valid-connection / best ids and track membership bit-exact, endpoints 1e-4, scores 1e-6."""
+import numpy as np
+import pytest
+
+from limap_b200.config import DEFAULT_YAML_TRIANGULATION
+from limap_b200.synth import CONFIGS, make_scene, make_tracks
+
+from parity_utils import compare_nodes_fast, compare_tracks
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(sc, img_ids=None, shard=None, cfg=None):
+    from limap_b200.engine import TriEngine
+    from oracle import oracle as orc
+    cfg = dict(DEFAULT_YAML_TRIANGULATION) if cfg is None else cfg
+    ids = [int(i) for i in (sc.img_ids if img_ids is None else img_ids)]
+    eng = TriEngine(cfg)
+    o = orc.OracleTri(cfg, threads=orc.usable_cpus(), node_parallel=True)
+    for t in (eng, o):
+        t.upload(sc)
+        t.set_ranges(*sc.ranges)
+    eng.add_matches_bulk(*sc.bulk_matches(ids))
+    if shard is not None:
+        eng.set_shard(*shard)
+    for i in ids:
+        o.add_image_matches(i, *sc.flat_matches(i))
+    st = eng.run()
+    assert st["n_rows"] == o.rows_tested() == sc.n_rows(ids)
+    return eng, o, st
+
+
+def test_hypersim100_full_size_matches_oracle():
+    sc = make_scene(**CONFIGS["hypersim100"])
+    eng, o, st = _both(sc)
+    assert st["n_rows"] == 20_000_000
+    r = compare_nodes_fast(sc.img_ids, eng, o)
+    assert r["nodes"] == 100_000 and r["candidates"] == st["n_candidates"] > 5_000_000
+    assert r["valid_edges"] == st["n_valid_edges"] > 500_000
+    tr = compare_tracks(eng, o)
+    assert tr["tracks"] > 1_000
+
+
+def test_sweep500_shard_matches_oracle():
+    c = dict(CONFIGS["sweep500"])
+    ve = 60
+    sc = make_scene(match_views=range(ve), **c)
+    eng, o, st = _both(sc, img_ids=sc.img_ids[:ve], shard=(0, ve))
+    assert st["max_rows_per_node"] == c["N"] * c["K"] == 400
+    assert st["n_rows"] == ve * c["L"] * c["N"] * c["K"]
+    r = compare_nodes_fast(sc.img_ids[:ve], eng, o)
+    assert r["candidates"] == st["n_candidates"] > 1_000_000
+
+
+def test_asset_unit_scene_over_1e6_rows():
+    sc = make_scene(V=30, L=500, N=10, K=8, seed=41, scale=100.0)
+    eng, o, st = _both(sc)
+    assert st["n_rows"] >= 1_000_000
+    r = compare_nodes_fast(sc.img_ids, eng, o)
+    assert r["candidates"] > 100_000
+    compare_tracks(eng, o)
+
+
+def test_multi_camera_pinhole_fx_ne_fy():
+    sc = make_scene(V=24, L=300, N=8, K=8, seed=42, camera_mix=True)
+    assert set(sc.model_ids.tolist()) == {0, 1} and (sc.kvec[1::2, 0] != sc.kvec[1::2, 1]).all()
+    assert len(np.unique(sc.kvec[:, 0])) == 24
+    eng, o, st = _both(sc)
+    r = compare_nodes_fast(sc.img_ids, eng, o)
+    assert r["candidates"] > 50_000 and r["valid_edges"] > 5_000
+    compare_tracks(eng, o)
+
+
+@pytest.mark.parametrize("max_iter", [100, 200])
+def test_line_ba_10k_tracks_x_30_supports(max_iter):
+    from limap_b200.engine import BAEngine
+    from oracle import oracle as orc
+    ts = make_tracks(T=10000, S=30, V=300, seed=1237)
+    g = BAEngine().solve_trackset(ts, max_num_iterations=max_iter)
+    o = orc.refine_tracks(ts, max_num_iterations=max_iter, threads=orc.usable_cpus())
+    assert np.abs(g["cost"][:, 0] - o["cost"][:, 0]).max() < 1e-9 * (1 + o["cost"][:, 0].max())
+    rel = np.abs(g["cost"][:, 1] - o["cost"][:, 1]) / (1e-12 + o["cost"][:, 1])
+    assert np.median(rel) < 1e-9 and rel.max() < 1e-5, (np.median(rel), rel.max())
+    d = np.minimum(np.abs(g["line"] - o["line"]).max(1), np.abs(g["line"] - o["line"][:, [3, 4, 5, 0, 1, 2]]).max(1))
+    assert d.max() <= 1e-4, d.max()
+    gi, oi = int(g["iters"][:, 0].sum()), int(o["iters"][:, 0].sum())
+    assert 0.8 < gi / oi < 1.25, (gi, oi)
+    assert (g["iters"][:, 0] <= max_iter).all()

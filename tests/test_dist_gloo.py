@@ -118,3 +118,47 @@ def test_sharded_line_ba_gather_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _vp_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from limap_b200.dist import detect_vps_sharded
+    from limap_b200.synth import make_vp_images
+    from oracle import oracle as orc
+    imgs = make_vp_images(5, 60, seed=3) + [np.zeros((0, 4))]
+
+    class R:  # VPResult-like
+        def __init__(self, labels, vps):
+            self.labels, self.vps = labels, vps
+
+    def cpu_detect(segs_list, image_index=None):  # stands in for JLinkageDetector.detect_batch (needs a GPU)
+        off = np.concatenate([[0], np.cumsum([len(s) for s in segs_list])]).astype(np.int64)
+        segs = np.concatenate(segs_list, 0) if len(segs_list) else np.zeros((0, 4))
+        lab, vo, vps = orc.detect_vps(off, segs, min_length=40, inlier_threshold=1.0, min_num_supports=5, seed=11,
+                                      n_models=500, threads=1, image_index=image_index)
+        return [R(lab[off[i]:off[i + 1]], vps[vo[i]:vo[i + 1]]) for i in range(len(segs_list))]
+    labels, vps = detect_vps_sharded(cpu_detect, imgs, rank, world, device="cpu")
+    ref = cpu_detect(imgs)  # the single call on all images
+    ok = all(np.array_equal(labels[i], np.asarray(ref[i].labels, np.int32)) for i in range(len(imgs)))
+    ok &= all(np.allclose(vps[i], np.asarray(ref[i].vps).reshape(-1, 3)) for i in range(len(imgs)))
+    ok &= any(len(v) > 0 for v in vps)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_sharded_jlinkage_identical_to_single_call_gloo_world2():
+    from oracle import oracle as orc
+    orc.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_vp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

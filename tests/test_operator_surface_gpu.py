@@ -136,3 +136,47 @@ def test_disk_formats_and_device_tensor_ingress(tmp_path):
     assert len(back) == len(ref)
     assert all(x.line_id_list == y.line_id_list and x.node_id_list == y.node_id_list for x, y in zip(ref, back))
     assert max(np.abs(x.line.as_array() - y.line.as_array()).max() for x, y in zip(ref, back)) <= 1e-9
+
+
+def test_valid_tris_getters_match_oracle_debug_mode():
+    """GetValidScoredTrisNode / ...NodeSet / GetValidTrisNode / GetValidTrisImage / GetAllValidTris
+    (global_line_triangulator.cc:380-470): valid_tris_ holds the candidates with score >= fullscore_th in
+    std::greater<(score, tri_id)> order, capped at max_valid_conns."""
+    import limap.base as base
+    import limap.triangulation as triangulation
+    from oracle import oracle as orc
+    sc = make_scene(V=6, L=60, N=4, K=6, seed=43)
+    for max_conns in (1000, 2):
+        cfg = dict(DEFAULT_YAML_TRIANGULATION, debug_mode=True, max_valid_conns=max_conns)
+        tri = triangulation.GlobalLineTriangulator(cfg)
+        tri.SetRanges(sc.ranges)
+        tri.Init(base.get_all_lines_2d({int(i): sc.lines_of(v) for v, i in enumerate(sc.img_ids)}), _imagecols(sc))
+        for img_id in sc.img_ids:
+            tri.TriangulateImage(int(img_id), sc.matches[int(img_id)])
+        o = orc.OracleTri(cfg)
+        o.upload(sc)
+        o.set_ranges(*sc.ranges)
+        for i in sc.img_ids:
+            o.add_image_matches(int(i), *sc.flat_matches(int(i)))
+        n_valid_total = 0
+        for i in sc.img_ids[:3]:
+            i = int(i)
+            ooff, oe = o.get_valid_edges(i)
+            n_img = 0
+            for l in range(tri.CountLines(i)):
+                cl, cng = o.get_cands_node(i, l)
+                order = sorted(range(len(cl)), key=lambda k: (-cl[k, 9], -k))[:max_conns]
+                exp = [k for k in order if cl[k, 9] >= cfg["fullscore_th"]]
+                got = tri.GetValidScoredTrisNode(i, l)
+                assert [g[2] for g in got] == [tuple(int(x) for x in cng[k]) for k in exp]
+                assert np.allclose([g[1] for g in got], cl[exp, 9], atol=1e-6)
+                assert sorted(g[2] for g in got) == sorted(map(tuple, oe[ooff[l]:ooff[l + 1]].tolist()))
+                assert len(tri.GetValidTrisNode(i, l)) == len(got)
+                ns = tri.GetValidScoredTrisNodeSet(i, l)
+                assert len(ns) == len({g[2][0] for g in got}) and all(isinstance(x[0], base.Line3d) for x in ns)
+                assert len(tri.GetValidTrisNodeSet(i, l)) == len(ns)
+                n_img += len(got)
+            assert len(tri.GetValidTrisImage(i)) == n_img == len(oe)
+            n_valid_total += n_img
+        assert n_valid_total > 0
+        assert len(tri.GetAllValidTris()) == tri.CountAllValidTris()
