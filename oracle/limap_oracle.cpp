@@ -285,6 +285,19 @@ double orc_score_3d(const orc_linker_cfg *c, const double *l1, const double *l2)
   LineLinker3d lk; lk.config = to_linker(*c);
   return lk.compute_score(mkline3(l1), mkline3(l2));
 }
+void orc_triangulate_line_with_direction(const double *l1, const double *cam1, const double *l2, const double *cam2,
+                                         const double *direction, double *out) {
+  Line2d a(V2(l1[0], l1[1]), V2(l1[2], l1[3])), b(V2(l2[0], l2[1]), V2(l2[2], l2[3]));
+  Line3d L = triangulate_line_with_direction(a, mkview(cam1), b, mkview(cam2), V3(direction[0], direction[1], direction[2]));
+  out[0] = L.start.x; out[1] = L.start.y; out[2] = L.start.z; out[3] = L.end.x; out[4] = L.end.y; out[5] = L.end.z;
+  out[6] = L.depths[0]; out[7] = L.depths[1]; out[8] = L.score;
+}
+void orc_ray_direction(const double *cam, const double *p, double *out) {
+  V3 r = mkview(cam).ray_direction(V2(p[0], p[1]));
+  out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+double orc_line3d_sensitivity(const double *l, const double *cam) { return mkline3(l).sensitivity(mkview(cam)); }
+double orc_line3d_uncertainty(const double *l, const double *cam, double var2d) { return mkline3(l).computeUncertainty(mkview(cam), var2d); }
 double orc_score_2d(const orc_linker_cfg *c, const double *l1, const double *l2) {
   LineLinker2d lk; lk.config = to_linker(*c);
   return lk.compute_score(Line2d(V2(l1[0], l1[1]), V2(l1[2], l1[3])), Line2d(V2(l2[0], l2[1]), V2(l2[2], l2[3])));

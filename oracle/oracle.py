@@ -92,23 +92,31 @@ class OracleTri:
     """fp64 CPU restatement of GlobalLineTriangulator, same array-level interface as
     limap_b200.engine.TriEngine."""
 
+    _PREFIX = "orc_"
+
+    @staticmethod
+    def _library():
+        return lib()
+
+    def _c(self, name):
+        return getattr(self._library(), self._PREFIX + name)
+
     def __init__(self, cfg=None, threads=None, node_parallel=False):
         """node_parallel=False keeps the reference's OpenMP schedule (inside one node); True moves the OpenMP loop out to
         the 2D lines of the image -- same results, the schedule a throughput-tuned CPU implementation would use."""
         from limap_b200.config import make_tri_config
         self.cfg = make_tri_config(cfg) if not hasattr(cfg, "_fields_") else cfg
-        L = lib()
         # parity runs do not need many threads; the reference's OpenMP regions are tiny (one node each)
-        L.orc_set_num_threads(int(threads) if threads else min(8, usable_cpus()))
-        self._h = L.orc_tri_create(C.byref(self.cfg))
+        self._c("set_num_threads")(int(threads) if threads else min(8, usable_cpus()))
+        self._h = self._c("tri_create")(C.byref(self.cfg))
         if not self._h:
-            raise RuntimeError(L.orc_last_error().decode())
+            raise RuntimeError(self._c("last_error")().decode())
         if node_parallel:
-            L.orc_tri_set_node_parallel(self._h, 1)
+            self._c("tri_set_node_parallel")(self._h, 1)
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().orc_tri_destroy(self._h)
+            self._c("tri_destroy")(self._h)
             self._h = None
 
     def upload_scene(self, img_ids, model_ids, kvec, qvec, tvec, line_off, segs):
@@ -117,7 +125,7 @@ class OracleTri:
         self._view = {int(i): v for v, i in enumerate(self.img_ids)}
         a = [self.img_ids, np.ascontiguousarray(model_ids, np.int32), _f64(kvec), _f64(qvec), _f64(tvec),
              self.line_off, _f64(segs)]
-        lib().orc_tri_init(self._h, len(self.img_ids), *[_p(x) for x in a])
+        self._c("tri_init")(self._h, len(self.img_ids), *[_p(x) for x in a])
 
     def upload(self, scene):
         self.upload_scene(scene.img_ids, scene.model_ids, scene.kvec, scene.qvec, scene.tvec,
@@ -128,7 +136,7 @@ class OracleTri:
         return int(self.line_off[v + 1] - self.line_off[v])
 
     def set_ranges(self, lo, hi):
-        lib().orc_tri_set_ranges(self._h, _p(_f64(lo)), _p(_f64(hi)))
+        self._c("tri_set_ranges")(self._h, _p(_f64(lo)), _p(_f64(hi)))
 
     def set_vps(self, vpresults, img_ids=None, line_off=None):
         """InitVPResults: {img_id: object with .labels and .vps}."""
@@ -144,56 +152,55 @@ class OracleTri:
             vp_off.append(vp_off[-1] + len(v))
         labels = np.ascontiguousarray(np.concatenate(labels) if labels else np.zeros(0, np.int32))
         vps = np.ascontiguousarray(np.concatenate(vps) if vps else np.zeros((0, 3)))
-        L = lib()
-        L.orc_tri_set_vps.argtypes = [_P, C.c_int, _P, _P, _P, _P, _P]
-        L.orc_tri_set_vps(self._h, len(ids), _p(np.asarray(ids, np.int32)), _p(np.asarray(label_off, np.int64)),
+        self._c("tri_set_vps").argtypes = [_P, C.c_int, _P, _P, _P, _P, _P]
+        self._c("tri_set_vps")(self._h, len(ids), _p(np.asarray(ids, np.int32)), _p(np.asarray(label_off, np.int64)),
                           _p(labels), _p(np.asarray(vp_off, np.int64)), _p(vps))
 
     def add_image_matches(self, img_id, ng_ids, row_off, pairs):
         ng_ids = np.ascontiguousarray(ng_ids, np.int32)
         row_off = np.ascontiguousarray(row_off, np.int64)
         pairs = np.ascontiguousarray(pairs, np.int32)
-        rc = lib().orc_tri_triangulate_image(self._h, int(img_id), len(ng_ids), _p(ng_ids), _p(row_off),
+        rc = self._c("tri_triangulate_image")(self._h, int(img_id), len(ng_ids), _p(ng_ids), _p(row_off),
                                              _p(pairs))
         if rc:
-            raise RuntimeError(lib().orc_last_error().decode())
+            raise RuntimeError(self._c("last_error")().decode())
 
     def add_image_exhaustive(self, img_id, neighbors):
         ng = np.ascontiguousarray(neighbors, np.int32)
-        rc = lib().orc_tri_triangulate_image_exhaustive(self._h, int(img_id), len(ng), _p(ng))
+        rc = self._c("tri_triangulate_image_exhaustive")(self._h, int(img_id), len(ng), _p(ng))
         if rc:
-            raise RuntimeError(lib().orc_last_error().decode())
+            raise RuntimeError(self._c("last_error")().decode())
 
     def rows_tested(self):
-        return int(lib().orc_tri_rows_tested(self._h))
+        return int(self._c("tri_rows_tested")(self._h))
 
     def get_best(self, img_id):
         L = self.n_lines(img_id)
         line = np.zeros((L, 10))
         ng = np.zeros((L, 2), np.int32)
         nc = np.zeros(L, np.int32)
-        lib().orc_tri_get_best(self._h, int(img_id), _p(line), _p(ng), _p(nc))
+        self._c("tri_get_best")(self._h, int(img_id), _p(line), _p(ng), _p(nc))
         return line, ng, nc
 
     def get_valid_edges(self, img_id):
         L = self.n_lines(img_id)
         off = np.zeros(L + 1, np.int64)
-        n = lib().orc_tri_get_valid_edges(self._h, int(img_id), _p(off), None)
+        n = self._c("tri_get_valid_edges")(self._h, int(img_id), _p(off), None)
         edges = np.zeros((max(n, 1), 2), np.int32)
-        lib().orc_tri_get_valid_edges(self._h, int(img_id), _p(off), _p(edges))
+        self._c("tri_get_valid_edges")(self._h, int(img_id), _p(off), _p(edges))
         return off, edges[:n]
 
     def get_cands_node(self, img_id, line_id, cap=4096):
         line = np.zeros((cap, 10))
         ng = np.zeros((cap, 2), np.int32)
-        n = lib().orc_tri_get_tris_node(self._h, int(img_id), int(line_id), cap, _p(line), _p(ng))
+        n = self._c("tri_get_tris_node")(self._h, int(img_id), int(line_id), cap, _p(line), _p(ng))
         if n > cap:
             return self.get_cands_node(img_id, line_id, n)
         return line[:n], ng[:n]
 
     def build_tracks(self):
         tot = C.c_int64(0)
-        T = lib().orc_tri_compute_tracks(self._h, C.byref(tot))
+        T = self._c("tri_compute_tracks")(self._h, C.byref(tot))
         n = tot.value
         track_off = np.zeros(T + 1, np.int64)
         img = np.zeros(max(n, 1), np.int32)
@@ -201,7 +208,7 @@ class OracleTri:
         node = np.zeros(max(n, 1), np.int32)
         l3d = np.zeros((max(n, 1), 10))
         tl = np.zeros((max(T, 1), 7))
-        lib().orc_tri_get_tracks(self._h, _p(track_off), _p(img), _p(line), _p(node), _p(l3d), _p(tl))
+        self._c("tri_get_tracks")(self._h, _p(track_off), _p(img), _p(line), _p(node), _p(l3d), _p(tl))
         return dict(track_off=track_off, img_ids=img[:n], line_ids=line[:n], node_ids=node[:n],
                     line3d=l3d[:n], track_line=tl[:T])
 

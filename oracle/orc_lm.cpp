@@ -92,6 +92,19 @@ void orc_minimal_from_line(const double *line, double *out6) {
   for (int i = 0; i < 4; ++i) out6[i] = ml.uvec[i];
   out6[4] = ml.wvec[0]; out6[5] = ml.wvec[1];
 }
+// GetLineSegmentFromInfiniteLine3d(inf_line(x6), line3ds, num_outliers) (base/infinite_line.cc:265-287)
+void orc_segment_from_minimal(const double *x6, const double *line3d, int64_t n, int num_outliers, double *out6) {
+  MinimalLine ml;
+  for (int i = 0; i < 4; ++i) ml.uvec[i] = x6[i];
+  ml.wvec[0] = x6[4]; ml.wvec[1] = x6[5];
+  V3 d, m;
+  InfiniteFromMinimal(ml, d, m);
+  std::vector<Line3d> ls;
+  for (int64_t k = 0; k < n; ++k) ls.push_back(Line3d(V3(line3d[6 * k], line3d[6 * k + 1], line3d[6 * k + 2]),
+                                                     V3(line3d[6 * k + 3], line3d[6 * k + 4], line3d[6 * k + 5])));
+  Line3d r = SegmentFromInfinite(d, m, ls, num_outliers);
+  out6[0] = r.start.x; out6[1] = r.start.y; out6[2] = r.start.z; out6[3] = r.end.x; out6[4] = r.end.y; out6[5] = r.end.z;
+}
 void orc_infinite_from_minimal(const double *x6, double *d3, double *m3) {
   MinimalLine ml;
   for (int i = 0; i < 4; ++i) ml.uvec[i] = x6[i];

@@ -1,0 +1,466 @@
+// oracle/ref_api.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// C entry points (ctypes) over the REFERENCE'S OWN hot-path sources, compiled unchanged from /root/reference by
+// oracle/Makefile (target _ref) against the header shims in oracle/ref_shim/ (Eigen subset, COLMAP camera struct,
+// glog macros, PoseLib quartic: none of them is in this image). The entry points mirror limap_oracle.cpp's
+// (prefix ref_ instead of orc_) so that tests pin the restatement to the reference's compiled code:
+//   GlobalLineTriangulator::{Init, TriangulateImage(ExhaustiveMatch), ComputeLineTracks} and its result tables,
+//   triangulation/functions.cc, LineLinker2d/3d::compute_score, Aggregator::aggregate_line3d_list,
+//   MinimalInfiniteLine3d, GetLineSegmentFromInfiniteLine3d, CheckReprojection / CheckSensitivity / overlap,
+//   RemergeLineTracks.
+// Nothing of the product links or loads this library.
+// every standard / third-party header first, with its own access specifiers intact ...
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <queue>
+#include <set>
+#include <sstream>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+#include <pybind11/eigen.h>
+#include <pybind11/embed.h>
+#include <pybind11/eval.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+#include <Eigen/Dense>
+#include <colmap/scene/camera.h>
+#include <colmap/util/logging.h>
+#include <third-party/half.h>
+// ... then the reference's class definitions with their result tables readable (layout is unaffected)
+#define private public
+#define protected public
+#include "limap/base/infinite_line.h"
+#include "limap/base/line_linker.h"
+#include "limap/merging/aggregator.h"
+#include "limap/merging/merging.h"
+#include "limap/merging/merging_utils.h"
+#include "limap/triangulation/functions.h"
+#include "limap/triangulation/global_line_triangulator.h"
+#undef private
+#undef protected
+#include <cstring>
+#include <memory>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace limap;
+using limap::triangulation::GlobalLineTriangulator;
+using limap::triangulation::GlobalLineTriangulatorConfig;
+using limap::triangulation::TriTuple;
+
+extern "C" {
+
+struct ref_linker_cfg {
+  double score_th, th_angle, th_overlap, th_smartoverlap, th_smartangle, th_perp, th_innerseg, th_scaleinv;
+  int32_t use_angle, use_overlap, use_smartangle, use_perp, use_innerseg, use_scaleinv;
+};
+struct ref_tri_cfg {
+  double min_length_2d, line_tri_angle_threshold, IoU_threshold, sensitivity_threshold, var2d, fullscore_th;
+  int32_t debug_mode, add_halfpix, use_vp, use_endpoints_triangulation;
+  int32_t disable_many_points_triangulation, disable_one_point_triangulation;
+  int32_t disable_algebraic_triangulation, disable_vp_triangulation;
+  int32_t max_valid_conns, min_num_outer_edges, num_outliers_aggregator, merging_strategy;
+  ref_linker_cfg linker2d, linker3d;
+};
+
+} // extern "C"
+template <typename L> static void fill_linker(L &l, const ref_linker_cfg &c) {
+  l.score_th = c.score_th; l.th_angle = c.th_angle; l.th_overlap = c.th_overlap; l.th_smartoverlap = c.th_smartoverlap;
+  l.th_smartangle = c.th_smartangle; l.th_perp = c.th_perp; l.th_innerseg = c.th_innerseg;
+  l.use_angle = c.use_angle; l.use_overlap = c.use_overlap; l.use_smartangle = c.use_smartangle; l.use_perp = c.use_perp;
+  l.use_innerseg = c.use_innerseg;
+}
+extern "C" {
+static LineLinker2dConfig to_linker2d(const ref_linker_cfg &c) { LineLinker2dConfig l; fill_linker(l, c); return l; }
+static LineLinker3dConfig to_linker3d(const ref_linker_cfg &c) {
+  LineLinker3dConfig l;
+  fill_linker(l, c);
+  l.th_scaleinv = c.th_scaleinv;
+  l.use_scaleinv = c.use_scaleinv;
+  return l;
+}
+
+struct RefTri {
+  std::unique_ptr<GlobalLineTriangulator> tri;
+  std::map<int, std::vector<Line2d>> segs;
+  std::unique_ptr<ImageCollection> imagecols;
+  long long rows = 0;
+};
+
+static thread_local std::string g_err;
+const char *ref_last_error() { return g_err.c_str(); }
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+void *ref_tri_create(const ref_tri_cfg *c) {
+  GlobalLineTriangulatorConfig cfg;
+  // debug_mode only decides whether the per-node candidate lists survive scoring (global_line_triangulator.cc:155-159);
+  // they are kept so that candidate counts and lists can be read back
+  cfg.debug_mode = true;
+  cfg.add_halfpix = c->add_halfpix; cfg.use_vp = c->use_vp;
+  cfg.use_endpoints_triangulation = c->use_endpoints_triangulation;
+  cfg.disable_many_points_triangulation = c->disable_many_points_triangulation;
+  cfg.disable_one_point_triangulation = c->disable_one_point_triangulation;
+  cfg.disable_algebraic_triangulation = c->disable_algebraic_triangulation;
+  cfg.disable_vp_triangulation = c->disable_vp_triangulation;
+  cfg.min_length_2d = c->min_length_2d; cfg.line_tri_angle_threshold = c->line_tri_angle_threshold;
+  cfg.IoU_threshold = c->IoU_threshold; cfg.sensitivity_threshold = c->sensitivity_threshold;
+  cfg.var2d = c->var2d; cfg.fullscore_th = c->fullscore_th;
+  cfg.max_valid_conns = c->max_valid_conns; cfg.min_num_outer_edges = c->min_num_outer_edges;
+  cfg.num_outliers_aggregator = c->num_outliers_aggregator;
+  cfg.merging_strategy = (c->merging_strategy == 0) ? "greedy" : "avg";
+  cfg.linker2d_config = to_linker2d(c->linker2d);
+  cfg.linker3d_config = to_linker3d(c->linker3d);
+  RefTri *h = new RefTri();
+  h->tri.reset(new GlobalLineTriangulator(cfg));
+  return h;
+}
+void ref_tri_destroy(void *hp) { delete (RefTri *)hp; }
+
+int ref_tri_init(void *hp, int n_views, const int32_t *img_ids, const int32_t *model_ids, const double *kvec,
+                 const double *qvec, const double *tvec, const int64_t *line_off, const double *segs) {
+  RefTri *h = (RefTri *)hp;
+  try {
+    std::map<int, Camera> cams;
+    std::map<int, CameraImage> imgs;
+    for (int v = 0; v < n_views; ++v) {
+      const double *k = kvec + 4 * v;
+      std::vector<double> params;
+      if (model_ids[v] == 0) params = {k[0], k[2], k[3]};
+      else params = {k[0], k[1], k[2], k[3]};
+      cams[v] = Camera(model_ids[v], params, v);
+      CameraPose pose(V4D(qvec[4 * v], qvec[4 * v + 1], qvec[4 * v + 2], qvec[4 * v + 3]),
+                      V3D(tvec[3 * v], tvec[3 * v + 1], tvec[3 * v + 2]));
+      imgs[img_ids[v]] = CameraImage(v, pose);
+      std::vector<Line2d> lines;
+      for (int64_t l = line_off[v]; l < line_off[v + 1]; ++l)
+        lines.push_back(Line2d(V2D(segs[4 * l], segs[4 * l + 1]), V2D(segs[4 * l + 2], segs[4 * l + 3])));
+      h->segs[img_ids[v]] = lines;
+    }
+    h->imagecols.reset(new ImageCollection(cams, imgs));
+    h->tri->Init(h->segs, *h->imagecols);
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+  return 0;
+}
+void ref_tri_set_ranges(void *hp, const double *lo, const double *hi) {
+  ((RefTri *)hp)->tri->SetRanges(std::make_pair(V3D(lo[0], lo[1], lo[2]), V3D(hi[0], hi[1], hi[2])));
+}
+void ref_tri_unset_ranges(void *hp) { ((RefTri *)hp)->tri->UnsetRanges(); }
+
+int ref_tri_set_vps(void *hp, int n_images, const int32_t *img_ids, const int64_t *label_off, const int32_t *labels,
+                    const int64_t *vp_off, const double *vps) {
+  std::map<int, vplib::VPResult> res;
+  for (int i = 0; i < n_images; ++i) {
+    vplib::VPResult r;
+    r.labels.assign(labels + label_off[i], labels + label_off[i + 1]);
+    for (int64_t k = vp_off[i]; k < vp_off[i + 1]; ++k) r.vps.push_back(V3D(vps[3 * k], vps[3 * k + 1], vps[3 * k + 2]));
+    res[img_ids[i]] = r;
+  }
+  ((RefTri *)hp)->tri->InitVPResults(res);
+  return 0;
+}
+
+int ref_tri_triangulate_image(void *hp, int img_id, int n_ng, const int32_t *ng_ids, const int64_t *row_off,
+                              const int32_t *pairs) {
+  RefTri *h = (RefTri *)hp;
+  std::map<int, Eigen::MatrixXi> matches;
+  for (int g = 0; g < n_ng; ++g) {
+    const int64_t n = row_off[g + 1] - row_off[g];
+    Eigen::MatrixXi m(n, 2);
+    for (int64_t r = 0; r < n; ++r) { m(r, 0) = pairs[2 * (row_off[g] + r)]; m(r, 1) = pairs[2 * (row_off[g] + r) + 1]; }
+    matches[ng_ids[g]] = m;
+    h->rows += n;
+  }
+  try {
+    h->tri->TriangulateImage(img_id, matches);
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+  return 0;
+}
+int ref_tri_triangulate_image_exhaustive(void *hp, int img_id, int n_ng, const int32_t *ng_ids) {
+  RefTri *h = (RefTri *)hp;
+  std::vector<int> ngs(ng_ids, ng_ids + n_ng);
+  try {
+    h->tri->TriangulateImageExhaustiveMatch(img_id, ngs);
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+  return 0;
+}
+long long ref_tri_rows_tested(void *hp) { return ((RefTri *)hp)->rows; }
+
+static void put_tri(const Line3d &l, double score, double *o) {
+  o[0] = l.start[0]; o[1] = l.start[1]; o[2] = l.start[2]; o[3] = l.end[0]; o[4] = l.end[1]; o[5] = l.end[2];
+  o[6] = l.depths[0]; o[7] = l.depths[1]; o[8] = l.uncertainty; o[9] = score;
+}
+int ref_tri_get_best(void *hp, int img_id, double *out_line, int32_t *out_ng, int32_t *out_ntris) {
+  RefTri *h = (RefTri *)hp;
+  auto &best = h->tri->tris_best_.at(img_id);
+  auto &tris = h->tri->tris_.at(img_id);
+  for (size_t l = 0; l < best.size(); ++l) {
+    const TriTuple &t = best[l];
+    const int n = (int)tris[l].size();
+    if (n > 0) {
+      put_tri(std::get<0>(t), std::get<1>(t), out_line + 10 * l);
+      out_ng[2 * l] = std::get<2>(t).first; out_ng[2 * l + 1] = std::get<2>(t).second;
+    } else { // the reference leaves tris_best_ default-constructed for nodes without candidates
+      for (int k = 0; k < 10; ++k) out_line[10 * l + k] = 0.0;
+      out_line[10 * l + 8] = -1.0;
+      out_ng[2 * l] = out_ng[2 * l + 1] = 0;
+    }
+    if (out_ntris) out_ntris[l] = n;
+  }
+  return (int)best.size();
+}
+long long ref_tri_get_valid_edges(void *hp, int img_id, int64_t *off, int32_t *edges) {
+  RefTri *h = (RefTri *)hp;
+  auto &ve = h->tri->valid_edges_.at(img_id);
+  auto &ngs = h->tri->neighbors_.at(img_id);
+  long long n = 0;
+  for (size_t l = 0; l < ve.size(); ++l) {
+    if (off) off[l] = n;
+    for (auto &e : ve[l]) {
+      if (edges) { edges[2 * n] = ngs[e.first]; edges[2 * n + 1] = e.second; }
+      ++n;
+    }
+  }
+  if (off) off[ve.size()] = n;
+  return n;
+}
+int ref_tri_get_tris_node(void *hp, int img_id, int line_id, int cap, double *out_line, int32_t *out_ng) {
+  RefTri *h = (RefTri *)hp;
+  auto &tris = h->tri->tris_.at(img_id)[line_id];
+  const int n = (int)tris.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    put_tri(std::get<0>(tris[i]), std::get<1>(tris[i]), out_line + 10 * i);
+    out_ng[2 * i] = std::get<2>(tris[i]).first; out_ng[2 * i + 1] = std::get<2>(tris[i]).second;
+  }
+  return n;
+}
+int ref_tri_compute_tracks(void *hp, int64_t *n_nodes_total) {
+  RefTri *h = (RefTri *)hp;
+  try {
+    h->tri->ComputeLineTracks();
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+  int64_t n = 0;
+  for (auto &t : h->tri->tracks_) n += (int64_t)t.image_id_list.size();
+  if (n_nodes_total) *n_nodes_total = n;
+  return (int)h->tri->tracks_.size();
+}
+int ref_tri_get_tracks(void *hp, int64_t *track_off, int32_t *img_ids, int32_t *line_ids, int32_t *node_ids,
+                       double *node_line3d, double *track_line) {
+  RefTri *h = (RefTri *)hp;
+  auto &tr = h->tri->tracks_;
+  int64_t n = 0;
+  for (size_t t = 0; t < tr.size(); ++t) {
+    track_off[t] = n;
+    for (size_t k = 0; k < tr[t].image_id_list.size(); ++k, ++n) {
+      img_ids[n] = tr[t].image_id_list[k];
+      line_ids[n] = tr[t].line_id_list[k];
+      node_ids[n] = tr[t].node_id_list[k];
+      put_tri(tr[t].line3d_list[k], tr[t].score_list[k], node_line3d + 10 * n);
+    }
+    const Line3d &L = tr[t].line;
+    double *o = track_line + 7 * t;
+    o[0] = L.start[0]; o[1] = L.start[1]; o[2] = L.start[2]; o[3] = L.end[0]; o[4] = L.end[1]; o[5] = L.end[2];
+    o[6] = L.uncertainty;
+  }
+  track_off[tr.size()] = n;
+  return (int)tr.size();
+}
+
+// ---- free functions ---------------------------------------------------------------------------------------------------
+static CameraView mkview(const double *cam /*model,fx,fy,cx,cy,qw,qx,qy,qz,tx,ty,tz*/) {
+  const int model = (int)cam[0];
+  std::vector<double> params;
+  if (model == 0) params = {cam[1], cam[3], cam[4]};
+  else params = {cam[1], cam[2], cam[3], cam[4]};
+  return CameraView(Camera(model, params, 0), CameraPose(V4D(cam[5], cam[6], cam[7], cam[8]), V3D(cam[9], cam[10], cam[11])));
+}
+static Line2d mk2(const double *s) { return Line2d(V2D(s[0], s[1]), V2D(s[2], s[3])); }
+double ref_line2d_length(const double *seg) { return mk2(seg).length(); }
+void ref_line2d_direction(const double *seg, double *out) { V2D d = mk2(seg).direction(); out[0] = d[0]; out[1] = d[1]; }
+double ref_compute_epipolar_IoU(const double *l1, const double *cam1, const double *l2, const double *cam2) {
+  return triangulation::compute_epipolar_IoU(mk2(l1), mkview(cam1), mk2(l2), mkview(cam2));
+}
+void ref_triangulate_line(const double *l1, const double *cam1, const double *l2, const double *cam2, int by_endpoints,
+                          double *out) {
+  Line3d L = by_endpoints ? triangulation::triangulate_line_by_endpoints(mk2(l1), mkview(cam1), mk2(l2), mkview(cam2))
+                          : triangulation::triangulate_line(mk2(l1), mkview(cam1), mk2(l2), mkview(cam2));
+  out[0] = L.start[0]; out[1] = L.start[1]; out[2] = L.start[2]; out[3] = L.end[0]; out[4] = L.end[1]; out[5] = L.end[2];
+  out[6] = L.depths[0]; out[7] = L.depths[1]; out[8] = L.score;
+}
+// triangulate_line_with_direction (functions.cc:389-446): out as above
+void ref_triangulate_line_with_direction(const double *l1, const double *cam1, const double *l2, const double *cam2,
+                                         const double *direction, double *out) {
+  Line3d L = triangulation::triangulate_line_with_direction(mk2(l1), mkview(cam1), mk2(l2), mkview(cam2),
+                                                            V3D(direction[0], direction[1], direction[2]));
+  out[0] = L.start[0]; out[1] = L.start[1]; out[2] = L.start[2]; out[3] = L.end[0]; out[4] = L.end[1]; out[5] = L.end[2];
+  out[6] = L.depths[0]; out[7] = L.depths[1]; out[8] = L.score;
+}
+void ref_project_point(const double *cam, const double *X, double *out) {
+  V2D p = mkview(cam).projection(V3D(X[0], X[1], X[2]));
+  out[0] = p[0]; out[1] = p[1];
+}
+void ref_ray_direction(const double *cam, const double *p, double *out) {
+  V3D r = mkview(cam).ray_direction(V2D(p[0], p[1]));
+  out[0] = r[0]; out[1] = r[1]; out[2] = r[2];
+}
+static Line3d mkline3(const double *l) { return Line3d(V3D(l[0], l[1], l[2]), V3D(l[3], l[4], l[5]), 1.0, l[6], l[7], l[8]); }
+double ref_line3d_sensitivity(const double *l, const double *cam) { return mkline3(l).sensitivity(mkview(cam)); }
+double ref_line3d_uncertainty(const double *l, const double *cam, double var2d) { return mkline3(l).computeUncertainty(mkview(cam), var2d); }
+double ref_score_3d(const ref_linker_cfg *c, const double *l1, const double *l2) {
+  LineLinker3d lk(to_linker3d(*c));
+  return lk.compute_score(mkline3(l1), mkline3(l2));
+}
+double ref_score_2d(const ref_linker_cfg *c, const double *l1, const double *l2) {
+  LineLinker2d lk(to_linker2d(*c));
+  return lk.compute_score(mk2(l1), mk2(l2));
+}
+int ref_check_connection_3d(const ref_linker_cfg *c, const double *l1, const double *l2) {
+  LineLinker3d lk(to_linker3d(*c));
+  return lk.check_connection(mkline3(l1), mkline3(l2)) ? 1 : 0;
+}
+
+// Aggregator::aggregate_line3d_list for T groups: lines[n][7] = start, end, uncertainty; out[T][7]
+int ref_aggregate_lines(int64_t T, const int64_t *off, const double *lines, const double *scores, int32_t num_outliers,
+                        double *out) {
+  for (int64_t t = 0; t < T; ++t) {
+    std::vector<Line3d> ls;
+    std::vector<double> sc;
+    for (int64_t s = off[t]; s < off[t + 1]; ++s) {
+      const double *l = lines + 7 * s;
+      Line3d x(V3D(l[0], l[1], l[2]), V3D(l[3], l[4], l[5]));
+      x.uncertainty = l[6];
+      ls.push_back(x);
+      sc.push_back(scores[s]);
+    }
+    double *o = out + 7 * t;
+    if (ls.empty()) { memset(o, 0, 7 * sizeof(double)); continue; }
+    Line3d r = merging::Aggregator::aggregate_line3d_list(ls, sc, num_outliers);
+    o[0] = r.start[0]; o[1] = r.start[1]; o[2] = r.start[2]; o[3] = r.end[0]; o[4] = r.end[1]; o[5] = r.end[2];
+    o[6] = r.uncertainty;
+  }
+  return 0;
+}
+
+void ref_minimal_from_line(const double *line, double *out6) {
+  MinimalInfiniteLine3d ml(Line3d(V3D(line[0], line[1], line[2]), V3D(line[3], line[4], line[5])));
+  for (int i = 0; i < 4; ++i) out6[i] = ml.uvec[i];
+  out6[4] = ml.wvec[0]; out6[5] = ml.wvec[1];
+}
+void ref_infinite_from_minimal(const double *x6, double *d3, double *m3) {
+  MinimalInfiniteLine3d ml(std::vector<double>(x6, x6 + 6));
+  InfiniteLine3d inf = ml.GetInfiniteLine();
+  for (int i = 0; i < 3; ++i) { d3[i] = inf.d[i]; m3[i] = inf.m[i]; }
+}
+// GetLineSegmentFromInfiniteLine3d(inf_line(x6), line3ds, num_outliers) (base/infinite_line.cc:265-287)
+void ref_segment_from_minimal(const double *x6, const double *line3d, int64_t n, int num_outliers, double *out6) {
+  MinimalInfiniteLine3d ml(std::vector<double>(x6, x6 + 6));
+  std::vector<Line3d> ls;
+  for (int64_t k = 0; k < n; ++k) ls.push_back(Line3d(V3D(line3d[6 * k], line3d[6 * k + 1], line3d[6 * k + 2]),
+                                                     V3D(line3d[6 * k + 3], line3d[6 * k + 4], line3d[6 * k + 5])));
+  Line3d r = GetLineSegmentFromInfiniteLine3d(ml.GetInfiniteLine(), ls, num_outliers);
+  for (int i = 0; i < 3; ++i) { out6[i] = r.start[i]; out6[3 + i] = r.end[i]; }
+}
+
+// CheckReprojection / CheckSensitivity / overlap bits per supporting line (merging_utils.cc:27-155), layout as in
+// orc_track_support_flags.
+int ref_track_support_flags(int32_t n_views, const int32_t *model_ids, const double *kvec, const double *qvec,
+                            const double *tvec, int64_t T, const int64_t *sup_off, const int32_t *sup_view,
+                            const double *segs, const double *track_line, double th_angular2d, double th_perp2d,
+                            double th_sv_angular3d, double th_overlap, uint8_t *out_flags) {
+  std::map<int, Camera> cams;
+  std::map<int, CameraImage> imgs;
+  for (int v = 0; v < n_views; ++v) {
+    const double *k = kvec + 4 * v;
+    const int model = model_ids ? model_ids[v] : 1;
+    std::vector<double> params;
+    if (model == 0) params = {k[0], k[2], k[3]};
+    else params = {k[0], k[1], k[2], k[3]};
+    cams[v] = Camera(model, params, v);
+    imgs[v] = CameraImage(v, CameraPose(V4D(qvec[4 * v], qvec[4 * v + 1], qvec[4 * v + 2], qvec[4 * v + 3]),
+                                        V3D(tvec[3 * v], tvec[3 * v + 1], tvec[3 * v + 2])));
+  }
+  ImageCollection imagecols(cams, imgs);
+  for (int64_t t = 0; t < T; ++t) {
+    LineTrack tr;
+    const double *tl = track_line + 6 * t;
+    tr.line = Line3d(V3D(tl[0], tl[1], tl[2]), V3D(tl[3], tl[4], tl[5]));
+    for (int64_t s = sup_off[t]; s < sup_off[t + 1]; ++s) {
+      tr.image_id_list.push_back(sup_view[s]);
+      tr.line_id_list.push_back((int)(s - sup_off[t]));
+      tr.line2d_list.push_back(mk2(segs + 4 * s));
+    }
+    std::vector<bool> rep, sens;
+    merging::CheckReprojection(rep, tr, imagecols, th_angular2d, th_perp2d);
+    merging::CheckSensitivity(sens, tr, imagecols, th_sv_angular3d);
+    for (int64_t s = sup_off[t]; s < sup_off[t + 1]; ++s) {
+      const size_t k = (size_t)(s - sup_off[t]);
+      uint8_t f = 0;
+      if (rep[k]) f |= 1;
+      if (sens[k]) f |= 2;
+      // FilterTracksByOverlap (merging_utils.cc:143-150)
+      Line2d proj = tr.line.projection(imagecols.camview(sup_view[s]));
+      if (compute_overlap<Line2d>(proj, tr.line2d_list[k]) >= th_overlap) f |= 4;
+      out_flags[s] = f;
+    }
+  }
+  return 0;
+}
+
+// RemergeLineTracks (merging/merging.cc:513-645) on tracks that carry only their 3D line (+uncertainty) and active flag:
+// out_labels[t] = index of the output track that absorbed input track t is not recoverable from the reference's return
+// value, so the comparison is on the PARTITION: out_group[t] = smallest input index merged with t.
+int64_t ref_remerge_groups(int64_t T, const double *track_line, const uint8_t *active, const ref_linker_cfg *c,
+                           int32_t *out_group) {
+  std::vector<LineTrack> tracks((size_t)T);
+  for (int64_t t = 0; t < T; ++t) {
+    const double *l = track_line + 7 * t;
+    tracks[t].line = Line3d(V3D(l[0], l[1], l[2]), V3D(l[3], l[4], l[5]));
+    tracks[t].line.uncertainty = l[6];
+    tracks[t].active = active[t] != 0;
+    // one supporting line per track, tagged with the input index, so that the merged tracks tell the partition
+    tracks[t].image_id_list.push_back((int)t);
+    tracks[t].line_id_list.push_back(0);
+    tracks[t].line2d_list.push_back(Line2d(V2D(0, 0), V2D(1, 1)));
+    tracks[t].line3d_list.push_back(tracks[t].line);
+    tracks[t].score_list.push_back(1.0);
+    tracks[t].node_id_list.push_back((int)t);
+  }
+  LineLinker3d linker3d(to_linker3d(*c));
+  std::vector<LineTrack> out = merging::RemergeLineTracks(tracks, linker3d, 0);
+  for (const LineTrack &o : out) {
+    int mn = o.image_id_list.empty() ? -1 : o.image_id_list[0];
+    for (int i : o.image_id_list) mn = std::min(mn, i);
+    for (int i : o.image_id_list) out_group[i] = mn;
+  }
+  return (int64_t)out.size();
+}
+
+} // extern "C"

@@ -1,0 +1,313 @@
+"""Pins the oracle (oracle/*.h, the restatement every GPU parity test compares against) to the REFERENCE'S OWN
+COMPILED CODE: oracle/_ref/liblimap_ref.so holds the reference's hot-path sources built unchanged from /root/reference
+(oracle/Makefile target `ref`; Eigen / COLMAP / glog / PoseLib come from the header shims in oracle/ref_shim/).
+
+  * whole pipeline: limap::triangulation::GlobalLineTriangulator (Init -> TriangulateImage -> ComputeLineTracks) against
+    OracleTri on seeded scenes and every configuration family the GPU tests use -- candidate lists, scores, valid
+    connections, best candidates, graph-ordered track membership bit-exact, coordinates to 1e-9;
+  * function level on 2e4..1e5 random inputs each: compute_epipolar_IoU, triangulate_line (plane pair and endpoints),
+    triangulate_line_with_direction, LineLinker2d/3d::compute_score, Line3d::sensitivity / computeUncertainty,
+    CameraView::projection / ray_direction, Aggregator::aggregate_line3d_list, MinimalInfiniteLine3d,
+    GetLineSegmentFromInfiniteLine3d, CheckReprojection / CheckSensitivity / overlap, RemergeLineTracks;
+  * the frozen golden fixtures (tests/golden/hotpath) are reproduced by the reference's compiled code.
+Skipped when the library is absent (it can only be built where /root/reference exists)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from limap_b200.config import DEFAULT_YAML_TRIANGULATION
+from limap_b200.synth import make_scene
+
+from parity_utils import compare_nodes, compare_tracks
+
+from oracle import oracle as orc
+from oracle import ref
+
+if ref.can_build():
+    ref.build()
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref is built only where /root/reference exists")
+
+TOL = 1e-9
+
+
+def _run(sc, cfg, exhaustive=False, ranges=True, vp=None):
+    o, r = orc.OracleTri(cfg, threads=1), ref.RefTri(cfg, threads=1)
+    for t in (o, r):
+        t.upload(sc)
+        if ranges:
+            t.set_ranges(*sc.ranges)
+        if vp is not None:
+            t.set_vps(vp, sc.img_ids, sc.line_off)
+        for i in sc.img_ids:
+            if exhaustive:
+                t.add_image_exhaustive(int(i), sc.neighbors[int(i)])
+            else:
+                t.add_image_matches(int(i), *sc.flat_matches(int(i)))
+    return o, r
+
+
+def _cfg(**kw):
+    c = dict(DEFAULT_YAML_TRIANGULATION, debug_mode=True)
+    c.update(kw)
+    return c
+
+
+def _vps(sc, seed):
+    rng = np.random.default_rng(seed)
+    out = {}
+
+    class R:
+        pass
+    for v, i in enumerate(sc.img_ids):
+        L = int(sc.line_off[v + 1] - sc.line_off[v])
+        q = rng.normal(size=(3, 3))
+        q[:, :2] *= 1000.0
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        lab = rng.integers(0, 3, L)
+        lab[rng.random(L) < 0.4] = -1
+        r = R()
+        r.labels, r.vps = lab.astype(np.int32), q
+        out[int(i)] = r
+    return out
+
+
+CASES = {
+    "default_yaml": (dict(V=8, L=120, N=5, K=6, seed=201), {}, {}),
+    "cpp_defaults_outer_edge_filter": (dict(V=8, L=120, N=5, K=5, seed=202), None, {}),
+    "asset_units_gaps_shuffled": (dict(V=8, L=100, N=5, K=4, seed=203, scale=100.0, id_stride=7, shuffle_rows=True), {}, {}),
+    "mixed_cameras": (dict(V=8, L=100, N=5, K=5, seed=204, camera_mix=True), {}, {}),
+    "endpoints_halfpix_no_ranges": (dict(V=6, L=80, N=4, K=4, seed=205), dict(use_endpoints_triangulation=True, add_halfpix=True), dict(ranges=False)),
+    "max_valid_conns": (dict(V=6, L=60, N=5, K=8, seed=206), dict(max_valid_conns=3), {}),
+    "exhaustive": (dict(V=5, L=40, N=3, K=2, seed=207), {}, dict(exhaustive=True)),
+    "vp_proposals": (dict(V=6, L=60, N=4, K=3, seed=208), dict(use_vp=True), dict(vp=9)),
+    "innerseg_2d_linker": (dict(V=6, L=80, N=4, K=4, seed=209), dict(linker2d_config=dict(use_innerseg=True, th_innerseg=3.0)), {}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_whole_pipeline_oracle_equals_compiled_reference(name, capfd):
+    kw, over, run = CASES[name]
+    sc = make_scene(**kw)
+    cfg = dict(debug_mode=True) if over is None else _cfg(**over)
+    run = dict(run)
+    if "vp" in run:
+        run["vp"] = _vps(sc, run["vp"])
+    o, r = _run(sc, cfg, **run)
+    import parity_utils
+    old = parity_utils.ENDPOINT_TOL, parity_utils.SCORE_TOL
+    parity_utils.ENDPOINT_TOL, parity_utils.SCORE_TOL = 1e-7 * (100.0 if kw.get("scale") else 1.0), 1e-9
+    try:
+        st = compare_nodes(sc, r, o, debug=True)  # candidate lists in reference order, scores, valid connections, best
+        assert st["candidates"] > 200 and st["valid_edges"] > 20
+        tr = compare_tracks(r, o)
+        assert tr["tracks"] > 5 and tr["exact_order"]
+    finally:
+        parity_utils.ENDPOINT_TOL, parity_utils.SCORE_TOL = old
+
+
+# ---- function level --------------------------------------------------------------------------------------------
+def _rand_cam(rng, mixed=True):
+    f = rng.uniform(400, 900)
+    model = int(rng.integers(0, 2)) if mixed else 0
+    fy = f * rng.uniform(0.9, 1.1) if model == 1 else f
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    return orc.cam_array(model, [f, fy, rng.uniform(300, 500), rng.uniform(200, 400)], q, rng.normal(size=3) * 3)
+
+
+def _look_at_cam(rng, target, dist):
+    from limap_b200.synth import _rot_to_quat
+    c = target + dist * (lambda v: v / np.linalg.norm(v))(rng.normal(size=3))
+    z = (target - c) / np.linalg.norm(target - c)
+    x = np.cross(z, rng.normal(size=3))
+    x /= np.linalg.norm(x)
+    R = np.stack([x, np.cross(z, x), z], 0)
+    f = rng.uniform(500, 800)
+    return orc.cam_array(0, [f, f, 400, 300], _rot_to_quat(R), -R @ c), R, -R @ c, f
+
+
+def _proj(R, t, f, X):
+    Xc = R @ X + t
+    return Xc[:2] / Xc[2] * f + np.array([400.0, 300.0])
+
+
+def _pairs_of_views(rng, n):
+    """(l1, cam1, l2, cam2): projections of a random 3D segment into two looking-at cameras, with pixel noise."""
+    out = []
+    for _ in range(n):
+        X0, X1 = rng.uniform(-2, 2, 3), rng.uniform(-2, 2, 3)
+        c1, R1, t1, f1 = _look_at_cam(rng, (X0 + X1) / 2, rng.uniform(6, 12))
+        c2, R2, t2, f2 = _look_at_cam(rng, (X0 + X1) / 2, rng.uniform(6, 12))
+        l1 = np.concatenate([_proj(R1, t1, f1, X0), _proj(R1, t1, f1, X1)]) + rng.normal(scale=1.0, size=4)
+        l2 = np.concatenate([_proj(R2, t2, f2, X0), _proj(R2, t2, f2, X1)]) + rng.normal(scale=1.0, size=4)
+        out.append((np.ascontiguousarray(l1), c1, np.ascontiguousarray(l2), c2))
+    return out
+
+
+def _close(a, b, tol=TOL):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.all((np.abs(a - b) <= tol * (1 + np.abs(b))) | (np.isnan(a) & np.isnan(b)))
+
+
+def test_two_view_functions_on_random_pairs():
+    rng = np.random.default_rng(301)
+    L, R = orc.lib(), ref.lib()
+    L.orc_triangulate_line_with_direction.argtypes = [C.c_void_p] * 6
+    p = orc._p
+    n_ok = 0
+    for l1, c1, l2, c2 in _pairs_of_views(rng, 20000):
+        a = L.orc_compute_epipolar_IoU(p(l1), p(c1), p(l2), p(c2))
+        b = R.ref_compute_epipolar_IoU(p(l1), p(c1), p(l2), p(c2))
+        assert _close(a, b), (a, b)
+        for by_end in (0, 1):
+            oa, ob = np.zeros(9), np.zeros(9)
+            L.orc_triangulate_line(p(l1), p(c1), p(l2), p(c2), by_end, p(oa))
+            R.ref_triangulate_line(p(l1), p(c1), p(l2), p(c2), by_end, p(ob))
+            assert oa[8] == ob[8]  # score: 1 on success, -1 on failure -- the same decision
+            if ob[8] > 0:
+                assert _close(oa, ob, 1e-8), (oa, ob)
+                n_ok += 1
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        oa, ob = np.zeros(9), np.zeros(9)
+        L.orc_triangulate_line_with_direction(p(l1), p(c1), p(l2), p(c2), p(d), p(oa))
+        R.ref_triangulate_line_with_direction(p(l1), p(c1), p(l2), p(c2), p(d), p(ob))
+        assert oa[8] == ob[8]
+        if ob[8] > 0:
+            assert _close(oa, ob, 1e-8)
+    assert n_ok > 20000
+
+
+def test_camera_and_line3d_functions():
+    rng = np.random.default_rng(302)
+    L, R = orc.lib(), ref.lib()
+    for f in ("orc_line3d_sensitivity", "orc_line3d_uncertainty"):
+        getattr(L, f).restype = C.c_double
+    L.orc_line3d_sensitivity.argtypes = [C.c_void_p] * 2
+    L.orc_line3d_uncertainty.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+    L.orc_ray_direction.argtypes = [C.c_void_p] * 3
+    p = orc._p
+    for _ in range(50000):
+        cam = _rand_cam(rng)
+        X = rng.normal(size=3) * 5
+        a, b = np.zeros(2), np.zeros(2)
+        L.orc_project_point(p(cam), p(X), p(a))
+        R.ref_project_point(p(cam), p(X), p(b))
+        assert _close(a, b, 1e-9)
+        px = rng.uniform(0, 800, 2)
+        ra, rb = np.zeros(3), np.zeros(3)
+        L.orc_ray_direction(p(cam), p(px), p(ra))
+        R.ref_ray_direction(p(cam), p(px), p(rb))
+        assert _close(ra, rb, 1e-12)
+        l3 = np.concatenate([rng.normal(size=6) * 3, rng.uniform(1, 9, 2), [0.1]])
+        assert _close(L.orc_line3d_sensitivity(p(l3), p(cam)), R.ref_line3d_sensitivity(p(l3), p(cam)), 1e-9)
+        assert _close(L.orc_line3d_uncertainty(p(l3), p(cam), 2.0), R.ref_line3d_uncertainty(p(l3), p(cam), 2.0), 1e-12)
+
+
+def test_linker_scores_on_random_pairs():
+    rng = np.random.default_rng(303)
+    L, R = orc.lib(), ref.lib()
+    p = orc._p
+    variants = [dict(), dict(use_perp=1, use_innerseg=0), dict(use_scaleinv=1, use_overlap=0, use_innerseg=0),
+                dict(use_innerseg=1, use_perp=1, use_scaleinv=1), dict(use_angle=0, use_smartangle=0)]
+    n_pos = 0
+    for k in range(100000):
+        v = dict(variants[k % len(variants)])
+        v.update(score_th=0.5, th_angle=rng.uniform(3, 12), th_overlap=rng.uniform(0.01, 0.2), th_smartoverlap=0.25,
+                 th_smartangle=1.0, th_perp=rng.uniform(0.5, 3), th_innerseg=rng.uniform(0.5, 3), th_scaleinv=0.05)
+        cfg = ref.linker_cfg(v)
+        # 2D: a segment and a noisy, shifted, maybe flipped copy
+        a = rng.uniform(0, 600, 4)
+        d = (a[2:] - a[:2]) / np.linalg.norm(a[2:] - a[:2])
+        s = rng.uniform(-0.5, 0.5, 2) * np.linalg.norm(a[2:] - a[:2])
+        b = np.concatenate([a[:2] + d * s[0], a[2:] + d * s[1]]) + rng.normal(scale=rng.choice([0.3, 3.0]), size=4)
+        if rng.random() < 0.5:
+            b = b[[2, 3, 0, 1]]
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        x, y = L.orc_score_2d(C.byref(cfg), p(a), p(b)), R.ref_score_2d(C.byref(cfg), p(a), p(b))
+        assert _close(x, y, 1e-9), (v, x, y)
+        # 3D: start3, end3, depths2, uncertainty
+        A = np.concatenate([rng.normal(size=6) * 2, rng.uniform(2, 9, 2), [rng.uniform(0.01, 0.2)]])
+        dd = (A[3:6] - A[:3]) / np.linalg.norm(A[3:6] - A[:3])
+        B = A.copy()
+        B[:3] += dd * rng.uniform(-0.5, 0.5) + rng.normal(scale=rng.choice([0.005, 0.1]), size=3)
+        B[3:6] += dd * rng.uniform(-0.5, 0.5) + rng.normal(scale=rng.choice([0.005, 0.1]), size=3)
+        x, y = L.orc_score_3d(C.byref(cfg), p(A), p(B)), R.ref_score_3d(C.byref(cfg), p(A), p(B))
+        assert _close(x, y, 1e-9), (v, x, y)
+        n_pos += (y > 0)
+    assert n_pos > 10000
+
+
+def test_aggregator_minimal_line_and_segment_cut():
+    rng = np.random.default_rng(304)
+    L, R = orc.lib(), ref.lib()
+    L.orc_minimal_from_line.argtypes = [C.c_void_p] * 2
+    L.orc_infinite_from_minimal.argtypes = [C.c_void_p] * 3
+    L.orc_segment_from_minimal.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    p = orc._p
+    # aggregate_line3d_list: groups of 1..12 noisy copies of a segment
+    sizes = rng.integers(1, 13, 20000)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    base = rng.normal(size=(len(sizes), 6)) * 3
+    lines = np.repeat(base, sizes, 0) + rng.normal(scale=0.02, size=(off[-1], 6))
+    lines = np.concatenate([lines, rng.uniform(0.01, 0.3, (off[-1], 1))], 1)
+    scores = rng.uniform(0, 5, off[-1])
+    for no in (0, 2):
+        ok = sizes * 2 - 1 - no >= no
+        o2 = np.concatenate([[0], np.cumsum(sizes[ok])]).astype(np.int64)
+        sel = np.repeat(ok, sizes)
+        a = orc.aggregate_lines(o2, lines[sel], scores[sel], no)
+        b = ref.aggregate_lines(o2, lines[sel], scores[sel], no)
+        d = np.minimum(np.abs(a[:, :6] - b[:, :6]).max(1), np.abs(a[:, :6] - b[:, [3, 4, 5, 0, 1, 2]]).max(1))
+        assert d.max() < 1e-8 and np.abs(a[:, 6] - b[:, 6]).max() == 0
+    # MinimalInfiniteLine3d round trip + segment cut
+    for _ in range(20000):
+        line = rng.normal(size=6) * 4
+        xa, xb = np.zeros(6), np.zeros(6)
+        L.orc_minimal_from_line(p(line), p(xa))
+        R.ref_minimal_from_line(p(line), p(xb))
+        assert _close(xa, xb, 1e-9) or _close(np.concatenate([-xa[:4], xa[4:]]), xb, 1e-9)  # q == -q
+        da, ma, db, mb = np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(3)
+        L.orc_infinite_from_minimal(p(xb), p(da), p(ma))
+        R.ref_infinite_from_minimal(p(xb), p(db), p(mb))
+        assert _close(da, db, 1e-12) and _close(ma, mb, 1e-10)
+        n = int(rng.integers(2, 9))
+        l3 = np.ascontiguousarray(np.tile(line, (n, 1)) + rng.normal(scale=0.05, size=(n, 6)))
+        sa, sb = np.zeros(6), np.zeros(6)
+        L.orc_segment_from_minimal(p(xb), p(l3), n, 1, p(sa))
+        R.ref_segment_from_minimal(p(xb), p(l3), n, 1, p(sb))
+        assert _close(sa, sb, 1e-9)
+
+
+def test_track_filters_and_remerge():
+    from limap_b200.synth import make_track_lines, make_tracks
+    ts = make_tracks(T=400, S=10, V=40, seed=305, noise_px=2.0)
+    views, first = np.unique(ts.img_ids, return_index=True)
+    remap = np.zeros(int(views.max()) + 1, np.int32)
+    remap[views] = np.arange(len(views), dtype=np.int32)
+    rng = np.random.default_rng(305)
+    tl = ts.gt + rng.normal(scale=0.03, size=ts.gt.shape)
+    a = (None, ts.kvec[first], ts.qvec[first], ts.tvec[first], ts.sup_off, remap[ts.img_ids], ts.segs, tl)
+    for kw in (dict(), dict(th_angular_2d=2.0, th_perp_2d=1.0, th_sv_angular_3d=60.0, th_overlap=0.9)):
+        fa, fb = orc.track_support_flags(*a, **kw), ref.track_support_flags(*a, **kw)
+        assert np.array_equal(fa, fb) and 0 < (fa == 7).sum() < len(fa)
+    lk = dict(score_th=0.5, th_angle=5.0, th_overlap=0.001, th_smartoverlap=0.1, th_smartangle=1.0, th_perp=1.0, th_innerseg=1.0)
+    TL = make_track_lines(3000, dup_frac=0.4, seed=7, extent=8.0)
+    for act in (np.ones(3000, np.uint8), (rng.random(3000) < 0.7).astype(np.uint8)):
+        labels, ng, ne = orc.remerge_labels(TL, act, lk, threads=1)
+        group, n_out = ref.remerge_groups(TL, act, lk)
+        # same partition: oracle labels <-> reference groups are in bijection
+        pairs = set(zip(labels.tolist(), group.tolist()))
+        assert len(pairs) == len(set(labels.tolist())) == len(set(group.tolist())) == ng == n_out
+        assert ng < 3000
+
+
+def test_golden_fixtures_are_reproduced_by_the_compiled_reference():
+    import test_golden_hotpath as g
+    for name in g.TRI:
+        z, cfg = g._load(name)
+        r = ref.RefTri(cfg, threads=1)
+        g._feed(r, z)
+        g._check_tri(r, z)
