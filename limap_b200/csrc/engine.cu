@@ -204,6 +204,8 @@ struct lm_ctx {
   DevBuf d_ba_in, d_ba_blocks, d_ba_out;
   DevBuf d_vp_pts, d_vp_off, d_vp_labels, d_vp_nc, d_vp_ps, d_vp_mat;
   lm_ba_stats ba_stats;
+  void *h_ba_pin = nullptr; // pinned landing pad of lm_ba_solve's results
+  size_t h_ba_pin_cap = 0;
   lm_vp_stats vp_stats;
   DevBuf d_vp_idx;
   // track filters / remerge
@@ -329,6 +331,7 @@ void lm_ctx_destroy(lm_ctx *c) {
   for (auto e : c->event_pool) cudaEventDestroy(e);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->h_pin) cudaFreeHost(c->h_pin);
+  if (c->h_ba_pin) cudaFreeHost(c->h_ba_pin);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1672,38 +1675,22 @@ int lm_ba_solve(lm_ctx *c, int32_t n_views, const double *kvec, const double *qv
   const int64_t n = sup_off[T];
   for (int64_t k = 0; k < n; ++k)
     if (sup_view[k] < 0 || sup_view[k] >= n_views) return fail(LM_ERR_INVALID, "support view index out of range");
-  // host prologue: minimal parameterisation of every start line, constant-track flags
-  std::vector<double> x0(6 * std::max<int64_t>(T, 1));
-  std::vector<uint8_t> active(std::max<int64_t>(T, 1));
-  std::vector<int32_t> tmp;
-  for (int64_t t = 0; t < T; ++t) {
-    if (sup_off[t + 1] > sup_off[t]) {
-      const double *l = line_init + 6 * t;
-      const double len2 = (l[0] - l[3]) * (l[0] - l[3]) + (l[1] - l[4]) * (l[1] - l[4]) + (l[2] - l[5]) * (l[2] - l[5]);
-      if (!(len2 > 0)) return fail(LM_ERR_INVALID, "track with a zero-length 3D line (CHECK_GT(line.length(), 0))");
-    }
-    minimal_from_line(line_init + 6 * t, &x0[6 * t]);
-    tmp.assign(sup_view + sup_off[t], sup_view + sup_off[t + 1]);
-    std::sort(tmp.begin(), tmp.end());
-    const int n_img = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
-    active[t] = n_img >= cfg->min_num_images; // ParameterizeLines (hybrid_bundle_adjustment.cc:106-123)
-  }
   // device input arena: [kvec | qvec | tvec | segs | x0 | sup_off | sup_view | active]
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   const size_t o_k = take(32 * n_views), o_q = take(32 * n_views), o_t = take(24 * n_views), o_s = take(32 * n),
                o_x = take(48 * T), o_so = take(8 * (T + 1)), o_sv = take(4 * n), o_a = take(T),
-               o_vp = take(sup_vp ? 24 * n : 0), o_l3 = take((line3d && out_line) ? 48 * n : 0);
+               o_vp = take(sup_vp ? 24 * n : 0), o_l3 = take((line3d && out_line) ? 48 * n : 0), o_li = take(48 * T),
+               o_err = take(32);
   CU(c->d_ba_in.ensure(off + 256));
   char *in = c->d_ba_in.as<char>();
   CU(cudaMemcpyAsync(in + o_k, kvec, 32 * n_views, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(in + o_q, qvec, 32 * n_views, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(in + o_t, tvec, 24 * n_views, cudaMemcpyHostToDevice, s));
   if (n) CU(cudaMemcpyAsync(in + o_s, segs, 32 * n, cudaMemcpyHostToDevice, s));
-  if (T) CU(cudaMemcpyAsync(in + o_x, x0.data(), 48 * T, cudaMemcpyHostToDevice, s));
+  if (T) CU(cudaMemcpyAsync(in + o_li, line_init, 48 * T, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(in + o_so, sup_off, 8 * (T + 1), cudaMemcpyHostToDevice, s));
   if (n) CU(cudaMemcpyAsync(in + o_sv, sup_view, 4 * n, cudaMemcpyHostToDevice, s));
-  if (T) CU(cudaMemcpyAsync(in + o_a, active.data(), T, cudaMemcpyHostToDevice, s));
   if (sup_vp && n) CU(cudaMemcpyAsync(in + o_vp, sup_vp, 24 * n, cudaMemcpyHostToDevice, s));
   const bool dev_seg = line3d && out_line && n;
   if (dev_seg) CU(cudaMemcpyAsync(in + o_l3, line3d, 48 * n, cudaMemcpyHostToDevice, s));
@@ -1715,6 +1702,12 @@ int lm_ba_solve(lm_ctx *c, int32_t n_views, const double *kvec, const double *qv
   CU(c->d_ba_out.ensure(oo + 256));
   char *out = c->d_ba_out.as<char>();
   CU(cudaEventRecord(c->ev0, s));
+  // per-track prologue on the device: minimal parameterisation of the start lines, constant-track flags
+  lm::launch_zero_words(in + o_err, 8, s);
+  lm::launch_lm_prologue(reinterpret_cast<const double *>(in + o_li), reinterpret_cast<const int64_t *>(in + o_so),
+                         reinterpret_cast<const int32_t *>(in + o_sv), T, cfg->min_num_images,
+                         reinterpret_cast<double *>(in + o_x), reinterpret_cast<uint8_t *>(in + o_a),
+                         reinterpret_cast<int *>(in + o_err), s);
   lm::launch_lm_prepare(reinterpret_cast<const double *>(in + o_s), reinterpret_cast<const int32_t *>(in + o_sv),
                         reinterpret_cast<const double *>(in + o_k), reinterpret_cast<const double *>(in + o_q),
                         reinterpret_cast<const double *>(in + o_t),
@@ -1732,6 +1725,7 @@ int lm_ba_solve(lm_ctx *c, int32_t n_views, const double *kvec, const double *qv
   p.term = reinterpret_cast<int32_t *>(out + oo_t);
   p.line3d = dev_seg ? reinterpret_cast<const double *>(in + o_l3) : nullptr;
   p.seg_out = dev_seg ? reinterpret_cast<double *>(out + oo_s) : nullptr;
+  p.next_track = reinterpret_cast<unsigned long long *>(in + o_err + 16);
   p.num_outliers = cfg->num_outliers;
   p.T = T;
   p.geometric_alpha = cfg->geometric_alpha;
@@ -1741,20 +1735,35 @@ int lm_ba_solve(lm_ctx *c, int32_t n_views, const double *kvec, const double *qv
   lm::launch_lm_refine(p, s);
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->evk1, s));
-  std::vector<double> xf(6 * std::max<int64_t>(T, 1)), cost(2 * std::max<int64_t>(T, 1));
-  std::vector<int32_t> iters(2 * std::max<int64_t>(T, 1));
-  std::vector<double> segd(dev_seg ? 6 * std::max<int64_t>(T, 1) : 0);
+  // results land in a pinned staging area of the context (a pageable destination would serialise the copies)
+  const size_t T1 = (size_t)std::max<int64_t>(T, 1);
+  const size_t need_pin = T1 * (48 + 16 + 8 + 48) + 64;
+  if (need_pin > c->h_ba_pin_cap) {
+    if (c->h_ba_pin) cudaFreeHost(c->h_ba_pin);
+    c->h_ba_pin = nullptr;
+    c->h_ba_pin_cap = 0;
+    CU(cudaHostAlloc(&c->h_ba_pin, need_pin + need_pin / 4, cudaHostAllocDefault));
+    c->h_ba_pin_cap = need_pin + need_pin / 4;
+  }
+  double *xf = reinterpret_cast<double *>(c->h_ba_pin);
+  double *cost = xf + 6 * T1;
+  double *segd = cost + 2 * T1;
+  int32_t *iters = reinterpret_cast<int32_t *>(segd + 6 * T1);
+  int *h_err = reinterpret_cast<int *>(iters + 2 * T1);
+  *h_err = 0;
   if (T) {
-    if (dev_seg) CU(cudaMemcpyAsync(segd.data(), out + oo_s, 48 * T, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(xf.data(), out + oo_x, 48 * T, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(iters.data(), out + oo_i, 8 * T, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(cost.data(), out + oo_c, 16 * T, cudaMemcpyDeviceToHost, s));
+    if (dev_seg) CU(cudaMemcpyAsync(segd, out + oo_s, 48 * T, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(xf, out + oo_x, 48 * T, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(iters, out + oo_i, 8 * T, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(cost, out + oo_c, 16 * T, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_err, in + o_err, 4, cudaMemcpyDeviceToHost, s));
   }
   CU(cudaStreamSynchronize(s));
+  if (*h_err) return fail(LM_ERR_INVALID, "track with a zero-length 3D line (CHECK_GT(line.length(), 0))");
   float ms0 = 0, ms1 = 0;
   CU(cudaEventElapsedTime(&ms0, c->ev0, c->evk0));
   CU(cudaEventElapsedTime(&ms1, c->evk0, c->evk1));
-  c->stats.n_kernel_launches += 2;
+  c->stats.n_kernel_launches += 4;
   c->ba_stats.n_tracks = T;
   c->ba_stats.n_blocks = n;
   c->ba_stats.prepare_ms = ms0;

@@ -20,7 +20,9 @@
 // per evaluation per track with 4-wide duals, and each lane carries 3-wide duals from m_c to the residual.
 // The solver restates Ceres' trust-region LM (DESIGN.md "LM recipe" lists the steps and their provenance).
 #include "lm_kernels.cuh"
+#include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 namespace lm {
 
@@ -104,6 +106,12 @@ LM_D void sphere2_plus(const double x[2], double delta, double out[2]) {
 struct LineLocal {
   Dual<4> d[3], m[3];
 };
+// The same, laid out for shared memory (one per warp): every lane evaluates a different residual block against the
+// same line, so the line and its 24 tangent derivatives are warp-uniform -- kept here, not in 60 registers per lane.
+struct LineShared {
+  double d[3], m[3];
+  double dv[3][4], mv[3][4];
+};
 LM_D void line_from_minimal(const double x[6], bool want_jac, LineLocal &L) {
   // ambient duals (6-wide) would be wasteful: seed the 4 local directions directly through the plus Jacobians
   Dual<4> u[4], w[2];
@@ -148,13 +156,13 @@ struct BlockEval {
 };
 
 // One residual block: from (d, m) to the two cosine-weighted point-line distances.
-LM_D void eval_block(const LMBlockDev &B, const LineLocal &L, double alpha, bool want_jac, BlockEval &o) {
+LM_D void eval_block(const LMBlockDev &B, const LineShared &L, double alpha, bool want_jac, BlockEval &o) {
   // m_c = R m + t x (R d)   (Line_WorldToPixel, matrix form R [m]x R^T - t (Rd)^T + (Rd) t^T)
   double Rd[3], Rm[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    Rd[i] = B.R[3 * i] * L.d[0].a + B.R[3 * i + 1] * L.d[1].a + B.R[3 * i + 2] * L.d[2].a;
-    Rm[i] = B.R[3 * i] * L.m[0].a + B.R[3 * i + 1] * L.m[1].a + B.R[3 * i + 2] * L.m[2].a;
+    Rd[i] = B.R[3 * i] * L.d[0] + B.R[3 * i + 1] * L.d[1] + B.R[3 * i + 2] * L.d[2];
+    Rm[i] = B.R[3 * i] * L.m[0] + B.R[3 * i + 1] * L.m[1] + B.R[3 * i + 2] * L.m[2];
   }
   const double mc[3] = {Rm[0] + (B.t[1] * Rd[2] - B.t[2] * Rd[1]), Rm[1] + (B.t[2] * Rd[0] - B.t[0] * Rd[2]),
                         Rm[2] + (B.t[0] * Rd[1] - B.t[1] * Rd[0])};
@@ -205,8 +213,8 @@ LM_D void eval_block(const LMBlockDev &B, const LineLocal &L, double alpha, bool
     double rd[3], rm[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      rd[i] = B.R[3 * i] * L.d[0].v[c] + B.R[3 * i + 1] * L.d[1].v[c] + B.R[3 * i + 2] * L.d[2].v[c];
-      rm[i] = B.R[3 * i] * L.m[0].v[c] + B.R[3 * i + 1] * L.m[1].v[c] + B.R[3 * i + 2] * L.m[2].v[c];
+      rd[i] = B.R[3 * i] * L.dv[0][c] + B.R[3 * i + 1] * L.dv[1][c] + B.R[3 * i + 2] * L.dv[2][c];
+      rm[i] = B.R[3 * i] * L.mv[0][c] + B.R[3 * i + 1] * L.mv[1][c] + B.R[3 * i + 2] * L.mv[2][c];
     }
     const double g0 = rm[0] + (B.t[1] * rd[2] - B.t[2] * rd[1]);
     const double g1 = rm[1] + (B.t[2] * rd[0] - B.t[0] * rd[2]);
@@ -223,29 +231,59 @@ struct Normal {
   double cost;
 };
 
+// Per-warp solver state in shared memory. One warp owns one track; everything below is warp-uniform, so it lives here
+// instead of in every lane's registers (the kernel used to need 255 registers, i.e. 8 warps per SM).
+struct WarpState {
+  LineShared L;
+  double x[6], cand[6], scale[4], diag[4];
+  Normal N;  // at x
+  Normal Nc; // at the candidate point
+  double cn2[4];
+};
+
 // Evaluate the whole track at x: cost (always) and, if want_jac, the loss-corrected normal equations with the
-// Jacobi column scaling applied (scale may be NULL -> unscaled, used to initialise the scaling).
-LM_D void eval_track(const LMBlockDev *blocks, int S, const double x[6], double alpha, double bq, bool want_jac,
-                     const double *scale, Normal &N, double colnorm2[4]) {
-  LineLocal L;
-  line_from_minimal(x, want_jac, L);
+// Jacobi column scaling applied (scale may be NULL -> unscaled, used to initialise the scaling). Results go to *out
+// (and column norms to cn2_out) in shared memory; every lane may read them after the trailing __syncwarp.
+// `acc` = this thread's column of the CTA's accumulator table ([19][kLmThreads] doubles in shared memory: the partial
+// sums of J^T J (10), J^T r (4), cost (1), column norms (4) stay out of the registers while a block is evaluated).
+static constexpr int kLmThreads = 128;
+LM_D void eval_track(const LMBlockDev *blocks, int S, const double *x, double alpha, double bq, bool want_jac,
+                     const double *scale, LineShared &Ls, Normal *out, double *cn2_out, double *acc) {
   const int lane = threadIdx.x & 31;
-  double A[10], g[4], cost = 0, cn2[4] = {0, 0, 0, 0};
+  {
+    double xr[6];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) A[i] = 0;
+    for (int i = 0; i < 6; ++i) xr[i] = x[i];
+    LineLocal L;
+    line_from_minimal(xr, want_jac, L); // redundantly on every lane (same instruction count as on one)
+    __syncwarp();
+    if (lane == 0) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) g[i] = 0;
+      for (int i = 0; i < 3; ++i) {
+        Ls.d[i] = L.d[i].a; Ls.m[i] = L.m[i].a;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { Ls.dv[i][c] = L.d[i].v[c]; Ls.mv[i][c] = L.m[i].v[c]; }
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < 19; ++i) acc[i * kLmThreads] = 0.0;
   const double cq = 1.0 / bq;
   for (int k = lane; k < S; k += 32) {
-    const LMBlockDev B = blocks[k];
+    const LMBlockDev &B = blocks[k];
     BlockEval e;
-    eval_block(B, L, alpha, want_jac, e);
+    eval_block(B, Ls, alpha, want_jac, e);
+    const double Bw = B.w, Bwvp = B.wvp;
     // ScaledLoss(CauchyLoss, w) + ceres Corrector
     const double s = e.r[0] * e.r[0] + e.r[1] * e.r[1];
     const double sum = 1.0 + s * cq, inv = 1.0 / sum;
-    const double rho0 = B.w * bq * log(sum), rho1 = B.w * fmax(DBL_MIN, inv), rho2 = B.w * (-cq * (inv * inv));
-    cost += 0.5 * rho0;
-    if (B.wvp > 0.0) cost += 0.5 * B.wvp * e.rv * e.rv; // ScaledLoss(TrivialLoss, w * vp_multiplier)
+    const double rho0 = Bw * bq * log(sum), rho1 = Bw * fmax(DBL_MIN, inv), rho2 = Bw * (-cq * (inv * inv));
+    {
+      double cost = 0.5 * rho0;
+      if (Bwvp > 0.0) cost += 0.5 * Bwvp * e.rv * e.rv; // ScaledLoss(TrivialLoss, w * vp_multiplier)
+      acc[14 * kLmThreads] += cost;
+    }
     if (!want_jac) continue;
     const double sqrt_rho1 = sqrt(rho1);
     double residual_scaling = sqrt_rho1, alpha_sq_norm = 0.0;
@@ -264,36 +302,44 @@ LM_D void eval_track(const LMBlockDev *blocks, int S, const double x[6], double 
         J0[c] = sqrt_rho1 * (e.J[c] - alpha_sq_norm * e.r[0] * rtj);
         J1[c] = sqrt_rho1 * (e.J[4 + c] - alpha_sq_norm * e.r[1] * rtj);
       }
-      cn2[c] += J0[c] * J0[c] + J1[c] * J1[c];
+      acc[(15 + c) * kLmThreads] += J0[c] * J0[c] + J1[c] * J1[c];
       if (scale) { J0[c] *= scale[c]; J1[c] *= scale[c]; }
     }
     const double r0 = e.r[0] * residual_scaling, r1 = e.r[1] * residual_scaling;
     double J2[4] = {0, 0, 0, 0}, r2 = 0.0;
-    if (B.wvp > 0.0) {
-      const double sq = sqrt(B.wvp);
+    if (Bwvp > 0.0) {
+      const double sq = sqrt(Bwvp);
       r2 = sq * e.rv;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         J2[c] = sq * e.Jv[c];
-        cn2[c] += J2[c] * J2[c];
+        acc[(15 + c) * kLmThreads] += J2[c] * J2[c];
         if (scale) J2[c] *= scale[c];
       }
     }
     int idx = 0;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      g[a] += J0[a] * r0 + J1[a] * r1 + J2[a] * r2;
+      acc[(10 + a) * kLmThreads] += J0[a] * r0 + J1[a] * r1 + J2[a] * r2;
 #pragma unroll
-      for (int b = a; b < 4; ++b) A[idx++] += J0[a] * J0[b] + J1[a] * J1[b] + J2[a] * J2[b];
+      for (int b = a; b < 4; ++b) { acc[idx * kLmThreads] += J0[a] * J0[b] + J1[a] * J1[b] + J2[a] * J2[b]; ++idx; }
     }
   }
-  N.cost = warp_sum(cost);
+  {
+    const double cost = warp_sum(acc[14 * kLmThreads]);
+    if (lane == 0) out->cost = cost;
+  }
   if (want_jac) {
 #pragma unroll
-    for (int i = 0; i < 10; ++i) N.A[i] = warp_sum(A[i]);
+    for (int i = 0; i < 10; ++i) { const double v = warp_sum(acc[i * kLmThreads]); if (lane == 0) out->A[i] = v; }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { N.g[i] = warp_sum(g[i]); if (colnorm2) colnorm2[i] = warp_sum(cn2[i]); }
+    for (int i = 0; i < 4; ++i) {
+      const double v = warp_sum(acc[(10 + i) * kLmThreads]);
+      if (lane == 0) out->g[i] = v;
+      if (cn2_out) { const double w = warp_sum(acc[(15 + i) * kLmThreads]); if (lane == 0) cn2_out[i] = w; }
+    }
   }
+  __syncwarp();
 }
 
 LM_D bool chol_solve4(const double Au[10], const double dg[4], const double b[4], double x[4]) {
@@ -329,40 +375,51 @@ LM_D bool chol_solve4(const double Au[10], const double dg[4], const double b[4]
   return true;
 }
 
-__global__ void __launch_bounds__(128) lm_refine_kernel(const __grid_constant__ LMParams p) {
+// MB = resident CTAs per SM the register allocation is bounded for (2: 255 registers, 3: 168, 4: 128).
+template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(const __grid_constant__ LMParams p) {
+  __shared__ WarpState s_ws[4];
+  __shared__ double s_acc[19 * kLmThreads];
+  double *acc = s_acc + threadIdx.x;
   const int warp_in_block = threadIdx.x >> 5;
-  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
-  if (t >= p.T) return;
   const int lane = threadIdx.x & 31;
+  // Persistent warps: a warp fetches its next track when it is done. Solves take 10..max_num_iterations iterations, so a
+  // static one-track-per-warp grid leaves every CTA slot waiting for its slowest track.
+  for (;;) {
+  long long t = 0;
+  if (lane == 0) t = (long long)atomicAdd(p.next_track, 1ull);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t >= p.T) break;
   const int64_t s0 = p.sup_off[t];
   const int S = (int)(p.sup_off[t + 1] - s0);
   const LMBlockDev *blocks = p.blocks + s0;
-  double x[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) x[i] = p.x0[6 * t + i];
+  WarpState &ws = s_ws[warp_in_block];
+  if (lane < 6) ws.x[lane] = p.x0[6 * t + lane];
+  __syncwarp();
   const double bq = p.cauchy_scale * p.cauchy_scale;
-  Normal N;
-  double cn2[4];
   int it = 0, successful = 0, term = 0;
   double cost0, cost;
   if (S == 0 || !p.active[t]) {
-    eval_track(blocks, S, x, p.geometric_alpha, bq, false, nullptr, N, nullptr);
-    cost0 = cost = N.cost;
+    eval_track(blocks, S, ws.x, p.geometric_alpha, bq, false, nullptr, ws.L, &ws.N, nullptr, acc);
+    cost0 = cost = ws.N.cost;
   } else {
     // iteration 0: evaluate, fix the Jacobi scaling 1/(1+||J_col||)
-    eval_track(blocks, S, x, p.geometric_alpha, bq, true, nullptr, N, cn2);
-    double scale[4];
+    eval_track(blocks, S, ws.x, p.geometric_alpha, bq, true, nullptr, ws.L, &ws.N, ws.cn2, acc);
+    if (lane == 0) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) scale[c] = 1.0 / (1.0 + sqrt(cn2[c]));
-    {
+      for (int c = 0; c < 4; ++c) ws.scale[c] = 1.0 / (1.0 + sqrt(ws.cn2[c]));
       int idx = 0;
 #pragma unroll
-      for (int a = 0; a < 4; ++a) { N.g[a] *= scale[a];
+      for (int a = 0; a < 4; ++a) {
+        ws.N.g[a] *= ws.scale[a];
 #pragma unroll
-        for (int b = a; b < 4; ++b) N.A[idx++] *= scale[a] * scale[b]; }
+        for (int b = a; b < 4; ++b) ws.N.A[idx++] *= ws.scale[a] * ws.scale[b];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ws.diag[c] = 0.0;
     }
-    cost0 = cost = N.cost;
-    double radius = 1e4, decrease_factor = 2.0, diag[4] = {0, 0, 0, 0};
+    __syncwarp();
+    cost0 = cost = ws.N.cost;
+    double radius = 1e4, decrease_factor = 2.0;
     bool reuse_diagonal = false;
     int invalid = 0;
     while (true) {
@@ -371,33 +428,45 @@ __global__ void __launch_bounds__(128) lm_refine_kernel(const __grid_constant__ 
       {
         double gmax = 0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) gmax = fmax(gmax, fabs(N.g[c] / scale[c]));
+        for (int c = 0; c < 4; ++c) gmax = fmax(gmax, fabs(ws.N.g[c] / ws.scale[c]));
         if (gmax <= 0.0) { term = 3; break; }
       }
       ++it;
-      const double dgi[4] = {N.A[0], N.A[4], N.A[7], N.A[9]};
-      if (!reuse_diagonal)
+      if (!reuse_diagonal) {
+        __syncwarp();
+        if (lane == 0) {
+          const double dgi[4] = {ws.N.A[0], ws.N.A[4], ws.N.A[7], ws.N.A[9]};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) diag[c] = fmin(fmax(dgi[c], 1e-6), 1e32);
-      reuse_diagonal = true;
-      double dg[4], step[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) dg[c] = diag[c] / radius;
-      bool ok = chol_solve4(N.A, dg, N.g, step);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) { step[c] = -step[c]; if (!isfinite(step[c])) ok = false; }
-      double mcc = 0;
-      if (ok) {
-        // model_cost_change = -(step . g + step^T (J^T J) step / 2)
-        double sg = 0, sAs = 0;
-        int idx = 0;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          sg += step[a] * N.g[a];
-#pragma unroll
-          for (int b = a; b < 4; ++b) { sAs += ((a == b) ? 1.0 : 2.0) * step[a] * step[b] * N.A[idx]; ++idx; }
+          for (int c = 0; c < 4; ++c) ws.diag[c] = fmin(fmax(dgi[c], 1e-6), 1e32);
         }
-        mcc = -(sg + 0.5 * sAs);
+        __syncwarp();
+      }
+      reuse_diagonal = true;
+      // the 4x4 solve is warp-uniform: every lane computes it from the shared state (no divergence, no extra issue slots)
+      double step[4];
+      bool ok;
+      double mcc = 0;
+      {
+        double An[10], gn[4], dg[4];
+#pragma unroll
+        for (int c = 0; c < 10; ++c) An[c] = ws.N.A[c];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { gn[c] = ws.N.g[c]; dg[c] = ws.diag[c] / radius; }
+        ok = chol_solve4(An, dg, gn, step);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { step[c] = -step[c]; if (!isfinite(step[c])) ok = false; }
+        if (ok) {
+          // model_cost_change = -(step . g + step^T (J^T J) step / 2)
+          double sg = 0, sAs = 0;
+          int idx = 0;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            sg += step[a] * gn[a];
+#pragma unroll
+            for (int b = a; b < 4; ++b) { sAs += ((a == b) ? 1.0 : 2.0) * step[a] * step[b] * An[idx]; ++idx; }
+          }
+          mcc = -(sg + 0.5 * sAs);
+        }
       }
       if (!ok || !(mcc > 0.0)) {
         if (++invalid >= p.max_invalid) { term = 4; break; }
@@ -405,24 +474,39 @@ __global__ void __launch_bounds__(128) lm_refine_kernel(const __grid_constant__ 
         continue;
       }
       invalid = 0;
-      double delta[4], cand[6];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) delta[c] = step[c] * scale[c];
-      quat_plus(x, delta, cand);
-      sphere2_plus(x + 4, delta[3], cand + 4);
-      Normal Nc;
-      eval_track(blocks, S, cand, p.geometric_alpha, bq, false, nullptr, Nc, nullptr);
       double sn = 0;
+      {
+        double xr[6], delta[4], cand[6];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) sn += (x[c] - cand[c]) * (x[c] - cand[c]);
+        for (int c = 0; c < 6; ++c) xr[c] = ws.x[c];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) delta[c] = step[c] * ws.scale[c];
+        quat_plus(xr, delta, cand);
+        sphere2_plus(xr + 4, delta[3], cand + 4);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) sn += (xr[c] - cand[c]) * (xr[c] - cand[c]);
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) ws.cand[c] = cand[c];
+        }
+        __syncwarp();
+      }
+      // One evaluation per iteration: the candidate point is evaluated WITH its Jacobian; if the step is accepted the
+      // normal equations are already there (a second evaluation at the same point would reproduce them bit for bit:
+      // the value parts of the duals do not depend on want_jac).
+      eval_track(blocks, S, ws.cand, p.geometric_alpha, bq, true, ws.scale, ws.L, &ws.Nc, nullptr, acc);
+      const double cost_c = ws.Nc.cost;
       if (!(sqrt(sn) > 0.0)) { term = 5; break; }
-      if (!(fabs(cost - Nc.cost) > 0.0)) { term = 6; break; }
-      const double rel = (cost - Nc.cost) / mcc;
+      if (!(fabs(cost - cost_c) > 0.0)) { term = 6; break; }
+      const double rel = (cost - cost_c) / mcc;
       if (rel > 1e-3) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) x[c] = cand[c];
-        eval_track(blocks, S, x, p.geometric_alpha, bq, true, scale, N, nullptr);
-        cost = N.cost;
+        __syncwarp();
+        if (lane < 6) ws.x[lane] = ws.cand[lane];
+        if (lane < 10) ws.N.A[lane] = ws.Nc.A[lane];
+        if (lane < 4) ws.N.g[lane] = ws.Nc.g[lane];
+        __syncwarp();
+        cost = cost_c;
         const double tq = 2.0 * rel - 1.0;
         radius = radius / fmax(1.0 / 3.0, 1.0 - tq * tq * tq);
         radius = fmin(1e16, radius);
@@ -433,6 +517,10 @@ __global__ void __launch_bounds__(128) lm_refine_kernel(const __grid_constant__ 
       }
     }
   }
+  __syncwarp();
+  double x[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = ws.x[i];
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) p.x_out[6 * t + i] = x[i];
@@ -450,7 +538,7 @@ __global__ void __launch_bounds__(128) lm_refine_kernel(const __grid_constant__ 
                     n2 - 1 - p.num_outliers >= 0;
     if (!ok) {
       if (lane < 6) p.seg_out[6 * t + lane] = __longlong_as_double(0x7ff8000000000000ll);
-      return;
+      continue;
     }
     // limap QuaternionToRotationMatrix (base/pose.cc:12-18): normalised quaternion
     double q[4];
@@ -487,7 +575,9 @@ __global__ void __launch_bounds__(128) lm_refine_kernel(const __grid_constant__ 
       if (rank == ka) { p.seg_out[6 * t] = pr0 + d0 * v; p.seg_out[6 * t + 1] = pr1 + d1 * v; p.seg_out[6 * t + 2] = pr2 + d2 * v; }
       if (rank == kb) { p.seg_out[6 * t + 3] = pr0 + d0 * v; p.seg_out[6 * t + 4] = pr1 + d1 * v; p.seg_out[6 * t + 5] = pr2 + d2 * v; }
     }
+    __syncwarp(); // vals[] is reused by the warp's next track
   }
+  } // track loop
 }
 
 // supports -> digested blocks: R from qvec via ceres::QuaternionToRotation (normalising), loss weight |seg|/30
@@ -523,6 +613,91 @@ __global__ void lm_prepare_blocks_kernel(const double *__restrict__ segs, const 
   out[k] = B;
 }
 
+// Per-track prologue on the device (one thread per track): the minimal parameterisation of the start line
+// (MinimalInfiniteLine3d(InfiniteLine3d(Line3d)), base/infinite_line.cc:67-71,180-218; Q -> quaternion as Eigen's
+// Quaterniond(Matrix3d) does) and the constant-track flag of ParameterizeLines (hybrid_bundle_adjustment.cc:106-123:
+// tracks seen in fewer than min_num_images distinct images keep their parameter blocks constant).
+__global__ void lm_track_prologue_kernel(const double *__restrict__ line_init, const int64_t *__restrict__ sup_off,
+                                         const int32_t *__restrict__ sup_view, int64_t T, int min_num_images,
+                                         double *__restrict__ x0, uint8_t *__restrict__ active, int *__restrict__ err) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const double *l = line_init + 6 * t;
+  double out[6];
+  {
+    double sx = l[0], sy = l[1], sz = l[2];
+    double ax = l[3] - sx, ay = l[4] - sy, az = l[5] - sz;
+    const double an2 = ax * ax + ay * ay + az * az;
+    if (!(an2 > 0) && sup_off[t + 1] > sup_off[t]) *err = 1; // CHECK_GT(line.length(), 0)
+    if (an2 > 0) { const double an = sqrt(an2); ax /= an; ay /= an; az /= an; } // direction() = normalized()
+    const double bx = sy * az - sz * ay, by = sz * ax - sx * az, bz = sx * ay - sy * ax; // m = p x d
+    const double bn = sqrt(bx * bx + by * by + bz * bz);
+    const double den = sqrt(1.0 + bn * bn);
+    out[4] = 1.0 / den;
+    out[5] = bn / den;
+    const double na = sqrt(ax * ax + ay * ay + az * az);
+    const double q0x = ax / na, q0y = ay / na, q0z = az / na;
+    double q1x, q1y, q1z, q2x, q2y, q2z;
+    if (bn > 1e-12) {
+      q1x = bx / bn; q1y = by / bn; q1z = bz / bn;
+      const double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+      const double cn = sqrt(cx * cx + cy * cy + cz * cz);
+      q2x = cx / cn; q2y = cy / cn; q2z = cz / cn;
+    } else {
+      const double av[3] = {ax, ay, az};
+      int best = 0;
+      if (fabs(av[1]) > fabs(av[0])) best = 1;
+      if (fabs(av[2]) > fabs(av[best])) best = 2;
+      const int i1 = (best + 1) % 3, i2 = (best + 2) % 3;
+      double bp[3];
+      bp[i1] = 1.0; bp[i2] = 1.0; bp[best] = -(av[i1] * bp[i1] + av[i2] * bp[i2]) / av[best];
+      const double pn = sqrt(bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
+      q1x = bp[0] / pn; q1y = bp[1] / pn; q1z = bp[2] / pn;
+      const double cx = ay * bp[2] - az * bp[1], cy = az * bp[0] - ax * bp[2], cz = ax * bp[1] - ay * bp[0];
+      const double cn = sqrt(cx * cx + cy * cy + cz * cz);
+      q2x = cx / cn; q2y = cy / cn; q2z = cz / cn;
+    }
+    const double R[3][3] = {{q0x, q1x, q2x}, {q0y, q1y, q2y}, {q0z, q1z, q2z}};
+    double tr = R[0][0] + R[1][1] + R[2][2];
+    if (tr > 0) {
+      tr = sqrt(tr + 1.0);
+      out[0] = 0.5 * tr;
+      tr = 0.5 / tr;
+      out[1] = (R[2][1] - R[1][2]) * tr; out[2] = (R[0][2] - R[2][0]) * tr; out[3] = (R[1][0] - R[0][1]) * tr;
+    } else {
+      int i = 0;
+      if (R[1][1] > R[0][0]) i = 1;
+      if (R[2][2] > R[i][i]) i = 2;
+      const int j = (i + 1) % 3, k = (j + 1) % 3;
+      tr = sqrt(R[i][i] - R[j][j] - R[k][k] + 1.0);
+      double v[3];
+      v[i] = 0.5 * tr;
+      tr = 0.5 / tr;
+      out[0] = (R[k][j] - R[j][k]) * tr;
+      v[j] = (R[j][i] + R[i][j]) * tr;
+      v[k] = (R[k][i] + R[i][k]) * tr;
+      out[1] = v[0]; out[2] = v[1]; out[3] = v[2];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x0[6 * t + i] = out[i];
+  // distinct images among the supports (tracks are short: quadratic scan)
+  const int64_t a = sup_off[t], b = sup_off[t + 1];
+  int n_img = 0;
+  for (int64_t k = a; k < b && n_img < min_num_images; ++k) {
+    const int v = sup_view[k];
+    bool seen = false;
+    for (int64_t q = a; q < k; ++q) if (sup_view[q] == v) { seen = true; break; }
+    n_img += !seen;
+  }
+  active[t] = n_img >= min_num_images;
+}
+void launch_lm_prologue(const double *line_init, const int64_t *sup_off, const int32_t *sup_view, int64_t T,
+                        int min_num_images, double *x0, uint8_t *active, int *err, cudaStream_t s) {
+  if (T <= 0) return;
+  lm_track_prologue_kernel<<<(int)((T + 127) / 128), 128, 0, s>>>(line_init, sup_off, sup_view, T, min_num_images, x0, active, err);
+}
+
 void launch_lm_prepare(const double *segs, const int32_t *sup_view, const double *kvec, const double *qvec,
                        const double *tvec, const double *sup_vp, double vp_multiplier, int64_t n, LMBlockDev *out,
                        cudaStream_t s) {
@@ -533,7 +708,14 @@ void launch_lm_prepare(const double *segs, const int32_t *sup_view, const double
 void launch_lm_refine(const LMParams &p, cudaStream_t s) {
   if (p.T <= 0) return;
   const int warps = 4;
-  lm_refine_kernel<<<(int)((p.T + warps - 1) / warps), warps * 32, 0, s>>>(p);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)std::min<int64_t>((p.T + warps - 1) / warps, (int64_t)sms * 4);
+  static const int mb = [] { const char *e = getenv("LIMAP_B200_LM_OCC"); return e ? atoi(e) : 2; }();
+  if (mb >= 4) lm_refine_kernel<4><<<grid, warps * 32, 0, s>>>(p);
+  else if (mb == 3) lm_refine_kernel<3><<<grid, warps * 32, 0, s>>>(p);
+  else lm_refine_kernel<2><<<grid, warps * 32, 0, s>>>(p);
 }
 
 } // namespace lm

@@ -26,6 +26,7 @@ struct LMParams {
   int32_t *term;            // [T] termination code
   const double *line3d;     // [n][6] track.line3d_list (start, end) or NULL
   double *seg_out;          // [T][6] output segment cut from the refined line; NaN when left to the host
+  unsigned long long *next_track; // device counter, zero at launch: warps fetch tracks dynamically
   int num_outliers;
   int64_t T;
   double geometric_alpha, cauchy_scale;
@@ -36,5 +37,7 @@ void launch_lm_prepare(const double *segs, const int32_t *sup_view, const double
                        const double *tvec, const double *sup_vp, double vp_multiplier, int64_t n, LMBlockDev *out,
                        cudaStream_t s);
 void launch_lm_refine(const LMParams &p, cudaStream_t s);
+void launch_lm_prologue(const double *line_init, const int64_t *sup_off, const int32_t *sup_view, int64_t T,
+                        int min_num_images, double *x0, uint8_t *active, int *err, cudaStream_t s);
 
 } // namespace lm

@@ -33,10 +33,13 @@ static constexpr int kListExtra = kFlush + 32;
 // (2 x uint32); plus per warp two survivor lists (uint32) and one prefilter list (uint16)
 static constexpr int kCandBytes = 17 * 8 + 48 + 8;
 
-// fast layout: one survivor list per warp (no 2d-gate stage) and three more doubles per candidate (reciprocals)
+// Shared-memory staging per node. Generic layout: 17 doubles + 48-byte fp32 gate record + ng/row per candidate, two
+// survivor lists and one prefilter list per warp. Fast layout (reduced-form scorer, plane-pair triangulation): 20 doubles
+// (three reciprocals more), a 32-byte gate record, ng/row, the depth-sorted order (float key + uint16 index) per
+// candidate, and per warp one pair list (uint16) with its scores (double): 246 bytes per candidate slot.
 size_t tri_smem_bytes(int cap, bool fast) {
-  const size_t lists = fast ? 1 : 2, extra = fast ? 24 : 0;
-  return (size_t)cap * (kCandBytes + extra) + (size_t)kWarps * lists * (cap + kListExtra) * 4 + (size_t)kWarps * cap * 2;
+  if (fast) return (size_t)cap * (20 * 8 + kWarps * 8 + 32 + 8 + 4 + 2 + kWarps * 2);
+  return (size_t)cap * kCandBytes + (size_t)kWarps * 2 * (cap + kListExtra) * 4 + (size_t)kWarps * cap * 2;
 }
 
 // fp32 copy of a candidate for the pruning gates (three 16-byte loads, conflict-free at 48-byte stride):
@@ -48,6 +51,16 @@ struct __align__(16) GateRec {
   float ex, ey, ez, pad;
 };
 
+// Fast-path gate record. Every candidate of a node starts on the ray of the source line's start point and ends on the
+// ray of its end point (X = ray * lambda + C1 in both the plane-pair and the VP-constrained triangulation), so the
+// scale-invariant endpoint test of LineLinker3d (line_linker.cc:269-277) is an interval test on lambda: 1-D, sortable.
+struct __align__(16) GateRecF {
+  float dx, dy, dz, lam_e; // unit direction; distance of the end point along the end ray
+  float lam_s;             // distance of the start point along the start ray
+  float lim_s, lim_e;      // largest |delta lambda| that can still pass, taken as l_i (widened, see phase A)
+  int img;                 // neighbour view of the candidate
+};
+
 struct Slab {
   double *sx, *sy, *sz, *ex, *ey, *ez, *dx, *dy, *dz, *zs, *ze, *unc, *q0, *q1, *q2, *q3, *score;
   double *izs2, *ize2, *inb; // fast layout only: 1/(zs+EPS)^2, 1/(ze+EPS)^2, 1/|q|^2
@@ -55,7 +68,15 @@ struct Slab {
   uint32_t *ng, *row;
   uint32_t *list;            // [kWarps][2][cap + kListExtra]: (row << 16 | j) survivor entries
   uint16_t *list0;           // [kWarps][cap]: j of the start-point prefilter
+  // fast layout only
+  GateRecF *gatef;
+  float *slam;               // [cap] lam_s in ascending order
+  uint16_t *sidx;            // [cap] candidate of each sorted position
+  double *psc;               // [kWarps][cap] scores of a warp's pair list
+  uint16_t *pent;            // [kWarps][cap] j of a warp's pair list (rows contiguous)
   LM_D void carve(char *base, int cap, bool fast) {
+    if (fast) { carve_fast(base, cap); return; }
+    gatef = nullptr; slam = nullptr; sidx = nullptr; psc = nullptr; pent = nullptr;
     double *d = reinterpret_cast<double *>(base);
     sx = d; sy = sx + cap; sz = sy + cap; ex = sz + cap; ey = ex + cap; ez = ey + cap;
     dx = ez + cap; dy = dx + cap; dz = dy + cap; zs = dz + cap; ze = zs + cap; unc = ze + cap;
@@ -69,11 +90,27 @@ struct Slab {
     list = row + cap;
     list0 = reinterpret_cast<uint16_t *>(list + (size_t)kWarps * (fast ? 1 : 2) * (cap + kListExtra));
   }
+  LM_D void carve_fast(char *base, int cap) {
+    double *d = reinterpret_cast<double *>(base);
+    sx = d; sy = sx + cap; sz = sy + cap; ex = sz + cap; ey = ex + cap; ez = ey + cap;
+    dx = ez + cap; dy = dx + cap; dz = dy + cap; zs = dz + cap; ze = zs + cap; unc = ze + cap;
+    q0 = unc + cap; q1 = q0 + cap; q2 = q1 + cap; q3 = q2 + cap; score = q3 + cap;
+    izs2 = score + cap; ize2 = izs2 + cap; inb = ize2 + cap;
+    psc = inb + cap;                                              // byte 160 cap
+    gatef = reinterpret_cast<GateRecF *>(psc + (size_t)kWarps * cap); // byte 192 cap
+    ng = reinterpret_cast<uint32_t *>(gatef + cap);               // byte 224 cap
+    row = ng + cap;
+    slam = reinterpret_cast<float *>(row + cap);                  // byte 232 cap
+    sidx = reinterpret_cast<uint16_t *>(slam + cap);              // byte 236 cap
+    pent = sidx + cap;                                            // byte 238 cap, [kWarps][cap]
+    gate = nullptr; list = nullptr; list0 = nullptr;
+  }
 };
 
 struct Cand {
   vec3<double> s, e;
   double zs, ze, unc;
+  double lam_s, lam_e; // s = ray1s * lam_s + C1, e = ray1e * lam_e + C1 (not set by endpoint triangulation)
 };
 
 LM_D double4 ld_seg(const double4 *p) {
@@ -219,6 +256,8 @@ LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const Src &src, uin
     Xs = src.ray1s * ls.x + src.C1;
     const vec3<double> le = solve3_cols(src.ray1e, nb, nc, B);
     Xe = src.ray1e * le.x + src.C1;
+    c.lam_s = ls.x;
+    c.lam_e = le.x;
     c.zs = v1.P[8] * Xs.x + v1.P[9] * Xs.y + v1.P[10] * Xs.z + v1.P[11];
     c.ze = v1.P[8] * Xe.x + v1.P[9] * Xe.y + v1.P[10] * Xe.z + v1.P[11];
     if (c.zs < EPS || c.ze < EPS) return false;
@@ -233,6 +272,7 @@ LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const Src &src, uin
     if (!triangulate_point(v1, v2, src.ray1e, r2e, src.C1, C2, Xe)) return false;
     c.zs = v1.P[8] * Xs.x + v1.P[9] * Xs.y + v1.P[10] * Xs.z + v1.P[11];
     c.ze = v1.P[8] * Xe.x + v1.P[9] * Xe.y + v1.P[10] * Xe.z + v1.P[11];
+    c.lam_s = c.lam_e = 0.0;
   }
   // sensitivity in both views (:315-317)
   const vec3<double> dir_raw = Xe - Xs;
@@ -279,6 +319,8 @@ LM_D bool gen_vp_candidate(const TriParams &p, const ViewD &v1, const ViewD &v2,
   const double d1s = (c1 + c2) * b / (c1 * c1 + c2 * c2);
   const double d1e = d1s * a1s / a1e;
   const vec3<double> Xs = src.ray1s * d1s + src.C1, Xe = src.ray1e * d1e + src.C1;
+  c.lam_s = d1s;
+  c.lam_e = d1e;
   c.zs = v1.P[8] * Xs.x + v1.P[9] * Xs.y + v1.P[10] * Xs.z + v1.P[11];
   c.ze = v1.P[8] * Xe.x + v1.P[9] * Xe.y + v1.P[10] * Xe.z + v1.P[11];
   if (c.zs < EPS || c.ze < EPS) return false;
@@ -530,9 +572,9 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
   Slab sl;
   if (SLAB) sl.carve(p.slab + (int64_t)blockIdx.x * p.slab_stride, p.cap, FAST);
   else sl.carve(reinterpret_cast<char *>(smem_raw), p.cap, FAST);
-  uint32_t *list1 = sl.list + (size_t)(warp * (FAST ? 1 : 2)) * (p.cap + kListExtra);
-  uint32_t *list2 = FAST ? list1 : list1 + p.cap + kListExtra;
-  uint16_t *list0 = sl.list0 + (size_t)warp * p.cap;
+  uint32_t *list1 = FAST ? nullptr : sl.list + (size_t)(warp * 2) * (p.cap + kListExtra);
+  uint32_t *list2 = FAST ? nullptr : list1 + p.cap + kListExtra;
+  uint16_t *list0 = FAST ? nullptr : sl.list0 + (size_t)warp * p.cap;
   unsigned long long n1_total = 0, n2_total = 0;
 
   for (int64_t node = p.node_begin + blockIdx.x; node < p.node_end; node += gridDim.x) {
@@ -635,19 +677,34 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         }
         sl.ng[idx] = ng;
         sl.row[idx] = (uint32_t)r * NS + k;
-        // fp32 gate copy, relative to the source camera centre (keeps |coord| ~ depth)
-        const vec3<double> rs = c.s - src.C1, re = c.e - src.C1;
-        // scale-invariance limit th * (z + EPS) widened by 0.5% plus 1e-5 of the coordinate magnitude
-        // (fp32 rounding of the two endpoints is < 1e-6 of it); see DESIGN.md "gates"
-        const double rad = sqrt(fmax(dot(rs, rs), dot(re, re)));
-        const double ls = p.l3d.th_scaleinv * (c.zs + consts<double>::eps()) * 1.005 + 1e-5 * rad;
-        const double le = p.l3d.th_scaleinv * (c.ze + consts<double>::eps()) * 1.005 + 1e-5 * rad;
-        GateRec g;
-        g.dx = (float)d.x; g.dy = (float)d.y; g.dz = (float)d.z; g.lims2 = (float)(ls * ls * 1.000001);
-        g.sx = (float)rs.x; g.sy = (float)rs.y; g.sz = (float)rs.z; g.lime2 = (float)(le * le * 1.000001);
-        g.ex = (float)re.x; g.ey = (float)re.y; g.ez = (float)re.z;
-        g.pad = 0.f;
-        sl.gate[idx] = g;
+        if (FAST) {
+          // fp32 gate record: the endpoints as distances along the two source rays. Limits: th * (z + EPS) widened by
+          // 0.5% plus 1e-5 of the larger distance (fp32 rounding of the two lambdas and of their difference is below
+          // 2e-7 of it, |X_i - X_j| and |lambda_i - lambda_j| agree to 1e-15); see DESIGN.md "gates"
+          const double rad = fmax(fabs(c.lam_s), fabs(c.lam_e));
+          const double ls = p.l3d.th_scaleinv * (c.zs + consts<double>::eps()) * 1.005 + 1e-5 * rad;
+          const double le = p.l3d.th_scaleinv * (c.ze + consts<double>::eps()) * 1.005 + 1e-5 * rad;
+          GateRecF g;
+          g.dx = (float)d.x; g.dy = (float)d.y; g.dz = (float)d.z; g.lam_e = (float)c.lam_e;
+          g.lam_s = (float)c.lam_s; g.lim_s = (float)(ls * 1.000001); g.lim_e = (float)(le * 1.000001);
+          g.img = (int)(ng >> 16);
+          sl.gatef[idx] = g;
+          reinterpret_cast<float *>(sl.psc)[idx] = g.lam_s; // unsorted keys of the depth sort (scratch: the score lists)
+        } else {
+          // fp32 gate copy, relative to the source camera centre (keeps |coord| ~ depth)
+          const vec3<double> rs = c.s - src.C1, re = c.e - src.C1;
+          // scale-invariance limit th * (z + EPS) widened by 0.5% plus 1e-5 of the coordinate magnitude
+          // (fp32 rounding of the two endpoints is < 1e-6 of it); see DESIGN.md "gates"
+          const double rad = sqrt(fmax(dot(rs, rs), dot(re, re)));
+          const double ls = p.l3d.th_scaleinv * (c.zs + consts<double>::eps()) * 1.005 + 1e-5 * rad;
+          const double le = p.l3d.th_scaleinv * (c.ze + consts<double>::eps()) * 1.005 + 1e-5 * rad;
+          GateRec g;
+          g.dx = (float)d.x; g.dy = (float)d.y; g.dz = (float)d.z; g.lims2 = (float)(ls * ls * 1.000001);
+          g.sx = (float)rs.x; g.sy = (float)rs.y; g.sz = (float)rs.z; g.lime2 = (float)(le * le * 1.000001);
+          g.ex = (float)re.x; g.ey = (float)re.y; g.ez = (float)re.z;
+          g.pad = 0.f;
+          sl.gate[idx] = g;
+        }
         ++idx;
       }
       count += tot;
@@ -657,6 +714,178 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
     if (tid == 0) { s_nvalid = 0; s_next_row = 0; }
     __syncthreads();
     // ---------------- phase B: all-pairs scoring ------------------------------------------------
+    if constexpr (FAST) {
+      // All candidates of the node start on one ray and end on another (GateRecF), so "l_j can score against l_i"
+      // needs |lam_s(j) - lam_s(i)| <= lim_s(i): after a sort by lam_s the partners of a row are a contiguous window.
+      //   B-sort   rank sort of the candidates by lam_s (ties by index), whole CTA
+      //   per warp, 32 rows at a time (lane = row):
+      //   B-window two binary searches per row
+      //   B-gate   the other fp32 gates (end-point interval, angle, other image) over the window, twice: count, then
+      //            write -- each row's partners land contiguously in the warp's pair list, no atomics, no compaction
+      //   B-score  exact fp64 scores of the pair list, 32 pairs per step (lane = pair; rows found by a search over
+      //            the lanes' offsets)
+      //   B-sum    lane = row again: maximum per neighbour image, images added in ascending order -- the order of the
+      //            reference's std::map (:105-112), so a row's total does not depend on how the work was split.
+      // Pruned pairs would have scored exactly 0 (DESIGN.md "Exactness argument"); every surviving pair is scored by
+      // pair_score_fast in fp64.
+      const unsigned FULL = 0xffffffffu;
+      {
+        float *ltmp = reinterpret_cast<float *>(sl.psc);
+        const int C4 = (C + 3) & ~3;
+        if (tid < C4 - C) ltmp[C + tid] = __int_as_float(0x7f800000); // +inf pads: never below a key, never tie-winners
+        __syncthreads();
+        for (int i = tid; i < C; i += kThreads) {
+          const float li = ltmp[i];
+          int r = 0;
+          for (int j4 = 0; j4 < C4; j4 += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(ltmp + j4);
+            r += (v.x < li) || (v.x == li && j4 < i);
+            r += (v.y < li) || (v.y == li && j4 + 1 < i);
+            r += (v.z < li) || (v.z == li && j4 + 2 < i);
+            r += (v.w < li) || (v.w == li && j4 + 3 < i);
+          }
+          sl.slam[r] = li;
+          sl.sidx[r] = (uint16_t)i;
+        }
+        __syncthreads(); // ltmp (= the score lists) is dead from here on
+      }
+      const float *slam = sl.slam;
+      const uint16_t *sidx = sl.sidx;
+      double *psc = sl.psc + (size_t)warp * p.cap;
+      uint16_t *pent = sl.pent + (size_t)warp * p.cap;
+      for (;;) {
+        int g0 = 0;
+        if (lane == 0) g0 = atomicAdd(&s_next_row, 32);
+        g0 = __shfl_sync(FULL, g0, 0);
+        if (g0 >= C) break;
+        const int i = g0 + lane;
+        const bool act = i < C;
+        GateRecF gi;
+        gi.dx = gi.dy = gi.dz = gi.lam_e = gi.lam_s = gi.lim_s = gi.lim_e = 0.f;
+        gi.img = -1;
+        int lo = 0, W = 0;
+        if (act) {
+          const float4 a0 = *reinterpret_cast<const float4 *>(&sl.gatef[i].dx);
+          const float4 a1 = *reinterpret_cast<const float4 *>(&sl.gatef[i].lam_s);
+          gi.dx = a0.x; gi.dy = a0.y; gi.dz = a0.z; gi.lam_e = a0.w;
+          gi.lam_s = a1.x; gi.lim_s = a1.y; gi.lim_e = a1.z; gi.img = __float_as_int(a1.w);
+          int hi = C;
+          if (gi.lim_s < 3e37f) { // (false for inf / NaN limits: the whole node is the window then)
+            const float wa = gi.lam_s - gi.lim_s, wb = gi.lam_s + gi.lim_s;
+            int l = 0, h = C;
+            while (l < h) { const int m = (l + h) >> 1; if (slam[m] < wa) l = m + 1; else h = m; }
+            lo = l;
+            h = C;
+            while (l < h) { const int m = (l + h) >> 1; if (!(slam[m] > wb)) l = m + 1; else h = m; }
+            hi = l;
+          }
+          W = hi - lo;
+        }
+        int Wmax = W;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) Wmax = max(Wmax, __shfl_xor_sync(FULL, Wmax, d));
+        // B-gate: the other fp32 gates over the window; the partners of a row are remembered as a bit mask of window
+        // positions (windows of more than 64 candidates are simply re-tested when the partners are written)
+        int n = 0;
+        unsigned long long pmask = 0ull;
+        for (int t = 0; t < Wmax; ++t) {
+          if (t < W) {
+            const int j = sidx[lo + t];
+            const float4 gj = *reinterpret_cast<const float4 *>(&sl.gatef[j].dx);
+            const int imgj = sl.gatef[j].img;
+            const bool pass = (imgj != gi.img) && !(fabsf(gj.w - gi.lam_e) > gi.lim_e) &&
+                              !(fabsf(gi.dx * gj.x + gi.dy * gj.y + gi.dz * gj.z) < p.cos_th3d_f);
+            n += pass;
+            if (pass && t < 64) pmask |= 1ull << t;
+          }
+        }
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int o = __shfl_up_sync(FULL, incl, d);
+          if (lane >= d) incl += o;
+        }
+        const int off = incl - n;
+        n1_total += (unsigned long long)__shfl_sync(FULL, incl, 31);
+        // rows are taken in chunks whose partners fit the pair list (one chunk unless the node is very dense)
+        int lane_begin = 0;
+        while (lane_begin < 32) {
+          const int s0 = __shfl_sync(FULL, off, lane_begin);
+          const bool in = lane >= lane_begin && (off + n - s0) <= p.cap; // a prefix of the lanes >= lane_begin, never empty
+          const int lane_end = lane_begin + __popc(__ballot_sync(FULL, in));
+          const int total_c = __shfl_sync(FULL, incl, lane_end - 1) - s0;
+          // write the partners of every row of the chunk at the row's own offset, in ascending candidate order
+          // (= ascending neighbour image: candidates are generated image by image), by insertion: rows have few partners
+          if (in && n > 0) {
+            uint16_t *row_ent = pent + (off - s0);
+            int c = 0;
+            if (W <= 64) {
+              unsigned long long m = pmask;
+              while (m) {
+                const int t = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const uint16_t j = sidx[lo + t];
+                int pos = c;
+                while (pos > 0 && row_ent[pos - 1] > j) { row_ent[pos] = row_ent[pos - 1]; --pos; }
+                row_ent[pos] = j;
+                ++c;
+              }
+            } else {
+              const float4 a0 = *reinterpret_cast<const float4 *>(&sl.gatef[i].dx);
+              const float4 a1 = *reinterpret_cast<const float4 *>(&sl.gatef[i].lam_s);
+              for (int t = 0; t < W; ++t) {
+                const uint16_t j = sidx[lo + t];
+                const float4 gj = *reinterpret_cast<const float4 *>(&sl.gatef[j].dx);
+                const int imgj = sl.gatef[j].img;
+                if ((imgj != __float_as_int(a1.w)) && !(fabsf(gj.w - a0.w) > a1.z) &&
+                    !(fabsf(a0.x * gj.x + a0.y * gj.y + a0.z * gj.z) < p.cos_th3d_f)) {
+                  int pos = c;
+                  while (pos > 0 && row_ent[pos - 1] > j) { row_ent[pos] = row_ent[pos - 1]; --pos; }
+                  row_ent[pos] = j;
+                  ++c;
+                }
+              }
+            }
+          }
+          __syncwarp();
+          // B-score: exact reference scores, lane = pair
+          for (int fb = 0; fb < total_c; fb += 32) {
+            const int f = fb + lane;
+            int r = lane_begin; // largest row of the chunk whose offset is <= f
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+              const int cand = r + step;
+              const int v = __shfl_sync(FULL, off, cand & 31);
+              if (cand < lane_end && v - s0 <= f) r = cand;
+            }
+            if (f < total_c) {
+              const int j = pent[f];
+              psc[f] = pair_score_fast(p, sl, g0 + r, j, (uint32_t)sl.gatef[j].img);
+            }
+          }
+          n2_total += (unsigned long long)total_c;
+          __syncwarp();
+          // B-sum: one image contributes its maximum once (:110-112), images in ascending order (the partners of a row
+          // are sorted by candidate index, i.e. by image)
+          if (in && act) {
+            const int b = off - s0;
+            double sum = 0.0, mx = 0.0;
+            int cur = -1;
+            for (int e = 0; e < n; ++e) {
+              const int im = sl.gatef[pent[b + e]].img;
+              const double sc = psc[b + e];
+              if (im != cur) { sum += mx; cur = im; mx = sc; }
+              else mx = (mx > sc) ? mx : sc;
+            }
+            sum += mx;
+            sl.score[i] = sum;
+          }
+          __syncwarp();
+          lane_begin = lane_end;
+        }
+      }
+      __syncthreads();
+    } else {
     // Warps fetch rows i dynamically. B1 prunes (i, j) pairs with the fp32 3d gates and appends the
     // survivors of several rows to a warp-private list until it holds >= kFlush entries, so that the fp64
     // stages B2 (2d margin gates) and B3 (exact reference score) run on dense 32-lane batches.
@@ -799,6 +1028,7 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
       __syncwarp();
     }
     __syncthreads();
+    } // generic phase B
     // ---------------- phase C: valid connections + best candidate (:115-153) ----------------
     int nvalid_local = 0;
     for (int i = tid; i < C; i += kThreads) {
