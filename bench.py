@@ -551,8 +551,13 @@ def side_legs(args, eng, rank, world, local_rank, barrier, reduce_max, reduce_su
     views, first_idx = np.unique(ts.img_ids, return_index=True)
     remap = np.zeros(int(views.max()) + 1, np.int32)
     remap[views] = np.arange(len(views), dtype=np.int32)
-    a = (ts.kvec[first_idx], ts.qvec[first_idx], ts.tvec[first_idx], ts.sup_off, remap[ts.img_ids], ts.segs,
-         ts.line3d, ts.line_init)
+    def pin(x):  # e2e inputs live in pinned host memory (the copies inside lm_ba_solve are then real async DMA)
+        x = np.ascontiguousarray(x)
+        t = torch.empty(x.shape, dtype=torch.from_numpy(x[:0].copy()).dtype, pin_memory=True)
+        t.numpy()[...] = x
+        return t.numpy()
+    a = tuple(pin(x) for x in (ts.kvec[first_idx], ts.qvec[first_idx], ts.tvec[first_idx], ts.sup_off.astype(np.int64),
+                               remap[ts.img_ids].astype(np.int32), ts.segs, ts.line3d, ts.line_init))
     k_ms = []
 
     def solve_once():

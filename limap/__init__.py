@@ -4,7 +4,7 @@ Only the hot-path packages exist; everything else of cvg/limap is out of scope (
 import importlib
 import sys
 
-for _name in ("base", "triangulation", "optimize", "vplib", "merging", "util", "util.io"):
+for _name in ("base", "triangulation", "optimize", "vplib", "merging", "util", "util.io", "runners", "visualize", "pointsfm"):
     try:
         _m = importlib.import_module(f"limap_b200.{_name}")
     except ModuleNotFoundError:

@@ -248,6 +248,22 @@ class Camera:
     def model_name(self):
         return MODEL_NAMES[self.model_id]
 
+    def resize(self, width, height):  # colmap Camera::Rescale(width, height) (base/camera.h:69-71)
+        sx, sy = width / float(self.width), height / float(self.height)
+        self.width, self.height = int(width), int(height)
+        p = self.params
+        if self.model_id == 0:
+            self.params = [p[0] * (sx + sy) / 2.0, p[1] * sx, p[2] * sy]
+        else:
+            self.params = [p[0] * sx, p[1] * sy, p[2] * sx, p[3] * sy]
+
+    def set_max_image_dim(self, val):  # base/camera.cc:216-226
+        if val <= 0:
+            raise RuntimeError("THROW_CHECK_GT(val, 0)")
+        ratio = float(val) / float(max(self.height, self.width))
+        if ratio < 1.0:
+            self.resize(int(round(ratio * self.width)), int(round(ratio * self.height)))
+
     def kvec(self):  # base/camera_models.h:29-44 ParamsToKvec
         p = self.params
         return np.array([p[0], p[0], p[1], p[2]] if self.model_id == 0 else [p[0], p[1], p[2], p[3]])
@@ -466,6 +482,23 @@ class ImageCollection:
 
     def IsUndistorted(self):
         return all(c.IsUndistorted() for c in self.cameras.values())
+
+    def set_max_image_dim(self, val):  # base/image_collection.cc: every camera
+        for c in self.cameras.values():
+            c.set_max_image_dim(val)
+
+    def get_image_name_dict(self):
+        return {i: self.images[i].image_name() for i in self.get_img_ids()}
+
+    def update_neighbors(self, neighbors):  # base/image_collection.cc:322-342
+        if len(neighbors) == self.NumImages():
+            return neighbors
+        out = {}
+        for i in self.get_img_ids():
+            if i not in neighbors:
+                raise RuntimeError("Error! The image id is not found in the input neighbors.")
+            out[i] = [j for j in neighbors[i] if self.exist_image(j)]
+        return out
 
     def as_dict(self):
         return {"cameras": {k: v.as_dict() for k, v in self.cameras.items()},

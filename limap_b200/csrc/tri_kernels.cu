@@ -753,13 +753,15 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
       const uint16_t *sidx = sl.sidx;
       double *psc = sl.psc + (size_t)warp * p.cap;
       uint16_t *pent = sl.pent + (size_t)warp * p.cap;
-      for (;;) {
-        int g0 = 0;
-        if (lane == 0) g0 = atomicAdd(&s_next_row, 32);
-        g0 = __shfl_sync(FULL, g0, 0);
+      // rows are dealt to the warps in equal shares (C = 100: 25 rows per warp, not 32 + 32 + 32 + 4), so the warps
+      // reach the barrier before phase C together
+      const int n_pass = (C + 32 * kWarps - 1) / (32 * kWarps);
+      const int G = (C + kWarps * n_pass - 1) / (kWarps * n_pass); // rows per warp and pass, <= 32
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int g0 = (pass * kWarps + warp) * G;
         if (g0 >= C) break;
         const int i = g0 + lane;
-        const bool act = i < C;
+        const bool act = lane < G && i < C;
         GateRecF gi;
         gi.dx = gi.dy = gi.dz = gi.lam_e = gi.lam_s = gi.lim_s = gi.lim_e = 0.f;
         gi.img = -1;

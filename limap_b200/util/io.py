@@ -212,3 +212,34 @@ def read_folder_linetracks_with_info(folder):
         got.append(read_npy(f).item() if os.path.isfile(f) else None)
     cfg, ic, segs = got
     return linetracks, cfg, (base.ImageCollection(ic) if ic is not None else None), segs
+
+
+def save_txt_imname_dict(fname, imname_dict):
+    """image_list.txt: a count line, then `img_id, image_name` per image (util/io.py:157-162)."""
+    _require_parent(fname)
+    rows = [f"number of images, {len(imname_dict)}"] + [f"{i}, {n}" for i, n in imname_dict.items()]
+    with open(fname, "w") as f:
+        f.write("\n".join(rows) + "\n")
+
+
+def read_txt_imname_dict(fname):
+    _require(fname)
+    with open(fname) as f:
+        rows = [r.rstrip("\n") for r in f.readlines()]
+    n = int(rows[0].split(",")[1])
+    out = {}
+    for r in rows[1:1 + n]:
+        k, v = r.split(",", 1)
+        out[int(k)] = v.strip()
+    return out
+
+
+def save_obj(fname, lines):
+    """Wavefront .obj of 3D segments (vertices + `l` elements, util/io.py:181-199)."""
+    arr = [np.asarray(l if isinstance(l, np.ndarray) else l.as_array(), float).reshape(2, 3) for l in lines]
+    with open(fname, "w") as f:
+        for a in arr:
+            for v in a:
+                f.write(f"v {v[0]} {v[1]} {v[2]}\n")
+        for k in range(len(arr)):
+            f.write(f"l {2 * k + 1} {2 * k + 2}\n")
