@@ -423,6 +423,7 @@ def main():
         eng2 = TriEngine(cfg, device=local_rank)
         eng2.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         eng2.set_pipeline_groups(args.groups)
+        eng2.upload(scene)  # (NodeGather reads the node ranges of the shards from the uploaded scene)
         gather2 = lmdist.NodeGather(eng2, world, rank) if world > 1 else None
         h2d = (scene.segs.nbytes + scene.kvec.nbytes + scene.qvec.nbytes + scene.tvec.nbytes +
                scene.line_off.nbytes + pinned_pairs.nbytes)

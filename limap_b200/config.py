@@ -97,3 +97,35 @@ DEFAULT_YAML_TRIANGULATION = dict(
                          th_smartangle=2.0, th_perp=1.0, th_innerseg=1.0, th_scaleinv=0.015),
     use_vp=False,
 )
+
+
+def default_runner_config(**over):
+    """cfgs/triangulation/default.yaml as the runner reads it (the keys line_triangulation touches), with the
+    load_det / load_match switches on: detections and matches are artefacts on disk here, not computed."""
+    cfg = dict(
+        cfg_type="triangulation", weight_path=None, load_meta=False, load_det=True, load_match=True, load_undistort=False,
+        use_tmp=False, n_visible_views=4, n_neighbors=20, use_cuda=True, visualize=False, max_image_dim=1600,
+        skip_exists=False, output_dir=None, output_folder="finaltracks", load_dir=None, n_jobs=-1,
+        undistortion_output_dir="undistorted_images",
+        line2d=dict(max_num_2d_segs=3000, do_merge_lines=False, visualize=False, save_l3dpp=False, compute_descinfo=False,
+                    detector=dict(method="lsd", skip_exists=False), extractor=dict(method="superpoint_endpoints", skip_exists=False),
+                    matcher=dict(method="nn_endpoints", n_jobs=1, topk=10, skip_exists=False)),
+        var2d=dict(sold2=5.0, lsd=2.0, hawpv3=5.0, tp_lsd=5.0, deeplsd=4.0),
+        triangulation=dict(DEFAULT_YAML_TRIANGULATION, var2d=-1.0, use_exhaustive_matcher=False, debug_mode=False,
+                           remerging=dict(disable=False, linker3d=dict(score_th=0.5, th_angle=5.0, th_overlap=0.001,
+                                                                       th_smartoverlap=0.1, th_smartangle=1.0, th_perp=1.0,
+                                                                       th_innerseg=1.0)),
+                           filtering2d=dict(th_angular_2d=8.0, th_perp_2d=5.0, th_sv_angular_3d=75.0, th_sv_num_supports=3,
+                                            th_overlap=0.5, th_overlap_num_supports=3),
+                           use_vp=False, vpdet_config=dict(method="jlinkage", n_jobs=8, min_length=40, inlier_threshold=1.0,
+                                                           min_num_supports=10),
+                           use_pointsfm=dict(enable=False, colmap_folder=None, reuse_sfminfos_colmap=True,
+                                             use_triangulated_points=True, use_neighbors=True)),
+        refinement=dict(disable=False, constant_intrinsics=True, constant_principal_point=True, constant_pose=True,
+                        constant_line=False, min_num_images=4, num_outliers_aggregator=2, use_geometric=True,
+                        geometric_alpha=10.0, use_vp=False, vp_multiplier=0.1, use_heatmap=False, use_feature=False),
+        structures=dict(bpt2d=dict(threshold_keypoints=2.0, threshold_intersection=2.0, threshold_merge_junctions=2.0)),
+    )
+    for k, v in over.items():
+        cfg[k] = v
+    return cfg
