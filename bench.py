@@ -308,6 +308,11 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # stdout carries exactly ONE line (the JSON): everything native libraries print (NCCL's version banner goes to fd 1
+    # whatever NCCL_DEBUG_FILE says) is redirected to stderr; the line itself goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -529,7 +534,8 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "parity": parity}
         line.update(extra)
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -8,7 +8,7 @@ import numpy as np
 from .config import TriConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liblimap_b200.so")
+LIB_PATH = os.environ.get("LIMAP_B200_LIB") or os.path.join(_HERE, "lib", "liblimap_b200.so")  # (override: A/B builds)
 _lib = None
 
 

@@ -24,6 +24,15 @@ static constexpr int kThreads = 128;
 static constexpr int kWarps = kThreads / 32;
 // per-candidate staging: 17 doubles (exact fp64 data + score), 11 floats (fp32 gate copies), ng + row
 // (2 x uint32); plus two survivor lists per warp
+// Staging the neighbour views of a node in shared memory with TMA bulk copies (cp.async.bulk + mbarrier) is
+// implemented and parity-tested, and measured 3% SLOWER than the L1-cached generic loads it replaces on hypersim100
+// (same box, 5 runs each: 6.90 ms with, 6.68 ms without; profiles/r02_tri_ab.txt): the views are already L1-resident
+// (100 views x 208 B), so the copies only add a scan, two barriers per 128 rows and the mbarrier wait. Off by default
+// for the headline instantiation; the VP instantiation (three proposals per row, each reading the neighbour view) keeps
+// it on, which also keeps the path under the parity tests (test_vp_proposals, golden tri_vp_proposals).
+#ifndef LM_TRI_TMA
+#define LM_TRI_TMA 0
+#endif
 #ifndef LM_KFLUSH
 #define LM_KFLUSH 64
 #endif
@@ -107,6 +116,30 @@ struct Slab {
   }
 };
 
+// ---- TMA bulk copies (cp.async.bulk + mbarrier): the neighbour views of a node are staged in shared memory ----------
+LM_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+LM_D void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+LM_D void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+LM_D void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+LM_D void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+
 struct Cand {
   vec3<double> s, e;
   double zs, ze, unc;
@@ -178,8 +211,8 @@ LM_D bool sensitivity_exceeds(const TriParams &p, const ViewD &v, vec3<double> X
 // Unit-vector normalisations that do not change a decision or an output beyond rounding are dropped; the
 // angle / sensitivity gates use margin forms with the reference's acos form as the tie fallback.
 template <bool ALLOW_ENDP>
-LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const Src &src, uint32_t ngv, uint32_t ngl, Cand &c,
-                        double4 &l2out) {
+LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const ViewD &v2, const Src &src, uint32_t ngv, uint32_t ngl,
+                        Cand &c, double4 &l2out) {
   const double4 l2 = ld_seg(&p.segs[p.line_off[ngv] + ngl]);
   l2out = l2;
   const vec2<double> s2 = mk2(l2.x, l2.y), e2 = mk2(l2.z, l2.w);
@@ -193,7 +226,6 @@ LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const Src &src, uin
     }
   }
   if (p.disable_algebraic) return false;
-  const ViewD &v2 = p.views[ngv];
   const vec3<double> c2s = mat3_mul_h(v2.M, l2.x, l2.y);
   const vec3<double> c2e = mat3_mul_h(v2.M, l2.z, l2.w);
   // getNormalDirection (functions.cc:28-35) + ray-plane angle tests (:292-302):
@@ -567,6 +599,12 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
   __shared__ int s_wtot[kWarps];
   __shared__ int s_nvalid;
   __shared__ int s_next_row;
+  __shared__ __align__(8) unsigned long long s_mbar; // completion of the neighbour-view bulk copies of a node
+  uint32_t mbar_parity = 0;
+  if constexpr (FAST && !SLAB && (LM_TRI_TMA || VP)) {
+    if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
+    __syncthreads();
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   Slab sl;
@@ -588,6 +626,52 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
       continue;
     }
     // ---------------- phase A: candidate generation with stable compaction -----------------
+    // ---- neighbour views of the node -> shared memory. Rows are ordered by neighbour view, so a new view starts where
+    // the view index changes; the thread that sees the change issues one 208-byte TMA bulk copy (cp.async.bulk,
+    // completion on an mbarrier) into the view's slot. Phase A then reads K|R|t-derived blocks from shared memory
+    // instead of chasing row -> view index -> global view record. The staging area aliases the phase-B score lists.
+    const ViewD *sviews = nullptr;
+    const uint8_t *slot_of_row = nullptr;
+    int n_stage = 0;
+    if constexpr (FAST && !SLAB && (LM_TRI_TMA || VP)) {
+      const int stage_off = p.cap * 4; // the depth-sort keys written by phase A come first
+      ViewD *sv = reinterpret_cast<ViewD *>(reinterpret_cast<char *>(sl.psc) + stage_off);
+      uint8_t *slots = reinterpret_cast<uint8_t *>(sl.sidx); // [nrows <= cap]; rewritten by the depth sort afterwards
+      const int stage_cap = min(255, (int)(((size_t)kWarps * p.cap * 8 - stage_off) / sizeof(ViewD)));
+      int carry = 0;
+      for (int base = 0; base < nrows; base += kThreads) {
+        const int r = base + tid;
+        uint32_t view = 0;
+        int flag = 0;
+        if (r < nrows) {
+          view = __ldg(&p.row_ng[r0 + r]) >> 16;
+          flag = (r == 0) || ((__ldg(&p.row_ng[r0 + r - 1]) >> 16) != view);
+        }
+        int incl = flag;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          if (w < warp) woff += s_wtot[w];
+          tot += s_wtot[w];
+        }
+        const int slot = carry + woff + incl - 1;
+        if (r < nrows) slots[r] = (uint8_t)min(slot, 255);
+        if (flag && slot < stage_cap) bulk_copy_g2s(sv + slot, p.views + view, (uint32_t)sizeof(ViewD), &s_mbar);
+        carry += tot;
+        __syncthreads();
+      }
+      n_stage = min(carry, stage_cap);
+      if (tid == 0) mbar_arrive_expect_tx(&s_mbar, (uint32_t)(n_stage * sizeof(ViewD)));
+      sviews = sv;
+      slot_of_row = slots; // (the copies are awaited after the source-line constants below: their latency is hidden)
+    }
     const uint32_t v1i = p.node_view[node];
     const ViewD &v1 = p.views[v1i];
     Src src;
@@ -601,6 +685,10 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
       src.ray1e = normalized(src.w1e);
       src.C1 = mk3(v1.C[0], v1.C[1], v1.C[2]);
       src.n1 = normalized(cross(src.w1s, src.w1e));
+    }
+    if constexpr (FAST && !SLAB && (LM_TRI_TMA || VP)) {
+      mbar_wait(&s_mbar, mbar_parity);
+      mbar_parity ^= 1u;
     }
     int count = 0;
     for (int base = 0; base < nrows; base += kThreads) {
@@ -619,7 +707,12 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
           const double4 l2v = ld_seg(&p.segs[p.line_off[ngv] + ngl]);
           const double ddx = l2v.x - l2v.z, ddy = l2v.y - l2v.w;
           if (!(sqrt(ddx * ddx + ddy * ddy) <= p.min_length_2d) && !p.disable_vp) {
-            const ViewD &v2 = p.views[ngv];
+            const ViewD *v2q = &p.views[ngv];
+            if constexpr (FAST && !SLAB && (LM_TRI_TMA || VP)) {
+              const int slot = slot_of_row[r];
+              if (slot < n_stage) v2q = &sviews[slot];
+            }
+            const ViewD &v2 = *v2q;
             const vec3<double> c2s = mat3_mul_h(v2.M, l2v.x, l2v.y), c2e = mat3_mul_h(v2.M, l2v.z, l2v.w);
             const int lab1 = p.vp_label[node];
             if (lab1 >= 0) {
@@ -634,7 +727,12 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
           }
           l2 = l2v;
         }
-        oks[NS - 1] = gen_candidate<!FAST>(p, v1, src, ngv, ngl, cs[NS - 1], l2);
+        const ViewD *v2p = &p.views[ngv];
+        if constexpr (FAST && !SLAB && (LM_TRI_TMA || VP)) {
+          const int slot = slot_of_row[r];
+          if (slot < n_stage) v2p = &sviews[slot];
+        }
+        oks[NS - 1] = gen_candidate<!FAST>(p, v1, *v2p, src, ngv, ngl, cs[NS - 1], l2);
       }
       int cnt = 0;
 #pragma unroll

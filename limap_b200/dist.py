@@ -152,7 +152,9 @@ def slice_tracks(index, sup_off, *per_support):
     sup_off = np.asarray(sup_off, dtype=np.int64)
     counts = (sup_off[1:] - sup_off[:-1])[index]
     new_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-    sel = np.concatenate([np.arange(sup_off[t], sup_off[t + 1]) for t in index]) if len(index) else np.zeros(0, np.int64)
+    # concatenated index ranges [sup_off[t], sup_off[t + 1]) of the chosen tracks, without a Python loop
+    sel = (np.repeat(sup_off[index] - new_off[:-1], counts) + np.arange(int(new_off[-1]), dtype=np.int64)) if len(index) \
+        else np.zeros(0, np.int64)
     return new_off, [np.ascontiguousarray(np.asarray(a)[sel]) for a in per_support]
 
 
