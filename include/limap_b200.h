@@ -295,6 +295,21 @@ typedef struct lm_vp_stats {
 } lm_vp_stats;
 int lm_vp_get_stats(lm_ctx *ctx, lm_vp_stats *out);
 
+/* ---- visual neighbours and robust ranges from a sparse point model: the step before the path.
+ * Replaces SfmModel::{GetMaxIoUImages (mode 0), GetMaxDiceCoeffImages (mode 1), GetMaxOverlapImages (mode 2)}
+ * (pointsfm/sfm_model.cc:88-226; Python glue pointsfm/functions.py:20-55) and SfmModel::ComputeRanges (:228-261).
+ * Images are indexed 0..n_images-1 (the caller maps indices to image ids as neighbors_vec_to_map does, :75-86);
+ * centres[n_images][3] = projection centres; points xyz[n_points][3] with tracks track_off[n_points+1],
+ * track_img[] (image indices). out_neighbors[n_images][num_images] (padded with -1), out_count[n_images]. Pairs whose
+ * 75th-percentile triangulation angle is below min_triangulation_angle_deg are dropped; ties of the score are broken
+ * by ascending image index (the reference's std::sort leaves them unspecified). */
+int lm_sfm_rank_neighbors(lm_ctx *ctx, int32_t n_images, const double *centres, int64_t n_points, const double *xyz,
+                          const int64_t *track_off, const int32_t *track_img, int32_t num_images,
+                          double min_triangulation_angle_deg, int32_t mode, int32_t *out_neighbors, int32_t *out_count);
+/* out[6] = lo3, hi3: per axis the (q_lo, q_hi) quantiles of the float coordinates, stretched by kstretch * (hi - lo). */
+int lm_sfm_robust_ranges(lm_ctx *ctx, int64_t n_points, const double *xyz, double q_lo, double q_hi, double kstretch,
+                         double out[6]);
+
 #ifdef __cplusplus
 }
 #endif

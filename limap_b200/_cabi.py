@@ -104,6 +104,8 @@ _SIGS = {
     "lm_vp_detect": (C.c_int64, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64]),
     "lm_vp_detect_indexed": (C.c_int64, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int64]),
     "lm_vp_get_stats": (C.c_int, [_P, _P]),
+    "lm_sfm_rank_neighbors": (C.c_int, [_P, C.c_int32, _P, C.c_int64, _P, _P, _P, C.c_int32, C.c_double, C.c_int32, _P, _P]),
+    "lm_sfm_robust_ranges": (C.c_int, [_P, C.c_int64, _P, C.c_double, C.c_double, C.c_double, _P]),
     "lm_tracks_support_flags": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "lm_aggregate_lines": (C.c_int, [C.c_int64, _P, _P, _P, C.c_int32, _P]),
     "lm_remerge_labels": (C.c_int64, [_P, C.c_int64, _P, _P, _P, _P, _P]),

@@ -14,6 +14,8 @@
 #include "lm_kernels.cuh"
 #include "vp_kernels.cuh"
 #include "merge_kernels.cuh"
+#include "sfm_kernels.cuh"
+#include <cub/device/device_run_length_encode.cuh>
 #include <algorithm>
 #ifdef LM_TRACE
 #include <chrono>
@@ -210,6 +212,7 @@ struct lm_ctx {
   DevBuf d_vp_idx;
   // track filters / remerge
   DevBuf d_mg_in, d_mg_out, d_mg_edges;
+  DevBuf d_sfm_in, d_sfm_keys, d_sfm_keys2, d_sfm_a, d_sfm_b, d_sfm_c, d_sfm_d; // neighbour ranking scratch
   lm_merge_stats mg_stats;
   // tracks
   std::vector<Track> tracks;
@@ -318,7 +321,7 @@ void lm_ctx_destroy(lm_ctx *c) {
                     &c->d_blk_src, &c->d_blk_ng, &c->d_blk_pair_off, &c->d_key, &c->d_key2, &c->d_val, &c->d_val2,
                     &c->d_sort_tmp, &c->d_node_row_off, &c->d_scalars, &c->d_nodes, &c->d_row_state, &c->d_row_cand,
                     &c->d_slab, &c->d_edges, &c->d_edges2, &c->d_edge_keys, &c->d_edge_keys2, &c->d_edge_w,
-                    &c->d_edge_cnt, &c->d_nvalid, &c->d_edge_off, &c->d_edge_ng, &c->d_ba_in, &c->d_ba_blocks, &c->d_ba_out, &c->d_raw_blocks, &c->d_bkey, &c->d_bkey2, &c->d_bval, &c->d_bval2, &c->d_blk_rows, &c->d_vp_label, &c->d_vp_voff, &c->d_vp_vps, &c->d_vp_pts, &c->d_vp_off, &c->d_vp_labels, &c->d_vp_nc, &c->d_vp_ps, &c->d_vp_mat, &c->d_mg_in, &c->d_mg_out, &c->d_mg_edges, &c->d_gather, &c->d_vp_idx};
+                    &c->d_edge_cnt, &c->d_nvalid, &c->d_edge_off, &c->d_edge_ng, &c->d_ba_in, &c->d_ba_blocks, &c->d_ba_out, &c->d_raw_blocks, &c->d_bkey, &c->d_bkey2, &c->d_bval, &c->d_bval2, &c->d_blk_rows, &c->d_vp_label, &c->d_vp_voff, &c->d_vp_vps, &c->d_vp_pts, &c->d_vp_off, &c->d_vp_labels, &c->d_vp_nc, &c->d_vp_ps, &c->d_vp_mat, &c->d_mg_in, &c->d_mg_out, &c->d_mg_edges, &c->d_gather, &c->d_vp_idx, &c->d_sfm_in, &c->d_sfm_keys, &c->d_sfm_keys2, &c->d_sfm_a, &c->d_sfm_b, &c->d_sfm_c, &c->d_sfm_d};
   for (DevBuf *b : bufs) b->release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -2164,6 +2167,166 @@ int64_t lm_remerge_labels(lm_ctx *c, int64_t T, const double *track_line, const 
 int lm_merge_get_stats(lm_ctx *c, lm_merge_stats *out) {
   if (!c || !out) return fail(LM_ERR_INVALID, "NULL argument");
   *out = c->mg_stats;
+  return LM_OK;
+}
+
+} // extern "C"
+
+// ---- visual-neighbour ranking and robust ranges from a sparse point model -------------------------
+extern "C" {
+
+int lm_sfm_rank_neighbors(lm_ctx *c, int32_t n_images, const double *centres, int64_t n_points, const double *xyz,
+                          const int64_t *track_off, const int32_t *track_img, int32_t num_images,
+                          double min_triangulation_angle_deg, int32_t mode, int32_t *out_neighbors, int32_t *out_count) {
+  if (!c || !centres || !track_off || !out_neighbors || !out_count) return fail(LM_ERR_INVALID, "NULL argument");
+  if (n_images <= 0 || n_images > 65535 || n_points < 0 || num_images <= 0 || mode < 0 || mode > 2)
+    return fail(LM_ERR_INVALID, "bad sizes");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const int64_t n_ent = track_off[n_points];
+  for (int64_t e = 0; e < n_ent; ++e)
+    if (track_img[e] < 0 || track_img[e] >= n_images) return fail(LM_ERR_INVALID, "track image index out of range");
+  // records per point: pairs of its track entries
+  std::vector<int64_t> rec_off(n_points + 1, 0);
+  for (int64_t p = 0; p < n_points; ++p) {
+    const int64_t t = track_off[p + 1] - track_off[p];
+    rec_off[p + 1] = rec_off[p] + t * (t - 1) / 2;
+  }
+  const int64_t n_rec = rec_off[n_points];
+  if (n_rec >= ((int64_t)1 << 31) - 64) return fail(LM_ERR_INVALID, "more than 2^31 (point, image pair) records");
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_c = take(24 * (size_t)n_images), o_x = take(24 * (size_t)std::max<int64_t>(n_points, 1)),
+               o_to = take(8 * (size_t)(n_points + 1)), o_ti = take(4 * (size_t)std::max<int64_t>(n_ent, 1)),
+               o_ro = take(8 * (size_t)(n_points + 1)), o_np = take(4 * (size_t)n_images), o_sc = take(64),
+               o_out = take(4 * (size_t)n_images * num_images), o_cnt = take(4 * (size_t)n_images);
+  CU(c->d_sfm_in.ensure(off + 256));
+  char *in = c->d_sfm_in.as<char>();
+  CU(cudaMemcpyAsync(in + o_c, centres, 24 * (size_t)n_images, cudaMemcpyHostToDevice, s));
+  if (n_points) CU(cudaMemcpyAsync(in + o_x, xyz, 24 * (size_t)n_points, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(in + o_to, track_off, 8 * (size_t)(n_points + 1), cudaMemcpyHostToDevice, s));
+  if (n_ent) CU(cudaMemcpyAsync(in + o_ti, track_img, 4 * (size_t)n_ent, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(in + o_ro, rec_off.data(), 8 * (size_t)(n_points + 1), cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(in + o_np, 0, 4 * (size_t)n_images, s));
+  CU(cudaMemsetAsync(in + o_sc, 0, 64, s));
+  unsigned int *d_np = reinterpret_cast<unsigned int *>(in + o_np);
+  unsigned int *d_ndir = reinterpret_cast<unsigned int *>(in + o_sc);
+  int *d_nruns = reinterpret_cast<int *>(in + o_sc + 16);
+  int64_t n_dir = 0;
+  if (n_rec > 0) {
+    // (a pair seen once yields two directed records: the scratch is sized for 2 n_rec)
+    CU(c->d_sfm_keys.ensure(16 * (size_t)n_rec));
+    CU(c->d_sfm_keys2.ensure(16 * (size_t)n_rec));
+    lm::launch_sfm_pair_keys(reinterpret_cast<const double *>(in + o_c), reinterpret_cast<const double *>(in + o_x),
+                             reinterpret_cast<const int64_t *>(in + o_to), reinterpret_cast<const int32_t *>(in + o_ti),
+                             reinterpret_cast<const int64_t *>(in + o_ro), n_points, n_rec,
+                             c->d_sfm_keys.as<unsigned long long>(), d_np, s);
+    cub::DoubleBuffer<unsigned long long> dk(c->d_sfm_keys.as<unsigned long long>(), c->d_sfm_keys2.as<unsigned long long>());
+    size_t tmp = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, dk, (int)n_rec, 0, 64, s));
+    CU(c->d_sort_tmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortKeys(c->d_sort_tmp.p, tmp, dk, (int)n_rec, 0, 64, s));
+    const unsigned long long *sorted = dk.Current();
+    // runs of equal image pairs: ids -> run-length encode -> starts
+    CU(c->d_sfm_a.ensure(8 * (size_t)n_rec));       // pair ids, later the directed records
+    CU(c->d_sfm_b.ensure(8 * (size_t)n_rec + 16));  // unique pairs, later the sort's alternate buffer
+    CU(c->d_sfm_c.ensure(4 * (size_t)n_rec + 16));  // run lengths
+    CU(c->d_sfm_d.ensure(4 * (size_t)n_rec + 16));  // run starts
+    lm::launch_sfm_pair_ids(sorted, n_rec, c->d_sfm_a.as<unsigned int>(), s);
+    size_t tmp2 = 0;
+    CU(cub::DeviceRunLengthEncode::Encode(nullptr, tmp2, c->d_sfm_a.as<unsigned int>(), c->d_sfm_b.as<unsigned int>(),
+                                          c->d_sfm_c.as<unsigned int>(), d_nruns, (int)n_rec, s));
+    CU(c->d_sort_tmp.ensure(tmp2));
+    CU(cub::DeviceRunLengthEncode::Encode(c->d_sort_tmp.p, tmp2, c->d_sfm_a.as<unsigned int>(), c->d_sfm_b.as<unsigned int>(),
+                                          c->d_sfm_c.as<unsigned int>(), d_nruns, (int)n_rec, s));
+    int n_runs = 0;
+    CU(cudaMemcpyAsync(&n_runs, d_nruns, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    size_t tmp3 = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp3, c->d_sfm_c.as<unsigned int>(), c->d_sfm_d.as<unsigned int>(), n_runs, s));
+    CU(c->d_sort_tmp.ensure(tmp3));
+    CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp3, c->d_sfm_c.as<unsigned int>(), c->d_sfm_d.as<unsigned int>(), n_runs, s));
+    // directed (source, destination) records of the pairs that pass the angle test; the sorted keys are dead afterwards,
+    // so their buffers carry the records: values in d_sfm_a (reused), keys in the alternate key buffer
+    unsigned int *dir_val = c->d_sfm_a.as<unsigned int>();
+    unsigned long long *dir_key = dk.Alternate();
+    const float min_angle = (float)(min_triangulation_angle_deg * 3.14159265358979323846 / 180.0);
+    lm::launch_sfm_scores(sorted, c->d_sfm_b.as<unsigned int>(), c->d_sfm_c.as<unsigned int>(), c->d_sfm_d.as<unsigned int>(),
+                          n_runs, d_np, min_angle, mode, dir_val, dir_key, d_ndir, s);
+    unsigned int h_ndir = 0;
+    CU(cudaMemcpyAsync(&h_ndir, d_ndir, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    n_dir = h_ndir;
+    if (n_dir > 0) {
+      // order: source ascending, score descending, destination ascending = three stable radix sorts, least significant first
+      unsigned int *val2 = c->d_sfm_b.as<unsigned int>();
+      unsigned long long *key2 = const_cast<unsigned long long *>(sorted); // the sorted pair keys are dead now
+      {
+        cub::DoubleBuffer<unsigned int> k(dir_val, val2);
+        cub::DoubleBuffer<unsigned long long> v(dir_key, key2);
+        size_t t1 = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, t1, k, v, (int)n_dir, 0, 32, s)); // by (source, destination)
+        CU(c->d_sort_tmp.ensure(t1));
+        CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, t1, k, v, (int)n_dir, 0, 32, s));
+        cub::DoubleBuffer<unsigned long long> k2(v.Current(), v.Alternate());
+        cub::DoubleBuffer<unsigned int> v2(k.Current(), k.Alternate());
+        size_t t2 = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, t2, k2, v2, (int)n_dir, 0, 64, s)); // by score, descending
+        CU(c->d_sort_tmp.ensure(t2));
+        CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, t2, k2, v2, (int)n_dir, 0, 64, s));
+        cub::DoubleBuffer<unsigned int> k3(v2.Current(), v2.Alternate());
+        size_t t3 = 0;
+        CU(cub::DeviceRadixSort::SortKeys(nullptr, t3, k3, (int)n_dir, 16, 32, s)); // by source (stable)
+        CU(c->d_sort_tmp.ensure(t3));
+        CU(cub::DeviceRadixSort::SortKeys(c->d_sort_tmp.p, t3, k3, (int)n_dir, 16, 32, s));
+        dir_val = k3.Current();
+      }
+    }
+    lm::launch_sfm_take(dir_val, n_dir, n_images, num_images, reinterpret_cast<int32_t *>(in + o_out),
+                        reinterpret_cast<int32_t *>(in + o_cnt), s);
+  } else {
+    lm::launch_sfm_take(nullptr, 0, n_images, num_images, reinterpret_cast<int32_t *>(in + o_out),
+                        reinterpret_cast<int32_t *>(in + o_cnt), s);
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out_neighbors, in + o_out, 4 * (size_t)n_images * num_images, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(out_count, in + o_cnt, 4 * (size_t)n_images, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  c->stats.n_kernel_launches += 12;
+  return LM_OK;
+}
+
+int lm_sfm_robust_ranges(lm_ctx *c, int64_t n_points, const double *xyz, double q_lo, double q_hi, double kstretch,
+                         double out[6]) {
+  if (!c || !xyz || !out) return fail(LM_ERR_INVALID, "NULL argument");
+  if (n_points <= 0 || n_points >= ((int64_t)1 << 31) - 64) return fail(LM_ERR_INVALID, "bad point count");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  // SfmModel::ComputeRanges keeps the coordinates as float (sfm_model.cc:245-252): one float column per axis, sorted
+  std::vector<float> col((size_t)n_points);
+  CU(c->d_sfm_a.ensure(4 * (size_t)n_points));
+  CU(c->d_sfm_b.ensure(4 * (size_t)n_points));
+  for (int ax = 0; ax < 3; ++ax) {
+    for (int64_t p = 0; p < n_points; ++p) col[p] = (float)xyz[3 * p + ax];
+    CU(cudaMemcpyAsync(c->d_sfm_a.p, col.data(), 4 * (size_t)n_points, cudaMemcpyHostToDevice, s));
+    cub::DoubleBuffer<float> dk(c->d_sfm_a.as<float>(), c->d_sfm_b.as<float>());
+    size_t tmp = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, dk, (int)n_points, 0, 32, s));
+    CU(c->d_sort_tmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortKeys(c->d_sort_tmp.p, tmp, dk, (int)n_points, 0, 32, s));
+    const float kmin = (float)q_lo, kmax = (float)q_hi;
+    const size_t i_lo = (size_t)((float)n_points * kmin), i_hi = (size_t)((float)n_points * kmax); // data[data.size() * k]
+    float lo = 0, hi = 0;
+    CU(cudaMemcpyAsync(&lo, dk.Current() + std::min<size_t>(i_lo, n_points - 1), 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&hi, dk.Current() + std::min<size_t>(i_hi, n_points - 1), 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const float ks = (float)kstretch, diff = hi - lo;
+    lo -= ks * diff;
+    hi += ks * diff;
+    out[ax] = lo;
+    out[3 + ax] = hi;
+  }
+  c->stats.n_kernel_launches += 12;
   return LM_OK;
 }
 

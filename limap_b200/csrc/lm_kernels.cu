@@ -20,6 +20,7 @@
 // per evaluation per track with 4-wide duals, and each lane carries 3-wide duals from m_c to the residual.
 // The solver restates Ceres' trust-region LM (DESIGN.md "LM recipe" lists the steps and their provenance).
 #include "lm_kernels.cuh"
+#include "lm_block.cuh"
 #include <algorithm>
 #include <cfloat>
 #include <cstdlib>
@@ -28,201 +29,10 @@ namespace lm {
 
 static constexpr int kSegMax = 128; // supports per track handled by the in-kernel segment cut
 
-template <int N> struct Dual {
-  double a;
-  double v[N];
-};
-template <int N> LM_D Dual<N> dconst(double x) { Dual<N> r; r.a = x;
-#pragma unroll
-  for (int i = 0; i < N; ++i) r.v[i] = 0; return r; }
-template <int N> LM_D Dual<N> operator+(const Dual<N> &f, const Dual<N> &g) { Dual<N> h; h.a = f.a + g.a;
-#pragma unroll
-  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] + g.v[i]; return h; }
-template <int N> LM_D Dual<N> operator-(const Dual<N> &f, const Dual<N> &g) { Dual<N> h; h.a = f.a - g.a;
-#pragma unroll
-  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] - g.v[i]; return h; }
-template <int N> LM_D Dual<N> operator-(const Dual<N> &f) { Dual<N> h; h.a = -f.a;
-#pragma unroll
-  for (int i = 0; i < N; ++i) h.v[i] = -f.v[i]; return h; }
-template <int N> LM_D Dual<N> operator*(const Dual<N> &f, const Dual<N> &g) { Dual<N> h; h.a = f.a * g.a;
-#pragma unroll
-  for (int i = 0; i < N; ++i) h.v[i] = f.a * g.v[i] + f.v[i] * g.a; return h; }
-template <int N> LM_D Dual<N> operator*(const Dual<N> &f, double s) { Dual<N> h; h.a = f.a * s;
-#pragma unroll
-  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * s; return h; }
-template <int N> LM_D Dual<N> operator/(const Dual<N> &f, const Dual<N> &g) { Dual<N> h; const double gi = 1.0 / g.a, q = f.a * gi; h.a = q;
-#pragma unroll
-  for (int i = 0; i < N; ++i) h.v[i] = (f.v[i] - q * g.v[i]) * gi; return h; }
-template <int N> LM_D Dual<N> dsqrt(const Dual<N> &f) { Dual<N> h; h.a = sqrt(f.a); const double t = 1.0 / (2.0 * h.a);
-#pragma unroll
-  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * t; return h; }
-template <int N> LM_D Dual<N> dexp(const Dual<N> &f) { Dual<N> h; h.a = exp(f.a);
-#pragma unroll
-  for (int i = 0; i < N; ++i) h.v[i] = h.a * f.v[i]; return h; }
-template <int N> LM_D Dual<N> dabs(const Dual<N> &f) { return f.a < 0 ? -f : f; }
-
 LM_D double warp_sum(double v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
   return v;
-}
-
-// ceres QuaternionManifold / SphereManifold<2> (DESIGN.md "LM recipe")
-LM_D void quat_plus(const double x[4], const double d[3], double out[4]) {
-  const double sq = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-  if (sq == 0.0) { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3]; return; }
-  const double nd = sqrt(sq), sbd = sin(nd) / nd;
-  const double z0 = cos(nd), z1 = sbd * d[0], z2 = sbd * d[1], z3 = sbd * d[2];
-  out[0] = z0 * x[0] - z1 * x[1] - z2 * x[2] - z3 * x[3];
-  out[1] = z0 * x[1] + z1 * x[0] + z2 * x[3] - z3 * x[2];
-  out[2] = z0 * x[2] - z1 * x[3] + z2 * x[0] + z3 * x[1];
-  out[3] = z0 * x[3] + z1 * x[2] - z2 * x[1] + z3 * x[0];
-}
-LM_D void householder2(const double x[2], double v[2], double &beta) {
-  const double sigma = x[0] * x[0];
-  v[0] = x[0]; v[1] = 1.0; beta = 0.0;
-  const double xp = x[1];
-  if (sigma <= DBL_EPSILON) { if (xp < 0.0) beta = 2.0; return; }
-  const double mu = sqrt(xp * xp + sigma);
-  const double vp = (xp <= 0.0) ? (xp - mu) : (-sigma / (xp + mu));
-  beta = 2.0 * vp * vp / (sigma + vp * vp);
-  v[0] /= vp;
-}
-LM_D void sphere2_plus(const double x[2], double delta, double out[2]) {
-  const double nd = fabs(delta);
-  if (nd == 0.0) { out[0] = x[0]; out[1] = x[1]; return; }
-  double v[2], beta;
-  householder2(x, v, beta);
-  const double y0 = sin(nd) / nd * delta, y1 = cos(nd);
-  const double vty = v[0] * y0 + v[1] * y1;
-  const double nx = sqrt(x[0] * x[0] + x[1] * x[1]);
-  out[0] = nx * (y0 - v[0] * (beta * vty));
-  out[1] = nx * (y1 - v[1] * (beta * vty));
-}
-
-// d and m (world-frame Pluecker line) with derivatives w.r.t. the 4 local (tangent) coordinates.
-// MinimalPluckerToPlucker with ceres::QuaternionToRotation (normalised by |u|^2), composed with the plus
-// Jacobians of the two manifolds.
-struct LineLocal {
-  Dual<4> d[3], m[3];
-};
-// The same, laid out for shared memory (one per warp): every lane evaluates a different residual block against the
-// same line, so the line and its 24 tangent derivatives are warp-uniform -- kept here, not in 60 registers per lane.
-struct LineShared {
-  double d[3], m[3];
-  double dv[3][4], mv[3][4];
-};
-LM_D void line_from_minimal(const double x[6], bool want_jac, LineLocal &L) {
-  // ambient duals (6-wide) would be wasteful: seed the 4 local directions directly through the plus Jacobians
-  Dual<4> u[4], w[2];
-  // QuaternionPlusJacobian (4x3)
-  const double Pq[12] = {-x[1], -x[2], -x[3], x[0], x[3], -x[2], -x[3], x[0], x[1], x[2], -x[1], x[0]};
-  double v2[2], beta;
-  householder2(x + 4, v2, beta);
-  const double nx = sqrt(x[4] * x[4] + x[5] * x[5]);
-  const double Ps[2] = {(-beta * v2[0] * v2[0] + 1.0) * nx, (-beta * v2[0] * v2[1]) * nx};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    u[i].a = x[i];
-    u[i].v[0] = want_jac ? Pq[3 * i] : 0; u[i].v[1] = want_jac ? Pq[3 * i + 1] : 0; u[i].v[2] = want_jac ? Pq[3 * i + 2] : 0;
-    u[i].v[3] = 0;
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    w[i].a = x[4 + i];
-    w[i].v[0] = w[i].v[1] = w[i].v[2] = 0;
-    w[i].v[3] = want_jac ? Ps[i] : 0;
-  }
-  const Dual<4> a = u[0], b = u[1], c = u[2], dd = u[3];
-  const Dual<4> aa = a * a, ab = a * b, ac = a * c, ad = a * dd, bb = b * b, bc = b * c, bd = b * dd, cc = c * c,
-                cd = c * dd, d2 = dd * dd;
-  const Dual<4> nrm = dconst<4>(1.0) / (aa + bb + cc + d2);
-  // column 0 of R: (R00, R10, R20); column 1: (R01, R11, R21)
-  L.d[0] = (aa + bb - cc - d2) * nrm;
-  L.d[1] = ((ad + bc) * 2.0) * nrm;
-  L.d[2] = ((bd - ac) * 2.0) * nrm;
-  const Dual<4> w1 = dabs(w[0]), w2 = dabs(w[1]);
-  const Dual<4> bn = w2 / (w1 + dconst<4>(consts<double>::eps()));
-  L.m[0] = (((bc - ad) * 2.0) * nrm) * bn;
-  L.m[1] = ((aa - bb + cc - d2) * nrm) * bn;
-  L.m[2] = (((ab + cd) * 2.0) * nrm) * bn;
-}
-
-struct BlockEval {
-  double r[2];     // raw residuals
-  double J[8];     // 2x4 local Jacobian (raw)
-  double rv;       // VP residual (VPConstraintsFunctor), only when B.wvp > 0
-  double Jv[4];
-};
-
-// One residual block: from (d, m) to the two cosine-weighted point-line distances.
-LM_D void eval_block(const LMBlockDev &B, const LineShared &L, double alpha, bool want_jac, BlockEval &o) {
-  // m_c = R m + t x (R d)   (Line_WorldToPixel, matrix form R [m]x R^T - t (Rd)^T + (Rd) t^T)
-  double Rd[3], Rm[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    Rd[i] = B.R[3 * i] * L.d[0] + B.R[3 * i + 1] * L.d[1] + B.R[3 * i + 2] * L.d[2];
-    Rm[i] = B.R[3 * i] * L.m[0] + B.R[3 * i + 1] * L.m[1] + B.R[3 * i + 2] * L.m[2];
-  }
-  const double mc[3] = {Rm[0] + (B.t[1] * Rd[2] - B.t[2] * Rd[1]), Rm[1] + (B.t[2] * Rd[0] - B.t[0] * Rd[2]),
-                        Rm[2] + (B.t[0] * Rd[1] - B.t[1] * Rd[0])};
-  // 3-wide duals seeded on m_c
-  Dual<3> q[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) { q[i].a = mc[i]; q[i].v[0] = (i == 0); q[i].v[1] = (i == 1); q[i].v[2] = (i == 2); }
-  // Line_ImgFromCam: coor = cof(K) m_c = (fy mx, fx my, fx fy mz - fy cx mx - fx cy my), then normalised (+EPS)
-  const double fx = B.k[0], fy = B.k[1], cx = B.k[2], cy = B.k[3];
-  Dual<3> c0 = q[0] * fy, c1 = q[1] * fx, c2 = q[2] * (fx * fy) - q[0] * (fy * cx) - q[1] * (fx * cy);
-  const Dual<3> eps = dconst<3>(consts<double>::eps());
-  const Dual<3> cn = dsqrt(c0 * c0 + c1 * c1 + c2 * c2 + eps);
-  c0 = c0 / cn; c1 = c1 / cn; c2 = c2 / cn;
-  // Ceres_CosineWeightedPerpendicularDist2D_1D
-  const Dual<3> dn = dsqrt(c0 * c0 + c1 * c1 + eps);
-  const Dual<3> dir0 = -c1 / dn, dir1 = c0 / dn;
-  const double sx = B.p[2] - B.p[0], sy = B.p[3] - B.p[1];
-  const Dual<3> n1 = dsqrt(dir0 * dir0 + dir1 * dir1 + eps);
-  const double n2 = sqrt(sx * sx + sy * sy + consts<double>::eps());
-  Dual<3> cosine = dabs((dir0 * sx + dir1 * sy) / (n1 * n2));
-  if (cosine.a > 1.0) cosine = dconst<3>(1.0);
-  const Dual<3> weight = dexp((dconst<3>(1.0) - cosine) * alpha);
-  const Dual<3> r0 = ((c0 * B.p[0] + c1 * B.p[1] + c2) / dn) * weight;
-  const Dual<3> r1 = ((c0 * B.p[2] + c1 * B.p[3] + c2) / dn) * weight;
-  o.r[0] = r0.a;
-  o.r[1] = r1.a;
-  Dual<3> rvp = dconst<3>(0.0);
-  if (B.wvp > 0.0) {
-    // VPConstraintsFunctor (cost_functions.h:60-85): sine between R d and the VP direction
-    // (CeresComputeDist3D_sine, ceresbase/line_dists.h:40-57); duals seeded on R d
-    Dual<3> a[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { a[i].a = Rd[i]; a[i].v[0] = (i == 0); a[i].v[1] = (i == 1); a[i].v[2] = (i == 2); }
-    const Dual<3> e3 = dconst<3>(consts<double>::eps());
-    const Dual<3> n1 = dsqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + e3);
-    const double n2 = sqrt(B.vdir[0] * B.vdir[0] + B.vdir[1] * B.vdir[1] + B.vdir[2] * B.vdir[2] + consts<double>::eps());
-    const Dual<3> ax = a[0] / n1, ay = a[1] / n1, az = a[2] / n1;
-    const double bx = B.vdir[0] / n2, by = B.vdir[1] / n2, bz = B.vdir[2] / n2;
-    const Dual<3> cx_ = ay * bz - az * by, cy_ = az * bx - ax * bz, cz_ = ax * by - ay * bx;
-    rvp = dsqrt(cx_ * cx_ + cy_ * cy_ + cz_ * cz_ + e3);
-    if (rvp.a > 1.0) rvp = dconst<3>(1.0);
-  }
-  o.rv = rvp.a;
-  if (!want_jac) return;
-  // G = d m_c / d local (3x4) = R Dm + t x (R Dd)
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    double rd[3], rm[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      rd[i] = B.R[3 * i] * L.dv[0][c] + B.R[3 * i + 1] * L.dv[1][c] + B.R[3 * i + 2] * L.dv[2][c];
-      rm[i] = B.R[3 * i] * L.mv[0][c] + B.R[3 * i + 1] * L.mv[1][c] + B.R[3 * i + 2] * L.mv[2][c];
-    }
-    const double g0 = rm[0] + (B.t[1] * rd[2] - B.t[2] * rd[1]);
-    const double g1 = rm[1] + (B.t[2] * rd[0] - B.t[0] * rd[2]);
-    const double g2 = rm[2] + (B.t[0] * rd[1] - B.t[1] * rd[0]);
-    o.J[c] = r0.v[0] * g0 + r0.v[1] * g1 + r0.v[2] * g2;
-    o.J[4 + c] = r1.v[0] * g0 + r1.v[1] * g1 + r1.v[2] * g2;
-    o.Jv[c] = rvp.v[0] * rd[0] + rvp.v[1] * rd[1] + rvp.v[2] * rd[2];
-  }
 }
 
 struct Normal {
@@ -254,15 +64,15 @@ LM_D void eval_track(const LMBlockDev *blocks, int S, const double *x, double al
     double xr[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) xr[i] = x[i];
-    LineLocal L;
-    line_from_minimal(xr, want_jac, L); // redundantly on every lane (same instruction count as on one)
+    Dual<1> dd[3], mm[3];
+    line_from_minimal_col(xr, lane & 3, want_jac, dd, mm); // lane c < 4 holds tangent column c (all lanes: the values)
     __syncwarp();
-    if (lane == 0) {
+    if (lane < 4) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        Ls.d[i] = L.d[i].a; Ls.m[i] = L.m[i].a;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { Ls.dv[i][c] = L.d[i].v[c]; Ls.mv[i][c] = L.m[i].v[c]; }
+        if (lane == 0) { Ls.d[i] = dd[i].a; Ls.m[i] = mm[i].a; }
+        Ls.dv[i][lane] = dd[i].v[0];
+        Ls.mv[i][lane] = mm[i].v[0];
       }
     }
     __syncwarp();

@@ -367,3 +367,33 @@ def make_vp_images(n_images, n_segments=300, seed=0, width=800, height=600, nois
         segs = np.concatenate(segs, 0)
         out.append(np.ascontiguousarray(segs[rng.permutation(len(segs))]))
     return out
+
+
+def make_sfm_points(scene, n_points=2000, seed=0, p_detect=0.7, max_track=None):
+    """A sparse point model for a Scene: random 3D points in the scene box, each tracked by the views that see it
+    (inside the image, in front of the camera) and 'detect' it with probability p_detect. Returns (centres[V,3],
+    xyz[P,3], track_off[P+1], track_img[...]) with image INDICES (view order), points with fewer than 2 views dropped."""
+    rng = np.random.default_rng(seed)
+    V = scene.n_views
+    s = float(scene.meta.get("scale", 1.0)) if isinstance(scene.meta, dict) else 1.0
+    X = rng.uniform(-5, 5, (n_points, 3)) * s
+    from .base import CameraPose
+    Rs = np.stack([CameraPose(scene.qvec[v], scene.tvec[v]).R() for v in range(V)])
+    centres = np.stack([-Rs[v].T @ scene.tvec[v] for v in range(V)])
+    off, img, keep = [0], [], []
+    for p in range(n_points):
+        Xc = np.einsum("vij,j->vi", Rs, X[p]) + scene.tvec
+        z = Xc[:, 2]
+        u = Xc[:, 0] / z * scene.kvec[:, 0] + scene.kvec[:, 2]
+        w = Xc[:, 1] / z * scene.kvec[:, 1] + scene.kvec[:, 3]
+        vis = (z > 0.5 * s) & (u >= 0) & (u <= 800) & (w >= 0) & (w <= 600) & (rng.random(V) < p_detect)
+        t = np.flatnonzero(vis)
+        if max_track is not None and len(t) > max_track:
+            t = np.sort(rng.choice(t, max_track, replace=False))
+        if len(t) < 2:
+            continue
+        keep.append(p)
+        img.append(t.astype(np.int32))
+        off.append(off[-1] + len(t))
+    return (np.ascontiguousarray(centres), np.ascontiguousarray(X[keep]), np.asarray(off, np.int64),
+            np.ascontiguousarray(np.concatenate(img) if img else np.zeros(0, np.int32)))

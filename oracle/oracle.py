@@ -323,3 +323,27 @@ def remerge_labels(track_line, active, linker, threads=None):
     ne = C.c_int64(0)
     ng = L.orc_remerge_labels(len(track_line), _p(track_line), _p(active), C.byref(cfg), _p(labels), C.byref(ne))
     return labels, int(ng), int(ne.value)
+
+
+# ---- visual neighbours / robust ranges (orc_sfm.cpp) ---------------------------------------------------------------
+def rank_neighbors(centres, xyz, track_off, track_img, num_images, min_triangulation_angle=1.0, mode=0):
+    L = lib()
+    L.orc_rank_neighbors.argtypes = [C.c_int, _P, C.c_int64, _P, _P, _P, C.c_int, C.c_double, C.c_int, _P, _P]
+    centres, xyz = _f64(centres), _f64(xyz)
+    track_off = np.ascontiguousarray(track_off, np.int64)
+    track_img = np.ascontiguousarray(track_img, np.int32)
+    n = len(centres)
+    out = np.full((n, int(num_images)), -1, np.int32)
+    cnt = np.zeros(n, np.int32)
+    L.orc_rank_neighbors(n, _p(centres), len(xyz), _p(xyz), _p(track_off), _p(track_img), int(num_images),
+                         float(min_triangulation_angle), int(mode), _p(out), _p(cnt))
+    return out, cnt
+
+
+def robust_ranges(xyz, q_lo, q_hi, kstretch):
+    L = lib()
+    L.orc_robust_ranges.argtypes = [C.c_int64, _P, C.c_double, C.c_double, C.c_double, _P]
+    xyz = _f64(xyz)
+    out = np.zeros(6)
+    L.orc_robust_ranges(len(xyz), _p(xyz), float(q_lo), float(q_hi), float(kstretch), _p(out))
+    return out[:3].copy(), out[3:].copy()
