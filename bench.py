@@ -487,6 +487,19 @@ def main():
         try:
             parity = tri_parity(eng, o2, done)
             parity["checked_rows"] = int(o2.rows_tested())
+            if len(done) == len(my_ids):  # the whole scene went through the oracle: ComputeLineTracks on both sides
+                t0 = time.perf_counter()
+                gt = eng.build_tracks()
+                t_gpu = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                ot = o2.build_tracks()
+                t_cpu = time.perf_counter() - t0
+                mem = lambda tr: sorted(tuple(sorted(zip(tr["img_ids"][a:b].tolist(), tr["line_ids"][a:b].tolist())))
+                                        for a, b in zip(tr["track_off"][:-1], tr["track_off"][1:]))
+                parity["tracks"] = {"n_tracks": len(gt["track_off"]) - 1, "membership_identical": mem(gt) == mem(ot),
+                                    "compute_line_tracks_ms": 1e3 * t_gpu, "cpu_port_ms": 1e3 * t_cpu,
+                                    "note": "run_clustering + greedy labels + aggregation: edge weights on the device, "
+                                            "union-find on the host (sequential by definition)"}
         except Exception as e:  # the check must never cost the bench line
             parity = {"error": str(e)}
         del o2

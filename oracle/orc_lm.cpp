@@ -87,6 +87,18 @@ void orc_geometric_residual(const double *x, const double *seg, const double *kv
   GeometricResidual<J>(b, u, w, alpha, rr);
   for (int i = 0; i < 2; ++i) { res[i] = rr[i].a; if (jac) for (int j = 0; j < 6; ++j) jac[6 * i + j] = rr[i].v[j]; }
 }
+// residual (1) and ambient Jacobian (1x6) of one VP block at x: unit-level parity hook
+void orc_vp_residual(const double *x, const double *vp, const double *kvec, const double *qvec, double *res, double *jac) {
+  LMBlock b;
+  for (int i = 0; i < 4; ++i) { b.kvec[i] = kvec[i]; b.qvec[i] = qvec[i]; }
+  for (int i = 0; i < 3; ++i) b.vp[i] = vp[i];
+  b.has_vp = true;
+  typedef Jet<6> J;
+  J u[4] = {J(x[0], 0), J(x[1], 1), J(x[2], 2), J(x[3], 3)}, w[2] = {J(x[4], 4), J(x[5], 5)};
+  J r = VPResidual<J>(b, u, w);
+  res[0] = r.a;
+  if (jac) for (int j = 0; j < 6; ++j) jac[j] = r.v[j];
+}
 void orc_minimal_from_line(const double *line, double *out6) {
   MinimalLine ml = MinimalFromLine3d(Line3d(V3(line[0], line[1], line[2]), V3(line[3], line[4], line[5])));
   for (int i = 0; i < 4; ++i) out6[i] = ml.uvec[i];

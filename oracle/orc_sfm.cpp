@@ -68,7 +68,12 @@ int orc_rank_neighbors(int n_images, const double *centres, int64_t n_points, co
       const float perc = a[(size_t)std::lround(75.0 / 100.0 * (double)(a.size() - 1))];
       if (!(perc >= min_angle)) continue;
       const int inter = kv.second, uni = num_points[i] + num_points[kv.first] - inter;
-      const double score = (mode == 0) ? double(inter) / double(uni) : double(2 * inter) / double(uni + inter);
+      // mode 0: IoU (sfm_model.cc:130-133); 1: Dice (:194-196); 2: shared points, as colmap::mvs::Model::
+      // GetMaxOverlappingImages, which GetMaxOverlapImages (:90-97) forwards to. COLMAP orders that list with an
+      // UNSTABLE std::sort / partial_sort, so its tie order is unspecified; ties here keep ascending image index like
+      // the two stable-sorted limap variants.
+      const double score = (mode == 0) ? double(inter) / double(uni)
+                           : (mode == 1) ? double(2 * inter) / double(uni + inter) : double(inter);
       ordered.emplace_back(kv.first, score);
     }
     std::stable_sort(ordered.begin(), ordered.end(),

@@ -81,6 +81,8 @@ def lib():
         L.ref_infinite_from_minimal.argtypes = [_P, _P, _P]
         L.ref_segment_from_minimal.argtypes = [_P, _P, C.c_int64, C.c_int, _P]
         L.ref_track_support_flags.argtypes = [C.c_int32, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P] + [C.c_double] * 4 + [_P]
+        L.ref_geometric_residual.argtypes = [C.c_int, _P, _P, _P, _P, _P, C.c_double, _P, _P]
+        L.ref_vp_residual.argtypes = [C.c_int, _P, _P, _P, _P, _P, _P]
         L.ref_remerge_groups.restype = C.c_int64
         L.ref_remerge_groups.argtypes = [C.c_int64, _P, _P, _P, _P]
         _lib = L

@@ -7,7 +7,9 @@
 //   GlobalLineTriangulator::{Init, TriangulateImage(ExhaustiveMatch), ComputeLineTracks} and its result tables,
 //   triangulation/functions.cc, LineLinker2d/3d::compute_score, Aggregator::aggregate_line3d_list,
 //   MinimalInfiniteLine3d, GetLineSegmentFromInfiniteLine3d, CheckReprojection / CheckSensitivity / overlap,
-//   RemergeLineTracks.
+//   RemergeLineTracks,
+//   optimize/line_refinement/cost_functions.h: GeometricRefinementFunctor / VPConstraintsFunctor evaluated on
+//   ceres::Jet<double, 6> (oracle/ref_shim/ceres: Jet arithmetic restated; the functors are the reference's).
 // Nothing of the product links or loads this library.
 // every standard / third-party header first, with its own access specifiers intact ...
 #include <algorithm>
@@ -44,6 +46,7 @@
 #include "limap/merging/aggregator.h"
 #include "limap/merging/merging.h"
 #include "limap/merging/merging_utils.h"
+#include "limap/optimize/line_refinement/cost_functions.h"
 #include "limap/triangulation/functions.h"
 #include "limap/triangulation/global_line_triangulator.h"
 #undef private
@@ -464,3 +467,40 @@ int64_t ref_remerge_groups(int64_t T, const double *track_line, const uint8_t *a
 }
 
 } // extern "C"
+
+// The reference's residual functors (optimize/line_refinement/cost_functions.h:35-190) evaluated with forward-mode
+// jets over the 6 line parameters, camera constant (the refine.cc configuration): res[2] (+ jac[2x6] row-major) for the
+// geometric functor, res[1] (+ jac[1x6]) for the VP functor. model: 0 = SIMPLE_PINHOLE (params f,cx,cy), 1 = PINHOLE.
+template <typename CameraModel>
+static void geometric_residual_impl(const double *x, const double *seg, const double *params, const double *qvec,
+                                    const double *tvec, double alpha, double *res, double *jac) {
+  typedef ceres::Jet<double, 6> J;
+  Line2d l(V2D(seg[0], seg[1]), V2D(seg[2], seg[3]));
+  optimize::line_refinement::GeometricRefinementFunctor<CameraModel> f(l, params, qvec, tvec, alpha);
+  J u[4] = {J(x[0], 0), J(x[1], 1), J(x[2], 2), J(x[3], 3)}, w[2] = {J(x[4], 4), J(x[5], 5)}, rr[2];
+  f(u, w, rr);
+  for (int i = 0; i < 2; ++i) { res[i] = rr[i].a; if (jac) for (int j = 0; j < 6; ++j) jac[6 * i + j] = rr[i].v[j]; }
+}
+template <typename CameraModel>
+static void vp_residual_impl(const double *x, const double *vp, const double *params, const double *qvec, double *res,
+                             double *jac) {
+  typedef ceres::Jet<double, 6> J;
+  optimize::line_refinement::VPConstraintsFunctor<CameraModel> f(V3D(vp[0], vp[1], vp[2]), params, qvec);
+  J u[4] = {J(x[0], 0), J(x[1], 1), J(x[2], 2), J(x[3], 3)}, w[2] = {J(x[4], 4), J(x[5], 5)}, rr[1];
+  f(u, w, rr);
+  res[0] = rr[0].a;
+  if (jac) for (int j = 0; j < 6; ++j) jac[j] = rr[0].v[j];
+}
+extern "C" {
+void ref_geometric_residual(int model, const double *x, const double *seg, const double *params, const double *qvec,
+                            const double *tvec, double alpha, double *res, double *jac) {
+  if (model == 0) geometric_residual_impl<colmap::SimplePinholeCameraModel>(x, seg, params, qvec, tvec, alpha, res, jac);
+  else geometric_residual_impl<colmap::PinholeCameraModel>(x, seg, params, qvec, tvec, alpha, res, jac);
+}
+void ref_vp_residual(int model, const double *x, const double *vp, const double *params, const double *qvec,
+                     double *res, double *jac) {
+  if (model == 0) vp_residual_impl<colmap::SimplePinholeCameraModel>(x, vp, params, qvec, res, jac);
+  else vp_residual_impl<colmap::PinholeCameraModel>(x, vp, params, qvec, res, jac);
+}
+}
+

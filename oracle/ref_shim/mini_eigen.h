@@ -29,7 +29,7 @@ using Index = std::ptrdiff_t;
 enum { ComputeThinU = 1, ComputeThinV = 2, ComputeFullU = 4, ComputeFullV = 8 };
 enum { ColMajor = 0, RowMajor = 1 };
 
-template <typename T, int R, int C> class Matrix;
+template <typename T, int R, int C, int Opt = 0> class Matrix;
 
 namespace detail {
 template <typename T, int R, int C, bool Dyn = (R == Dynamic || C == Dynamic)> struct Storage {
@@ -56,7 +56,7 @@ template <typename T, int R, int C> class CommaInit;
 template <typename M> class LDLT;
 template <typename M> class JacobiSVD;
 
-template <typename T, int R, int C> class Matrix {
+template <typename T, int R, int C, int Opt> class Matrix {
 public:
   typedef T Scalar;
   enum { RowsAtCompileTime = R, ColsAtCompileTime = C };
@@ -320,8 +320,8 @@ public:
   }
   bool colmode = false;
 };
-template <typename T, int R, int C> CommaInit<T, R, C> Matrix<T, R, C>::operator<<(T v) { CommaInit<T, R, C> c(*this); c.put(v); return c; }
-template <typename T, int R, int C> template <int R2, int C2> CommaInit<T, R, C> Matrix<T, R, C>::operator<<(const Matrix<T, R2, C2> &b) { CommaInit<T, R, C> c(*this); c.place(b); return c; }
+template <typename T, int R, int C, int Opt> CommaInit<T, R, C> Matrix<T, R, C, Opt>::operator<<(T v) { CommaInit<T, R, C> c(*this); c.put(v); return c; }
+template <typename T, int R, int C, int Opt> template <int R2, int C2> CommaInit<T, R, C> Matrix<T, R, C, Opt>::operator<<(const Matrix<T, R2, C2> &b) { CommaInit<T, R, C> c(*this); c.place(b); return c; }
 
 // ---- determinant / inverse (cofactors, as Eigen does for fixed sizes up to 4) --------------------------------------
 namespace detail {
@@ -341,8 +341,8 @@ template <typename T, int R, int C> T det_rec(const Matrix<T, R, C> &a) {
   return d;
 }
 } // namespace detail
-template <typename T, int R, int C> T Matrix<T, R, C>::determinant() const { assert(rows() == cols()); return detail::det_rec(*this); }
-template <typename T, int R, int C> Matrix<T, R, C> Matrix<T, R, C>::inverse() const {
+template <typename T, int R, int C, int Opt> T Matrix<T, R, C, Opt>::determinant() const { assert(rows() == cols()); return detail::det_rec(*this); }
+template <typename T, int R, int C, int Opt> Matrix<T, R, C, Opt> Matrix<T, R, C, Opt>::inverse() const {
   assert(rows() == cols());
   const Index n = rows();
   Matrix inv;
@@ -534,6 +534,22 @@ public:
 typedef Quaternion<double> Quaterniond;
 typedef Quaternion<float> Quaternionf;
 
+// Eigen::Map as the path uses it: a read view of a plain array. Here it is a VALUE (copied at construction), which is
+// equivalent for the const / temporary uses in ceresbase/line_projection.h; RowMajor of the mapped type is honoured.
+template <typename M> class Map;
+template <typename T, int R, int C, int Opt> class Map<Matrix<T, R, C, Opt>> : public Matrix<T, R, C> {
+public:
+  explicit Map(const T *p) {
+    for (int i = 0; i < R; ++i) for (int j = 0; j < C; ++j) (*this)(i, j) = (Opt == RowMajor) ? p[i * C + j] : p[j * R + i];
+  }
+};
+template <typename T, int R, int C, int Opt> class Map<const Matrix<T, R, C, Opt>> : public Matrix<T, R, C> {
+public:
+  explicit Map(const T *p) {
+    for (int i = 0; i < R; ++i) for (int j = 0; j < C; ++j) (*this)(i, j) = (Opt == RowMajor) ? p[i * C + j] : p[j * R + i];
+  }
+};
+
 #define MINI_EIGEN_TYPEDEFS(T, S)                                                                                      \
   typedef Matrix<T, 2, 1> Vector2##S; typedef Matrix<T, 3, 1> Vector3##S; typedef Matrix<T, 4, 1> Vector4##S;            \
   typedef Matrix<T, Dynamic, 1> VectorX##S; typedef Matrix<T, 1, Dynamic> RowVectorX##S;                                \
@@ -548,8 +564,8 @@ typedef Matrix<double, 6, 1> Vector6d;
 typedef Matrix<double, 6, 6> Matrix6d;
 template <typename T, int N> using Vector = Matrix<T, N, 1>;
 
-template <typename T, int R, int C> LDLT<Matrix<T, R, C>> Matrix<T, R, C>::ldlt() const { return LDLT<Matrix<T, R, C>>(*this); }
-template <typename T, int R, int C> JacobiSVD<Matrix<T, R, C>> Matrix<T, R, C>::jacobiSvd(unsigned o) const { return JacobiSVD<Matrix<T, R, C>>(*this, o); }
+template <typename T, int R, int C, int Opt> LDLT<Matrix<T, R, C, Opt>> Matrix<T, R, C, Opt>::ldlt() const { return LDLT<Matrix<T, R, C, Opt>>(*this); }
+template <typename T, int R, int C, int Opt> JacobiSVD<Matrix<T, R, C, Opt>> Matrix<T, R, C, Opt>::jacobiSvd(unsigned o) const { return JacobiSVD<Matrix<T, R, C, Opt>>(*this, o); }
 } // namespace Eigen
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
 #define EIGEN_STL_VECTOR_SPECIALIZATION_H

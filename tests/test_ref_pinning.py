@@ -281,6 +281,51 @@ def test_aggregator_minimal_line_and_segment_cut():
         assert _close(sa, sb, 1e-9)
 
 
+def test_refinement_residual_functors():
+    """a14/a15: the reference's GeometricRefinementFunctor / VPConstraintsFunctor (cost_functions.h), compiled and
+    evaluated on forward-mode jets, against the restatement the LM oracle is built from: residuals AND the 6-column
+    Jacobians, PINHOLE and SIMPLE_PINHOLE, unnormalised quaternions included."""
+    rng = np.random.default_rng(306)
+    L, R = orc.lib(), ref.lib()
+    L.orc_geometric_residual.argtypes = [C.c_void_p] * 5 + [C.c_double] + [C.c_void_p] * 2
+    L.orc_vp_residual.argtypes = [C.c_void_p] * 6
+    L.orc_minimal_from_line.argtypes = [C.c_void_p] * 2
+    p = orc._p
+    worst = 0.0
+    for it in range(20000):
+        model = it & 1
+        f = rng.uniform(300, 900)
+        params = np.array([f, rng.uniform(300, 400), rng.uniform(200, 300)]) if model == 0 else \
+            np.array([f, f * rng.uniform(0.9, 1.1), rng.uniform(300, 400), rng.uniform(200, 300)])
+        kvec = np.array([params[0], params[0], params[1], params[2]]) if model == 0 else params.copy()
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        q *= rng.choice([1.0, 1.0, 0.7, 1.3])     # ceres::QuaternionToRotation normalises: not assumed unit
+        t = rng.normal(size=3) * 2
+        line = rng.normal(size=6) * 3
+        x = np.zeros(6)
+        L.orc_minimal_from_line(p(line), p(x))
+        x += rng.normal(scale=0.01, size=6)       # off the manifold too: the functors are ambient
+        seg = rng.uniform(0, 700, 4)
+        alpha = float(rng.choice([10.0, 0.0, 3.0]))
+        ra, ja, rb, jb = np.zeros(2), np.zeros(12), np.zeros(2), np.zeros(12)
+        L.orc_geometric_residual(p(x), p(seg), p(kvec), p(q), p(t), alpha, p(ra), p(ja))
+        R.ref_geometric_residual(model, p(x), p(seg), p(params), p(q), p(t), alpha, p(rb), p(jb))
+        s = max(1.0, np.abs(rb).max())
+        assert np.abs(ra - rb).max() <= 1e-9 * s, (it, ra, rb)
+        sj = max(1.0, np.abs(jb).max())
+        assert np.abs(ja - jb).max() <= 1e-8 * sj, (it, ja, jb)
+        worst = max(worst, np.abs(ja - jb).max() / sj)
+        vp = rng.normal(size=3)
+        vp /= np.linalg.norm(vp)
+        va, vja, vb, vjb = np.zeros(1), np.zeros(6), np.zeros(1), np.zeros(6)
+        L.orc_vp_residual(p(x), p(vp), p(kvec), p(q), p(va), p(vja))
+        R.ref_vp_residual(model, p(x), p(vp), p(params), p(q), p(vb), p(vjb))
+        assert abs(va[0] - vb[0]) <= 1e-10, (it, va, vb)
+        assert np.abs(vja - vjb).max() <= 1e-8 * max(1.0, np.abs(vjb).max()), (it, vja, vjb)
+    assert worst < 1e-8
+
+
 def test_track_filters_and_remerge():
     from limap_b200.synth import make_track_lines, make_tracks
     ts = make_tracks(T=400, S=10, V=40, seed=305, noise_px=2.0)
