@@ -33,6 +33,11 @@ static constexpr int kWarps = kThreads / 32;
 #ifndef LM_TRI_TMA
 #define LM_TRI_TMA 0
 #endif
+// Phase A in two passes (fast instantiation): the gates that need no 3D point for every row, stable compaction of the
+// survivors, then triangulation on dense lanes.
+#ifndef LM_TRI_SPLIT_A
+#define LM_TRI_SPLIT_A 1
+#endif
 #ifndef LM_KFLUSH
 #define LM_KFLUSH 64
 #endif
@@ -210,11 +215,8 @@ LM_D bool sensitivity_exceeds(const TriParams &p, const ViewD &v, vec3<double> X
 // One match row -> candidate. Steps follow triangulateOneNode "Step 3" (base_line_triangulator.cc:290-326).
 // Unit-vector normalisations that do not change a decision or an output beyond rounding are dropped; the
 // angle / sensitivity gates use margin forms with the reference's acos form as the tie fallback.
-template <bool ALLOW_ENDP>
-LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const ViewD &v2, const Src &src, uint32_t ngv, uint32_t ngl,
-                        Cand &c, double4 &l2out) {
-  const double4 l2 = ld_seg(&p.segs[p.line_off[ngv] + ngl]);
-  l2out = l2;
+// The gates of a match row that need no 3D point: segment length, ray-plane angles, epipolar IoU (:290-305).
+LM_D bool cand_gates(const TriParams &p, const ViewD &v2, const Src &src, const double4 &l2) {
   const vec2<double> s2 = mk2(l2.x, l2.y), e2 = mk2(l2.z, l2.w);
   const vec2<double> v2d = e2 - s2;
   const double len2sq = dot(v2d, v2d);
@@ -277,6 +279,15 @@ LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const ViewD &v2, co
     }
     if (IoU < p.IoU_threshold) return false;
   }
+  return true;
+}
+
+// Triangulation of a row that passed cand_gates, with the gates on the 3D points (:306-326).
+template <bool ALLOW_ENDP>
+LM_D bool cand_triangulate(const TriParams &p, const ViewD &v1, const ViewD &v2, const Src &src, const double4 &l2, Cand &c) {
+  const vec3<double> c2s = mat3_mul_h(v2.M, l2.x, l2.y);
+  const vec3<double> c2e = mat3_mul_h(v2.M, l2.z, l2.w);
+  const vec3<double> C2 = mk3(v2.C[0], v2.C[1], v2.C[2]);
   vec3<double> Xs, Xe;
   const double EPS = consts<double>::eps();
   if (!ALLOW_ENDP || !p.use_endpoints_triangulation) {
@@ -328,6 +339,14 @@ LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const ViewD &v2, co
   c.s = Xs;
   c.e = Xe;
   return true;
+}
+
+template <bool ALLOW_ENDP>
+LM_D bool gen_candidate(const TriParams &p, const ViewD &v1, const ViewD &v2, const Src &src, uint32_t ngv, uint32_t ngl,
+                        Cand &c, double4 &l2out) {
+  const double4 l2 = ld_seg(&p.segs[p.line_off[ngv] + ngl]);
+  l2out = l2;
+  return cand_gates(p, v2, src, l2) && cand_triangulate<ALLOW_ENDP>(p, v1, v2, src, l2, c);
 }
 
 // triangulate_line_with_direction (triangulation/functions.cc:389-446) for a VP proposal
@@ -596,7 +615,7 @@ template <bool SLAB, bool VP, bool FAST>
 __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(const __grid_constant__ TriParams p) {
   constexpr int NS = VP ? 3 : 1; // proposal slots per match row: [vp1, vp2, algebraic] (base_line_triangulator.cc:258-326)
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_wtot[kWarps];
+  __shared__ int s_wtot[2][kWarps];
   __shared__ int s_nvalid;
   __shared__ int s_next_row;
   __shared__ __align__(8) unsigned long long s_mbar; // completion of the neighbour-view bulk copies of a node
@@ -653,13 +672,13 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
           const int o = __shfl_up_sync(0xffffffffu, incl, d);
           if (lane >= d) incl += o;
         }
-        if (lane == 31) s_wtot[warp] = incl;
+        if (lane == 31) s_wtot[0][warp] = incl;
         __syncthreads();
         int woff = 0, tot = 0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
-          if (w < warp) woff += s_wtot[w];
-          tot += s_wtot[w];
+          if (w < warp) woff += s_wtot[0][w];
+          tot += s_wtot[0][w];
         }
         const int slot = carry + woff + incl - 1;
         if (r < nrows) slots[r] = (uint8_t)min(slot, 255);
@@ -691,6 +710,89 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
       mbar_parity ^= 1u;
     }
     int count = 0;
+    if constexpr (FAST && !VP && LM_TRI_SPLIT_A) {
+      // pass 1: length / ray-plane angle / epipolar IoU gates, one thread per match row; the rows that pass are listed
+      // in order (ballot + warp totals; the totals alternate between two arrays, so one barrier per 128 rows)
+      uint16_t *surv = sl.sidx; // [nrows <= cap]; rewritten by the depth sort afterwards
+      int ns = 0, par = 0;
+      for (int base = 0; base < nrows; base += kThreads, par ^= 1) {
+        const int r = base + tid;
+        bool ok = false;
+        if (r < nrows) {
+          p.row_state[(int64_t)(r0 + r)] = 0;
+          if (src.ok) {
+            const uint32_t ng = __ldg(&p.row_ng[r0 + r]);
+            const uint32_t ngv = ng >> 16, ngl = ng & 0xffffu;
+            const double4 l2 = ld_seg(&p.segs[p.line_off[ngv] + ngl]);
+            ok = cand_gates(p, p.views[ngv], src, l2);
+          }
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_wtot[par][warp] = __popc(b);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          if (w < warp) woff += s_wtot[par][w];
+          tot += s_wtot[par][w];
+        }
+        if (ok) surv[ns + woff + __popc(b & lt_mask)] = (uint16_t)r;
+        ns += tot;
+      }
+      __syncthreads();
+      // pass 2: triangulation + the gates on the 3D points, one thread per surviving row; stable compaction again
+      for (int base = 0; base < ns; base += kThreads, par ^= 1) {
+        const int t = base + tid;
+        Cand c;
+        bool ok = false;
+        double4 l2 = make_double4(0, 0, 0, 0);
+        uint32_t ng = 0;
+        int r = 0;
+        if (t < ns) {
+          r = surv[t];
+          ng = __ldg(&p.row_ng[r0 + r]);
+          const uint32_t ngv = ng >> 16, ngl = ng & 0xffffu;
+          l2 = ld_seg(&p.segs[p.line_off[ngv] + ngl]);
+          ok = cand_triangulate<false>(p, v1, p.views[ngv], src, l2, c);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_wtot[par][warp] = __popc(b);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          if (w < warp) woff += s_wtot[par][w];
+          tot += s_wtot[par][w];
+        }
+        if (ok) {
+          const int idx = count + woff + __popc(b & lt_mask);
+          const vec3<double> dr = c.e - c.s;
+          const double dn2 = dot(dr, dr);
+          const vec3<double> d = (dn2 > 0.0) ? dr * (1.0 / sqrt(dn2)) : dr;
+          sl.sx[idx] = c.s.x; sl.sy[idx] = c.s.y; sl.sz[idx] = c.s.z;
+          sl.ex[idx] = c.e.x; sl.ey[idx] = c.e.y; sl.ez[idx] = c.e.z;
+          sl.dx[idx] = d.x; sl.dy[idx] = d.y; sl.dz[idx] = d.z;
+          sl.zs[idx] = c.zs; sl.ze[idx] = c.ze; sl.unc[idx] = c.unc;
+          sl.q0[idx] = l2.x; sl.q1[idx] = l2.y; sl.q2[idx] = l2.z; sl.q3[idx] = l2.w;
+          const double zs1 = c.zs + consts<double>::eps(), ze1 = c.ze + consts<double>::eps();
+          const double qx = l2.z - l2.x, qy = l2.w - l2.y;
+          sl.izs2[idx] = 1.0 / (zs1 * zs1); sl.ize2[idx] = 1.0 / (ze1 * ze1); sl.inb[idx] = 1.0 / (qx * qx + qy * qy);
+          sl.ng[idx] = ng;
+          sl.row[idx] = (uint32_t)r;
+          // fp32 gate record (see the one-pass variant below for the limits)
+          const double rad = fmax(fabs(c.lam_s), fabs(c.lam_e));
+          const double ls = p.l3d.th_scaleinv * zs1 * 1.005 + 1e-5 * rad;
+          const double le = p.l3d.th_scaleinv * ze1 * 1.005 + 1e-5 * rad;
+          GateRecF g;
+          g.dx = (float)d.x; g.dy = (float)d.y; g.dz = (float)d.z; g.lam_e = (float)c.lam_e;
+          g.lam_s = (float)c.lam_s; g.lim_s = (float)(ls * 1.000001); g.lim_e = (float)(le * 1.000001);
+          g.img = (int)(ng >> 16);
+          sl.gatef[idx] = g;
+          reinterpret_cast<float *>(sl.psc)[idx] = g.lam_s;
+        }
+        count += tot;
+      }
+    } else
     for (int base = 0; base < nrows; base += kThreads) {
       const int r = base + tid;
       Cand cs[NS];
@@ -747,13 +849,13 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         const int o = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += o;
       }
-      if (lane == 31) s_wtot[warp] = incl;
+      if (lane == 31) s_wtot[0][warp] = incl;
       __syncthreads();
       int woff = 0, tot = 0;
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) {
-        if (w < warp) woff += s_wtot[w];
-        tot += s_wtot[w];
+        if (w < warp) woff += s_wtot[0][w];
+        tot += s_wtot[0][w];
       }
       int idx = count + woff + incl - cnt;
 #pragma unroll
