@@ -49,6 +49,9 @@ struct WarpState {
   Normal N;  // at x
   Normal Nc; // at the candidate point
   double cn2[4];
+  // trust-region scalars (warp-uniform; every lane writes the same value, so no ordering is needed): kept here and
+  // accessed through volatile references so that they are not live in registers across the track evaluations
+  double cost0, cost, radius, decrease_factor, mcc, sn;
 };
 
 // Evaluate the whole track at x: cost (always) and, if want_jac, the loss-corrected normal equations with the
@@ -57,6 +60,7 @@ struct WarpState {
 // `acc` = this thread's column of the CTA's accumulator table ([19][kLmThreads] doubles in shared memory: the partial
 // sums of J^T J (10), J^T r (4), cost (1), column norms (4) stay out of the registers while a block is evaluated).
 static constexpr int kLmThreads = 128;
+static constexpr int kAccStride = kLmThreads + 1; // doubles between two accumulator rows (bank spread for the row sums)
 LM_D void eval_track(const LMBlockDev *blocks, int S, const double *x, double alpha, double bq, bool want_jac,
                      const double *scale, LineShared &Ls, Normal *out, double *cn2_out, double *acc) {
   const int lane = threadIdx.x & 31;
@@ -77,8 +81,11 @@ LM_D void eval_track(const LMBlockDev *blocks, int S, const double *x, double al
     }
     __syncwarp();
   }
+  // Accumulators: one column of the CTA's table per thread, written through a volatile pointer so that they really
+  // stay in shared memory (promoted to registers they would be live across the whole block evaluation: 38 registers).
+  volatile double *va = acc;
 #pragma unroll
-  for (int i = 0; i < 19; ++i) acc[i * kLmThreads] = 0.0;
+  for (int i = 0; i < 19; ++i) va[i * kAccStride] = 0.0;
   const double cq = 1.0 / bq;
   for (int k = lane; k < S; k += 32) {
     const LMBlockDev &B = blocks[k];
@@ -92,7 +99,7 @@ LM_D void eval_track(const LMBlockDev *blocks, int S, const double *x, double al
     {
       double cost = 0.5 * rho0;
       if (Bwvp > 0.0) cost += 0.5 * Bwvp * e.rv * e.rv; // ScaledLoss(TrivialLoss, w * vp_multiplier)
-      acc[14 * kLmThreads] += cost;
+      va[14 * kAccStride] += cost;
     }
     if (!want_jac) continue;
     const double sqrt_rho1 = sqrt(rho1);
@@ -112,8 +119,6 @@ LM_D void eval_track(const LMBlockDev *blocks, int S, const double *x, double al
         J0[c] = sqrt_rho1 * (e.J[c] - alpha_sq_norm * e.r[0] * rtj);
         J1[c] = sqrt_rho1 * (e.J[4 + c] - alpha_sq_norm * e.r[1] * rtj);
       }
-      acc[(15 + c) * kLmThreads] += J0[c] * J0[c] + J1[c] * J1[c];
-      if (scale) { J0[c] *= scale[c]; J1[c] *= scale[c]; }
     }
     const double r0 = e.r[0] * residual_scaling, r1 = e.r[1] * residual_scaling;
     double J2[4] = {0, 0, 0, 0}, r2 = 0.0;
@@ -121,32 +126,36 @@ LM_D void eval_track(const LMBlockDev *blocks, int S, const double *x, double al
       const double sq = sqrt(Bwvp);
       r2 = sq * e.rv;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        J2[c] = sq * e.Jv[c];
-        acc[(15 + c) * kLmThreads] += J2[c] * J2[c];
-        if (scale) J2[c] *= scale[c];
-      }
+      for (int c = 0; c < 4; ++c) J2[c] = sq * e.Jv[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      va[(15 + c) * kAccStride] += J0[c] * J0[c] + J1[c] * J1[c] + J2[c] * J2[c];
+      if (scale) { const double sc = scale[c]; J0[c] *= sc; J1[c] *= sc; J2[c] *= sc; }
     }
     int idx = 0;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      acc[(10 + a) * kLmThreads] += J0[a] * r0 + J1[a] * r1 + J2[a] * r2;
+      va[(10 + a) * kAccStride] += J0[a] * r0 + J1[a] * r1 + J2[a] * r2;
 #pragma unroll
-      for (int b = a; b < 4; ++b) { acc[idx * kLmThreads] += J0[a] * J0[b] + J1[a] * J1[b] + J2[a] * J2[b]; ++idx; }
+      for (int b = a; b < 4; ++b) { va[idx * kAccStride] += J0[a] * J0[b] + J1[a] * J1[b] + J2[a] * J2[b]; ++idx; }
     }
   }
-  {
-    const double cost = warp_sum(acc[14 * kLmThreads]);
-    if (lane == 0) out->cost = cost;
-  }
-  if (want_jac) {
+  __syncwarp();
+  // Reduction across the warp's 32 columns: lane i adds up accumulator i (4 partial sums, fixed order) instead of 19
+  // butterfly reductions of 5 shuffle rounds each. The row stride (kAccStride = 129 doubles) keeps the 19 lanes on
+  // different banks.
+  if (lane < 19) {
+    const volatile double *row = acc - lane + lane * kAccStride; // this warp's 32 columns of row `lane`
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) { const double v = warp_sum(acc[i * kLmThreads]); if (lane == 0) out->A[i] = v; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const double v = warp_sum(acc[(10 + i) * kLmThreads]);
-      if (lane == 0) out->g[i] = v;
-      if (cn2_out) { const double w = warp_sum(acc[(15 + i) * kLmThreads]); if (lane == 0) cn2_out[i] = w; }
+    for (int j = 0; j < 32; j += 4) { s0 += row[j]; s1 += row[j + 1]; s2 += row[j + 2]; s3 += row[j + 3]; }
+    const double v = (s0 + s1) + (s2 + s3);
+    if (lane == 14) out->cost = v;
+    if (want_jac) {
+      if (lane < 10) out->A[lane] = v;
+      else if (lane < 14) out->g[lane - 10] = v;
+      else if (lane > 14 && cn2_out) cn2_out[lane - 15] = v;
     }
   }
   __syncwarp();
@@ -188,7 +197,7 @@ LM_D bool chol_solve4(const double Au[10], const double dg[4], const double b[4]
 // MB = resident CTAs per SM the register allocation is bounded for (2: 255 registers, 3: 168, 4: 128).
 template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(const __grid_constant__ LMParams p) {
   __shared__ WarpState s_ws[4];
-  __shared__ double s_acc[19 * kLmThreads];
+  __shared__ double s_acc[19 * kAccStride];
   double *acc = s_acc + threadIdx.x;
   const int warp_in_block = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -207,10 +216,11 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
   __syncwarp();
   const double bq = p.cauchy_scale * p.cauchy_scale;
   int it = 0, successful = 0, term = 0;
-  double cost0, cost;
+  volatile double &cost0 = ws.cost0, &cost = ws.cost, &radius = ws.radius, &decrease_factor = ws.decrease_factor;
+  volatile double &mcc = ws.mcc, &sn = ws.sn;
   if (S == 0 || !p.active[t]) {
     eval_track(blocks, S, ws.x, p.geometric_alpha, bq, false, nullptr, ws.L, &ws.N, nullptr, acc);
-    cost0 = cost = ws.N.cost;
+    { const double c_ = ws.N.cost; cost0 = c_; cost = c_; }
   } else {
     // iteration 0: evaluate, fix the Jacobi scaling 1/(1+||J_col||)
     eval_track(blocks, S, ws.x, p.geometric_alpha, bq, true, nullptr, ws.L, &ws.N, ws.cn2, acc);
@@ -228,8 +238,8 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
       for (int c = 0; c < 4; ++c) ws.diag[c] = 0.0;
     }
     __syncwarp();
-    cost0 = cost = ws.N.cost;
-    double radius = 1e4, decrease_factor = 2.0;
+    { const double c_ = ws.N.cost; cost0 = c_; cost = c_; }
+    radius = 1e4; decrease_factor = 2.0;
     bool reuse_diagonal = false;
     int invalid = 0;
     while (true) {
@@ -255,13 +265,15 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
       // the 4x4 solve is warp-uniform: every lane computes it from the shared state (no divergence, no extra issue slots)
       double step[4];
       bool ok;
-      double mcc = 0;
+      mcc = 0;
       {
         double An[10], gn[4], dg[4];
 #pragma unroll
         for (int c = 0; c < 10; ++c) An[c] = ws.N.A[c];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { gn[c] = ws.N.g[c]; dg[c] = ws.diag[c] / radius; }
+        const double rad_ = radius;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { gn[c] = ws.N.g[c]; dg[c] = ws.diag[c] / rad_; }
         ok = chol_solve4(An, dg, gn, step);
 #pragma unroll
         for (int c = 0; c < 4; ++c) { step[c] = -step[c]; if (!isfinite(step[c])) ok = false; }
@@ -280,12 +292,12 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
       }
       if (!ok || !(mcc > 0.0)) {
         if (++invalid >= p.max_invalid) { term = 4; break; }
-        radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+        { const double r_ = radius, f_ = decrease_factor; __syncwarp(); radius = r_ / f_; decrease_factor = f_ * 2.0; } reuse_diagonal = true;
         continue;
       }
       invalid = 0;
-      double sn = 0;
       {
+        double snl = 0;
         double xr[6], delta[4], cand[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) xr[c] = ws.x[c];
@@ -294,7 +306,8 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
         quat_plus(xr, delta, cand);
         sphere2_plus(xr + 4, delta[3], cand + 4);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) sn += (xr[c] - cand[c]) * (xr[c] - cand[c]);
+        for (int c = 0; c < 6; ++c) snl += (xr[c] - cand[c]) * (xr[c] - cand[c]);
+        sn = snl;
         __syncwarp();
         if (lane == 0) {
 #pragma unroll
@@ -308,8 +321,9 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
       eval_track(blocks, S, ws.cand, p.geometric_alpha, bq, true, ws.scale, ws.L, &ws.Nc, nullptr, acc);
       const double cost_c = ws.Nc.cost;
       if (!(sqrt(sn) > 0.0)) { term = 5; break; }
-      if (!(fabs(cost - cost_c) > 0.0)) { term = 6; break; }
-      const double rel = (cost - cost_c) / mcc;
+      const double cost_x = cost;
+      if (!(fabs(cost_x - cost_c) > 0.0)) { term = 6; break; }
+      const double rel = (cost_x - cost_c) / mcc;
       if (rel > 1e-3) {
         __syncwarp();
         if (lane < 6) ws.x[lane] = ws.cand[lane];
@@ -318,12 +332,11 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
         __syncwarp();
         cost = cost_c;
         const double tq = 2.0 * rel - 1.0;
-        radius = radius / fmax(1.0 / 3.0, 1.0 - tq * tq * tq);
-        radius = fmin(1e16, radius);
+        { const double r_ = radius; __syncwarp(); radius = fmin(1e16, r_ / fmax(1.0 / 3.0, 1.0 - tq * tq * tq)); }
         decrease_factor = 2.0; reuse_diagonal = false;
         ++successful;
       } else {
-        radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+        { const double r_ = radius, f_ = decrease_factor; __syncwarp(); radius = r_ / f_; decrease_factor = f_ * 2.0; } reuse_diagonal = true;
       }
     }
   }

@@ -33,11 +33,6 @@ static constexpr int kWarps = kThreads / 32;
 #ifndef LM_TRI_TMA
 #define LM_TRI_TMA 0
 #endif
-// Phase A in two passes (fast instantiation): the gates that need no 3D point for every row, stable compaction of the
-// survivors, then triangulation on dense lanes.
-#ifndef LM_TRI_SPLIT_A
-#define LM_TRI_SPLIT_A 1
-#endif
 #ifndef LM_KFLUSH
 #define LM_KFLUSH 64
 #endif
@@ -615,7 +610,7 @@ template <bool SLAB, bool VP, bool FAST>
 __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(const __grid_constant__ TriParams p) {
   constexpr int NS = VP ? 3 : 1; // proposal slots per match row: [vp1, vp2, algebraic] (base_line_triangulator.cc:258-326)
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_wtot[2][kWarps];
+  __shared__ int s_wtot[kWarps];
   __shared__ int s_nvalid;
   __shared__ int s_next_row;
   __shared__ __align__(8) unsigned long long s_mbar; // completion of the neighbour-view bulk copies of a node
@@ -672,13 +667,13 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
           const int o = __shfl_up_sync(0xffffffffu, incl, d);
           if (lane >= d) incl += o;
         }
-        if (lane == 31) s_wtot[0][warp] = incl;
+        if (lane == 31) s_wtot[warp] = incl;
         __syncthreads();
         int woff = 0, tot = 0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
-          if (w < warp) woff += s_wtot[0][w];
-          tot += s_wtot[0][w];
+          if (w < warp) woff += s_wtot[w];
+          tot += s_wtot[w];
         }
         const int slot = carry + woff + incl - 1;
         if (r < nrows) slots[r] = (uint8_t)min(slot, 255);
@@ -710,89 +705,6 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
       mbar_parity ^= 1u;
     }
     int count = 0;
-    if constexpr (FAST && !VP && LM_TRI_SPLIT_A) {
-      // pass 1: length / ray-plane angle / epipolar IoU gates, one thread per match row; the rows that pass are listed
-      // in order (ballot + warp totals; the totals alternate between two arrays, so one barrier per 128 rows)
-      uint16_t *surv = sl.sidx; // [nrows <= cap]; rewritten by the depth sort afterwards
-      int ns = 0, par = 0;
-      for (int base = 0; base < nrows; base += kThreads, par ^= 1) {
-        const int r = base + tid;
-        bool ok = false;
-        if (r < nrows) {
-          p.row_state[(int64_t)(r0 + r)] = 0;
-          if (src.ok) {
-            const uint32_t ng = __ldg(&p.row_ng[r0 + r]);
-            const uint32_t ngv = ng >> 16, ngl = ng & 0xffffu;
-            const double4 l2 = ld_seg(&p.segs[p.line_off[ngv] + ngl]);
-            ok = cand_gates(p, p.views[ngv], src, l2);
-          }
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) s_wtot[par][warp] = __popc(b);
-        __syncthreads();
-        int woff = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-          if (w < warp) woff += s_wtot[par][w];
-          tot += s_wtot[par][w];
-        }
-        if (ok) surv[ns + woff + __popc(b & lt_mask)] = (uint16_t)r;
-        ns += tot;
-      }
-      __syncthreads();
-      // pass 2: triangulation + the gates on the 3D points, one thread per surviving row; stable compaction again
-      for (int base = 0; base < ns; base += kThreads, par ^= 1) {
-        const int t = base + tid;
-        Cand c;
-        bool ok = false;
-        double4 l2 = make_double4(0, 0, 0, 0);
-        uint32_t ng = 0;
-        int r = 0;
-        if (t < ns) {
-          r = surv[t];
-          ng = __ldg(&p.row_ng[r0 + r]);
-          const uint32_t ngv = ng >> 16, ngl = ng & 0xffffu;
-          l2 = ld_seg(&p.segs[p.line_off[ngv] + ngl]);
-          ok = cand_triangulate<false>(p, v1, p.views[ngv], src, l2, c);
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) s_wtot[par][warp] = __popc(b);
-        __syncthreads();
-        int woff = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-          if (w < warp) woff += s_wtot[par][w];
-          tot += s_wtot[par][w];
-        }
-        if (ok) {
-          const int idx = count + woff + __popc(b & lt_mask);
-          const vec3<double> dr = c.e - c.s;
-          const double dn2 = dot(dr, dr);
-          const vec3<double> d = (dn2 > 0.0) ? dr * (1.0 / sqrt(dn2)) : dr;
-          sl.sx[idx] = c.s.x; sl.sy[idx] = c.s.y; sl.sz[idx] = c.s.z;
-          sl.ex[idx] = c.e.x; sl.ey[idx] = c.e.y; sl.ez[idx] = c.e.z;
-          sl.dx[idx] = d.x; sl.dy[idx] = d.y; sl.dz[idx] = d.z;
-          sl.zs[idx] = c.zs; sl.ze[idx] = c.ze; sl.unc[idx] = c.unc;
-          sl.q0[idx] = l2.x; sl.q1[idx] = l2.y; sl.q2[idx] = l2.z; sl.q3[idx] = l2.w;
-          const double zs1 = c.zs + consts<double>::eps(), ze1 = c.ze + consts<double>::eps();
-          const double qx = l2.z - l2.x, qy = l2.w - l2.y;
-          sl.izs2[idx] = 1.0 / (zs1 * zs1); sl.ize2[idx] = 1.0 / (ze1 * ze1); sl.inb[idx] = 1.0 / (qx * qx + qy * qy);
-          sl.ng[idx] = ng;
-          sl.row[idx] = (uint32_t)r;
-          // fp32 gate record (see the one-pass variant below for the limits)
-          const double rad = fmax(fabs(c.lam_s), fabs(c.lam_e));
-          const double ls = p.l3d.th_scaleinv * zs1 * 1.005 + 1e-5 * rad;
-          const double le = p.l3d.th_scaleinv * ze1 * 1.005 + 1e-5 * rad;
-          GateRecF g;
-          g.dx = (float)d.x; g.dy = (float)d.y; g.dz = (float)d.z; g.lam_e = (float)c.lam_e;
-          g.lam_s = (float)c.lam_s; g.lim_s = (float)(ls * 1.000001); g.lim_e = (float)(le * 1.000001);
-          g.img = (int)(ng >> 16);
-          sl.gatef[idx] = g;
-          reinterpret_cast<float *>(sl.psc)[idx] = g.lam_s;
-        }
-        count += tot;
-      }
-    } else
     for (int base = 0; base < nrows; base += kThreads) {
       const int r = base + tid;
       Cand cs[NS];
@@ -849,13 +761,13 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
         const int o = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += o;
       }
-      if (lane == 31) s_wtot[0][warp] = incl;
+      if (lane == 31) s_wtot[warp] = incl;
       __syncthreads();
       int woff = 0, tot = 0;
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) {
-        if (w < warp) woff += s_wtot[0][w];
-        tot += s_wtot[0][w];
+        if (w < warp) woff += s_wtot[w];
+        tot += s_wtot[w];
       }
       int idx = count + woff + incl - cnt;
 #pragma unroll
@@ -960,20 +872,14 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
       for (int pass = 0; pass < n_pass; ++pass) {
         const int g0 = (pass * kWarps + warp) * G;
         if (g0 >= C) break;
-        const int i = g0 + lane;
-        const bool act = lane < G && i < C;
-        GateRecF gi;
-        gi.dx = gi.dy = gi.dz = gi.lam_e = gi.lam_s = gi.lim_s = gi.lim_e = 0.f;
-        gi.img = -1;
+        const int Gact = min(G, C - g0);
+        // B-window, lane = row: two binary searches over the sorted start distances
         int lo = 0, W = 0;
-        if (act) {
-          const float4 a0 = *reinterpret_cast<const float4 *>(&sl.gatef[i].dx);
-          const float4 a1 = *reinterpret_cast<const float4 *>(&sl.gatef[i].lam_s);
-          gi.dx = a0.x; gi.dy = a0.y; gi.dz = a0.z; gi.lam_e = a0.w;
-          gi.lam_s = a1.x; gi.lim_s = a1.y; gi.lim_e = a1.z; gi.img = __float_as_int(a1.w);
+        if (lane < Gact) {
+          const float4 a1 = *reinterpret_cast<const float4 *>(&sl.gatef[g0 + lane].lam_s);
           int hi = C;
-          if (gi.lim_s < 3e37f) { // (false for inf / NaN limits: the whole node is the window then)
-            const float wa = gi.lam_s - gi.lim_s, wb = gi.lam_s + gi.lim_s;
+          if (a1.y < 3e37f) { // (false for inf / NaN limits: the whole node is the window then)
+            const float wa = a1.x - a1.y, wb = a1.x + a1.y;
             int l = 0, h = C;
             while (l < h) { const int m = (l + h) >> 1; if (slam[m] < wa) l = m + 1; else h = m; }
             lo = l;
@@ -983,107 +889,110 @@ __global__ void __launch_bounds__(kThreads, LM_TRI_MIN_BLOCKS) tri_node_kernel(c
           }
           W = hi - lo;
         }
-        int Wmax = W;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) Wmax = max(Wmax, __shfl_xor_sync(FULL, Wmax, d));
-        // B-gate: the other fp32 gates over the window; the partners of a row are remembered as a bit mask of window
-        // positions (windows of more than 64 candidates are simply re-tested when the partners are written)
-        int n = 0;
-        unsigned long long pmask = 0ull;
-        for (int t = 0; t < Wmax; ++t) {
-          if (t < W) {
-            const int j = sidx[lo + t];
-            const float4 gj = *reinterpret_cast<const float4 *>(&sl.gatef[j].dx);
-            const int imgj = sl.gatef[j].img;
-            const bool pass = (imgj != gi.img) && !(fabsf(gj.w - gi.lam_e) > gi.lim_e) &&
-                              !(fabsf(gi.dx * gj.x + gi.dy * gj.y + gi.dz * gj.z) < p.cos_th3d_f);
-            n += pass;
-            if (pass && t < 64) pmask |= 1ull << t;
-          }
-        }
-        int incl = n;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int o = __shfl_up_sync(FULL, incl, d);
-          if (lane >= d) incl += o;
-        }
-        const int off = incl - n;
-        n1_total += (unsigned long long)__shfl_sync(FULL, incl, 31);
-        // rows are taken in chunks whose partners fit the pair list (one chunk unless the node is very dense)
-        int lane_begin = 0;
-        while (lane_begin < 32) {
-          const int s0 = __shfl_sync(FULL, off, lane_begin);
-          const bool in = lane >= lane_begin && (off + n - s0) <= p.cap; // a prefix of the lanes >= lane_begin, never empty
-          const int lane_end = lane_begin + __popc(__ballot_sync(FULL, in));
-          const int total_c = __shfl_sync(FULL, incl, lane_end - 1) - s0;
-          // write the partners of every row of the chunk at the row's own offset, in ascending candidate order
-          // (= ascending neighbour image: candidates are generated image by image), by insertion: rows have few partners
-          if (in && n > 0) {
-            uint16_t *row_ent = pent + (off - s0);
-            int c = 0;
-            if (W <= 64) {
-              unsigned long long m = pmask;
-              while (m) {
-                const int t = __ffsll((long long)m) - 1;
-                m &= m - 1;
-                const uint16_t j = sidx[lo + t];
-                int pos = c;
-                while (pos > 0 && row_ent[pos - 1] > j) { row_ent[pos] = row_ent[pos - 1]; --pos; }
-                row_ent[pos] = j;
-                ++c;
-              }
-            } else {
-              const float4 a0 = *reinterpret_cast<const float4 *>(&sl.gatef[i].dx);
-              const float4 a1 = *reinterpret_cast<const float4 *>(&sl.gatef[i].lam_s);
-              for (int t = 0; t < W; ++t) {
-                const uint16_t j = sidx[lo + t];
+        int rr = 0;
+        while (rr < Gact) {
+          // B-gate, one row at a time, lane = window position: the other fp32 gates (end-point interval, angle, other
+          // image). The partners of a row are written in ascending candidate order (= ascending neighbour image:
+          // candidates are generated image by image) at the running fill of the warp's pair list; lane r keeps the
+          // offset and the count of row r of the chunk. A chunk ends when the next row would not fit the list.
+          const int cb = rr;
+          int fill = 0, off = 0, n = 0;
+          for (; rr < Gact; ++rr) {
+            const int lo_r = __shfl_sync(FULL, lo, rr), W_r = __shfl_sync(FULL, W, rr);
+            const float4 a0 = *reinterpret_cast<const float4 *>(&sl.gatef[g0 + rr].dx);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&sl.gatef[g0 + rr].lam_s);
+            int n_r = 0;
+            if (W_r <= 32) {
+              int j = 0x7fffffff;
+              bool ok = false;
+              if (lane < W_r) {
+                j = sidx[lo_r + lane];
                 const float4 gj = *reinterpret_cast<const float4 *>(&sl.gatef[j].dx);
                 const int imgj = sl.gatef[j].img;
-                if ((imgj != __float_as_int(a1.w)) && !(fabsf(gj.w - a0.w) > a1.z) &&
-                    !(fabsf(a0.x * gj.x + a0.y * gj.y + a0.z * gj.z) < p.cos_th3d_f)) {
-                  int pos = c;
-                  while (pos > 0 && row_ent[pos - 1] > j) { row_ent[pos] = row_ent[pos - 1]; --pos; }
-                  row_ent[pos] = j;
-                  ++c;
+                ok = (imgj != __float_as_int(a1.w)) && !(fabsf(gj.w - a0.w) > a1.z) &&
+                     !(fabsf(a0.x * gj.x + a0.y * gj.y + a0.z * gj.z) < p.cos_th3d_f);
+              }
+              unsigned m = __ballot_sync(FULL, ok);
+              n_r = __popc(m);
+              if (n_r) {
+                if (fill + n_r > p.cap) break; // (a row has fewer than C <= cap partners: an empty list always takes it)
+                int rank = 0;
+                while (m) { // rank among the partners by candidate index: n_r independent shuffles
+                  const int t = __ffs((int)m) - 1;
+                  m &= m - 1;
+                  rank += __shfl_sync(FULL, j, t) < j;
                 }
+                if (ok) pent[fill + rank] = (uint16_t)j;
+              }
+            } else {
+              // wide window: partners appended unordered to scratch (the score slots of this chunk's tail are free until
+              // B-score), then placed by rank
+              uint16_t *tmp = reinterpret_cast<uint16_t *>(psc + fill);
+              bool fits = true;
+              for (int tb = 0; tb < W_r; tb += 32) {
+                const int t = tb + lane;
+                int j = 0;
+                bool ok = false;
+                if (t < W_r) {
+                  j = sidx[lo_r + t];
+                  const float4 gj = *reinterpret_cast<const float4 *>(&sl.gatef[j].dx);
+                  const int imgj = sl.gatef[j].img;
+                  ok = (imgj != __float_as_int(a1.w)) && !(fabsf(gj.w - a0.w) > a1.z) &&
+                       !(fabsf(a0.x * gj.x + a0.y * gj.y + a0.z * gj.z) < p.cos_th3d_f);
+                }
+                const unsigned m = __ballot_sync(FULL, ok);
+                if (fill + n_r + __popc(m) > p.cap) { fits = false; break; }
+                if (ok) tmp[n_r + __popc(m & lt_mask)] = (uint16_t)j;
+                n_r += __popc(m);
+              }
+              if (!fits) break;
+              __syncwarp();
+              // (tmp occupies 2 bytes per partner inside psc[fill ..), pent[fill ..) is a different array)
+              for (int e = lane; e < n_r; e += 32) {
+                const uint16_t v = tmp[e];
+                int rank = 0;
+                for (int x = 0; x < n_r; ++x) rank += tmp[x] < v;
+                pent[fill + rank] = v;
               }
             }
+            if (lane == rr) { off = fill; n = n_r; }
+            fill += n_r;
           }
+          const int ce = rr;
+          n1_total += (unsigned long long)fill;
           __syncwarp();
           // B-score: exact reference scores, lane = pair
-          for (int fb = 0; fb < total_c; fb += 32) {
+          for (int fb = 0; fb < fill; fb += 32) {
             const int f = fb + lane;
-            int r = lane_begin; // largest row of the chunk whose offset is <= f
+            int r = cb; // largest row of the chunk whose offset is <= f (rows without partners share the next offset)
 #pragma unroll
             for (int step = 16; step >= 1; step >>= 1) {
               const int cand = r + step;
               const int v = __shfl_sync(FULL, off, cand & 31);
-              if (cand < lane_end && v - s0 <= f) r = cand;
+              if (cand < ce && v <= f) r = cand;
             }
-            if (f < total_c) {
+            if (f < fill) {
               const int j = pent[f];
               psc[f] = pair_score_fast(p, sl, g0 + r, j, (uint32_t)sl.gatef[j].img);
             }
           }
-          n2_total += (unsigned long long)total_c;
+          n2_total += (unsigned long long)fill;
           __syncwarp();
           // B-sum: one image contributes its maximum once (:110-112), images in ascending order (the partners of a row
           // are sorted by candidate index, i.e. by image)
-          if (in && act) {
-            const int b = off - s0;
+          if (lane >= cb && lane < ce) {
             double sum = 0.0, mx = 0.0;
             int cur = -1;
             for (int e = 0; e < n; ++e) {
-              const int im = sl.gatef[pent[b + e]].img;
-              const double sc = psc[b + e];
+              const int im = sl.gatef[pent[off + e]].img;
+              const double sc = psc[off + e];
               if (im != cur) { sum += mx; cur = im; mx = sc; }
               else mx = (mx > sc) ? mx : sc;
             }
             sum += mx;
-            sl.score[i] = sum;
+            sl.score[g0 + lane] = sum;
           }
           __syncwarp();
-          lane_begin = lane_end;
         }
       }
       __syncthreads();
