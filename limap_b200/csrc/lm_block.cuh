@@ -46,8 +46,11 @@ template <int N> LM_HD Dual<N> dabs(const Dual<N> &f) { return f.a < 0 ? -f : f;
 LM_HD void quat_plus(const double x[4], const double d[3], double out[4]) {
   const double sq = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
   if (sq == 0.0) { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3]; return; }
-  const double nd = sqrt(sq), sbd = sin(nd) / nd;
-  const double z0 = cos(nd), z1 = sbd * d[0], z2 = sbd * d[1], z3 = sbd * d[2];
+  const double nd = sqrt(sq);
+  double sn_, cs_;
+  sincos(nd, &sn_, &cs_);
+  const double sbd = sn_ / nd;
+  const double z0 = cs_, z1 = sbd * d[0], z2 = sbd * d[1], z3 = sbd * d[2];
   out[0] = z0 * x[0] - z1 * x[1] - z2 * x[2] - z3 * x[3];
   out[1] = z0 * x[1] + z1 * x[0] + z2 * x[3] - z3 * x[2];
   out[2] = z0 * x[2] - z1 * x[3] + z2 * x[0] + z3 * x[1];
@@ -68,7 +71,9 @@ LM_HD void sphere2_plus(const double x[2], double delta, double out[2]) {
   if (nd == 0.0) { out[0] = x[0]; out[1] = x[1]; return; }
   double v[2], beta;
   householder2(x, v, beta);
-  const double y0 = sin(nd) / nd * delta, y1 = cos(nd);
+  double sn_, cs_;
+  sincos(nd, &sn_, &cs_);
+  const double y0 = sn_ / nd * delta, y1 = cs_;
   const double vty = v[0] * y0 + v[1] * y1;
   const double nx = sqrt(x[0] * x[0] + x[1] * x[1]);
   out[0] = nx * (y0 - v[0] * (beta * vty));

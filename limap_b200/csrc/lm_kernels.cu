@@ -161,36 +161,42 @@ LM_D void eval_track(const LMBlockDev *blocks, int S, const double *x, double al
   __syncwarp();
 }
 
+// Solve (A + diag(dg)) x = b for the symmetric positive definite 4x4 system of one LM step. Ceres' DENSE_NORMAL_CHOLESKY
+// is an LL^T factorisation; this is the square-root-free L D L^T form of the same factorisation (x agrees to rounding;
+// "not positive definite" <=> a pivot d_k <= 0 <=> LL^T meets a non-positive diagonal): 4 reciprocals instead of 4 square
+// roots and 14 divisions in what is a strictly sequential, warp-uniform chain.
 LM_D bool chol_solve4(const double Au[10], const double dg[4], const double b[4], double x[4]) {
-  // A = upper-triangle storage + dg on the diagonal
-  double A[4][4];
-  int idx = 0;
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int c = a; c < 4; ++c) { A[a][c] = Au[idx]; A[c][a] = Au[idx]; ++idx; }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) A[a][a] += dg[a];
-  double Lm[4][4] = {{0}};
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j <= i; ++j) {
-      double s = A[i][j];
-#pragma unroll
-      for (int k = 0; k < j; ++k) s -= Lm[i][k] * Lm[j][k];
-      if (i == j) { if (!(s > 0)) return false; Lm[i][i] = sqrt(s); }
-      else Lm[i][j] = s / Lm[j][j];
-    }
-  double y[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { double s = b[i];
-#pragma unroll
-    for (int k = 0; k < i; ++k) s -= Lm[i][k] * y[k]; y[i] = s / Lm[i][i]; }
-#pragma unroll
-  for (int i = 3; i >= 0; --i) { double s = y[i];
-#pragma unroll
-    for (int k = i + 1; k < 4; ++k) s -= Lm[k][i] * x[k]; x[i] = s / Lm[i][i]; }
+  // upper-triangle storage 00 01 02 03 11 12 13 22 23 33
+  const double a00 = Au[0] + dg[0], a10 = Au[1], a20 = Au[2], a30 = Au[3];
+  const double a11 = Au[4] + dg[1], a21 = Au[5], a31 = Au[6];
+  const double a22 = Au[7] + dg[2], a32 = Au[8];
+  const double a33 = Au[9] + dg[3];
+  const double d0 = a00;
+  if (!(d0 > 0)) return false;
+  const double i0 = 1.0 / d0;
+  const double l10 = a10 * i0, l20 = a20 * i0, l30 = a30 * i0;
+  const double d1 = a11 - l10 * a10;
+  if (!(d1 > 0)) return false;
+  const double i1 = 1.0 / d1;
+  const double u21 = a21 - l20 * a10, u31 = a31 - l30 * a10; // (L D) entries of column 1
+  const double l21 = u21 * i1, l31 = u31 * i1;
+  const double d2 = a22 - l20 * a20 - l21 * u21;
+  if (!(d2 > 0)) return false;
+  const double i2 = 1.0 / d2;
+  const double u32 = a32 - l30 * a20 - l31 * u21;
+  const double l32 = u32 * i2;
+  const double d3 = a33 - l30 * a30 - l31 * u31 - l32 * u32;
+  if (!(d3 > 0)) return false;
+  const double i3 = 1.0 / d3;
+  // L y = b, D z = y, L^T x = z
+  const double y0 = b[0];
+  const double y1 = b[1] - l10 * y0;
+  const double y2 = b[2] - l20 * y0 - l21 * y1;
+  const double y3 = b[3] - l30 * y0 - l31 * y1 - l32 * y2;
+  x[3] = y3 * i3;
+  x[2] = y2 * i2 - l32 * x[3];
+  x[1] = y1 * i1 - l21 * x[2] - l31 * x[3];
+  x[0] = y0 * i0 - l10 * x[1] - l20 * x[2] - l30 * x[3];
   return true;
 }
 
@@ -246,9 +252,11 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
       if (it >= p.max_num_iterations) { term = 1; break; }
       if (radius <= 1e-32) { term = 2; break; }
       {
+        // max |g_c / scale_c| <= 0 (the unscaled gradient is exactly zero): scale_c is in (0, 1], so the quotient is zero
+        // exactly when g_c is
         double gmax = 0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) gmax = fmax(gmax, fabs(ws.N.g[c] / ws.scale[c]));
+        for (int c = 0; c < 4; ++c) gmax = fmax(gmax, fabs(ws.N.g[c]));
         if (gmax <= 0.0) { term = 3; break; }
       }
       ++it;
@@ -535,7 +543,7 @@ void launch_lm_refine(const LMParams &p, cudaStream_t s) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)std::min<int64_t>((p.T + warps - 1) / warps, (int64_t)sms * 4);
-  static const int mb = [] { const char *e = getenv("LIMAP_B200_LM_OCC"); return e ? atoi(e) : 2; }();
+  static const int mb = [] { const char *e = getenv("LIMAP_B200_LM_OCC"); return e ? atoi(e) : 3; }();
   if (mb >= 4) lm_refine_kernel<4><<<grid, warps * 32, 0, s>>>(p);
   else if (mb == 3) lm_refine_kernel<3><<<grid, warps * 32, 0, s>>>(p);
   else lm_refine_kernel<2><<<grid, warps * 32, 0, s>>>(p);
