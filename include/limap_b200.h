@@ -112,6 +112,12 @@ int lm_tri_set_shard(lm_ctx *ctx, int32_t view_begin, int32_t view_end);
  * soon as the match chunks of its images have arrived on the copy stream, so they can run under the upload of
  * the later groups. Results do not depend on n (nodes are independent). */
 int lm_tri_set_pipeline_groups(lm_ctx *ctx, int32_t n_groups);
+/* Result sink of the next runs (NULL: none): lm_tri_run copies the node records of every pipeline group into
+ * host_nodes[view-order node index] (layout of lm_tri_get_nodes, 96 bytes per 2D line of the scene) as soon as the
+ * group's kernel has finished, on a stream of its own, under the kernels of the later groups; all records of the
+ * run's shard are there when lm_tri_run returns. Pass page-locked memory (pageable memory makes the copies
+ * synchronous). Replaces a lm_tri_get_nodes call after the run for single-GPU callers. */
+int lm_tri_set_node_sink(lm_ctx *ctx, void *host_nodes);
 
 /* Candidate generation + scoring + selection for every enqueued image:
  * triangulateOneNode (base_line_triangulator.cc:161-337) + scoreOneNode

@@ -78,6 +78,7 @@ _SIGS = {
     "lm_tri_clear": (C.c_int, [_P]),
     "lm_tri_set_shard": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "lm_tri_set_pipeline_groups": (C.c_int, [_P, C.c_int32]),
+    "lm_tri_set_node_sink": (C.c_int, [_P, _P]),
     "lm_tri_run": (C.c_int, [_P]),
     "lm_tri_get_stats": (C.c_int, [_P, C.POINTER(TriStats)]),
     "lm_tri_get_best": (C.c_int, [_P, C.c_int32, _P, _P, _P]),

@@ -11,15 +11,14 @@
 // There is no CPU fallback: without a CUDA device lm_ctx_create fails with LM_ERR_NOGPU.
 #include "../../include/limap_b200.h"
 #include "tri_kernels.cuh"
+#include "graph_kernels.cuh"
 #include "lm_kernels.cuh"
 #include "vp_kernels.cuh"
 #include "merge_kernels.cuh"
 #include "sfm_kernels.cuh"
 #include <cub/device/device_run_length_encode.cuh>
 #include <algorithm>
-#ifdef LM_TRACE
 #include <chrono>
-#endif
 #include <array>
 #include <cmath>
 #include <cstdio>
@@ -124,6 +123,11 @@ struct lm_ctx {
   // match uploads run on their own stream so that a run can start on the first source images while the rest
   // of the tables is still crossing PCIe
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t prep_stream = nullptr; // row expansion + sort of pipeline group g+1 run under the node kernel of group g
+  std::vector<cudaEvent_t> evp;       // per pipeline group: rows of the group sorted, node offsets known
+  cudaEvent_t ev_run_begin = nullptr;
+  cudaStream_t out_stream = nullptr;  // device -> host copies of finished groups (lm_tri_set_node_sink)
+  char *node_sink = nullptr;
   struct CopyChunk { int64_t row_end; cudaEvent_t ev; };
   std::vector<CopyChunk> chunks;
   std::vector<cudaEvent_t> event_pool;
@@ -137,7 +141,6 @@ struct lm_ctx {
   // bulk match upload issued in between (measured in round 1: ~3 ms per hypersim100 step).
   cudaEvent_t ev_scene = nullptr;
   std::vector<lm::ViewD> h_views;    // staging of the scene tables (kept alive: the copies are asynchronous)
-  std::vector<uint16_t> h_node_view;
   std::vector<cudaEvent_t> evk;      // per pipeline group: node-kernel begin/end (read after the run's only sync)
   DevBuf d_gather;                   // [0] total edges, [1] overflow flag of the last unpack; +64: rank node table
   int64_t gather_tab[64] = {0};
@@ -154,10 +157,8 @@ struct lm_ctx {
   std::vector<int> img_ids;
   std::unordered_map<int, int> id2view;
   std::vector<int64_t> line_off;
-  std::vector<double> h_segs; // after add_halfpix
-  std::vector<double> h_segs_raw;
   int64_t n_nodes = 0;
-  DevBuf d_views, d_segs, d_node_view, d_line_off, d_img_ids, d_host_edges;
+  DevBuf d_views, d_segs, d_segs_raw, d_node_view, d_line_off, d_img_ids, d_host_edges;
   // config
   bool have_cfg = false;
   lm_tri_config cfg;
@@ -184,6 +185,7 @@ struct lm_ctx {
   DevBuf d_node_row_off, d_scalars; // scalars: [0] max_rows(uint) [1] err(int) ; counters at +16
   DevBuf d_nodes, d_row_state, d_row_cand, d_slab;
   DevBuf d_edges, d_edges2, d_edge_keys, d_edge_keys2, d_edge_w, d_edge_cnt;
+  DevBuf d_g_flag, d_g_pos, d_g_kc, d_g_wc, d_g_occ, d_g_occ2, d_g_hk, d_g_hk2, d_g_gidx, d_g_gnode, d_g_k1, d_g_k1b, d_g_k2, d_g_k2b;
   DevBuf d_nvalid, d_edge_off, d_edge_ng; // compact valid_edges_ of the shard (node-major, candidate order)
   uint32_t *sorted_val = nullptr;
   uint32_t *sorted_key = nullptr;
@@ -301,6 +303,13 @@ int lm_ctx_create(int device, lm_ctx **out) {
   CU(cudaEventCreate(&c->evk0));
   CU(cudaEventCreate(&c->evk1));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  {
+    int lo_p = 0, hi_p = 0; // (numerically lowest = greatest priority: the small preparation kernels take the next free SM slots)
+    CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+    CU(cudaStreamCreateWithPriority(&c->prep_stream, cudaStreamNonBlocking, hi_p));
+    CU(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_run_begin, cudaEventDisableTiming));
+  }
   CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_pin), 2048, cudaHostAllocDefault));
   CU(cudaEventCreateWithFlags(&c->ev_scene, cudaEventDisableTiming));
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -317,11 +326,11 @@ void lm_ctx_destroy(lm_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf *bufs[] = {&c->d_img_ids, &c->d_host_edges, &c->d_views, &c->d_segs, &c->d_node_view, &c->d_line_off, &c->d_pairs, &c->d_blk_row_off,
+  DevBuf *bufs[] = {&c->d_segs_raw, &c->d_img_ids, &c->d_host_edges, &c->d_views, &c->d_segs, &c->d_node_view, &c->d_line_off, &c->d_pairs, &c->d_blk_row_off,
                     &c->d_blk_src, &c->d_blk_ng, &c->d_blk_pair_off, &c->d_key, &c->d_key2, &c->d_val, &c->d_val2,
                     &c->d_sort_tmp, &c->d_node_row_off, &c->d_scalars, &c->d_nodes, &c->d_row_state, &c->d_row_cand,
                     &c->d_slab, &c->d_edges, &c->d_edges2, &c->d_edge_keys, &c->d_edge_keys2, &c->d_edge_w,
-                    &c->d_edge_cnt, &c->d_nvalid, &c->d_edge_off, &c->d_edge_ng, &c->d_ba_in, &c->d_ba_blocks, &c->d_ba_out, &c->d_raw_blocks, &c->d_bkey, &c->d_bkey2, &c->d_bval, &c->d_bval2, &c->d_blk_rows, &c->d_vp_label, &c->d_vp_voff, &c->d_vp_vps, &c->d_vp_pts, &c->d_vp_off, &c->d_vp_labels, &c->d_vp_nc, &c->d_vp_ps, &c->d_vp_mat, &c->d_mg_in, &c->d_mg_out, &c->d_mg_edges, &c->d_gather, &c->d_vp_idx, &c->d_sfm_in, &c->d_sfm_keys, &c->d_sfm_keys2, &c->d_sfm_a, &c->d_sfm_b, &c->d_sfm_c, &c->d_sfm_d};
+                    &c->d_edge_cnt, &c->d_nvalid, &c->d_edge_off, &c->d_edge_ng, &c->d_ba_in, &c->d_ba_blocks, &c->d_ba_out, &c->d_raw_blocks, &c->d_bkey, &c->d_bkey2, &c->d_bval, &c->d_bval2, &c->d_blk_rows, &c->d_vp_label, &c->d_vp_voff, &c->d_vp_vps, &c->d_vp_pts, &c->d_vp_off, &c->d_vp_labels, &c->d_vp_nc, &c->d_vp_ps, &c->d_vp_mat, &c->d_mg_in, &c->d_mg_out, &c->d_mg_edges, &c->d_gather, &c->d_vp_idx, &c->d_sfm_in, &c->d_sfm_keys, &c->d_sfm_keys2, &c->d_sfm_a, &c->d_sfm_b, &c->d_sfm_c, &c->d_sfm_d, &c->d_g_flag, &c->d_g_pos, &c->d_g_kc, &c->d_g_wc, &c->d_g_occ, &c->d_g_occ2, &c->d_g_hk, &c->d_g_hk2, &c->d_g_gidx, &c->d_g_gnode, &c->d_g_k1, &c->d_g_k1b, &c->d_g_k2, &c->d_g_k2b};
   for (DevBuf *b : bufs) b->release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -333,6 +342,10 @@ void lm_ctx_destroy(lm_ctx *c) {
   for (auto &ch : c->chunks) cudaEventDestroy(ch.ev);
   for (auto e : c->event_pool) cudaEventDestroy(e);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->prep_stream) { cudaStreamSynchronize(c->prep_stream); cudaStreamDestroy(c->prep_stream); }
+  if (c->out_stream) { cudaStreamSynchronize(c->out_stream); cudaStreamDestroy(c->out_stream); }
+  for (auto e : c->evp) cudaEventDestroy(e);
+  if (c->ev_run_begin) cudaEventDestroy(c->ev_run_begin);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->h_ba_pin) cudaFreeHost(c->h_ba_pin);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -376,17 +389,15 @@ static void make_view(int model_id, const double *kv, const double *qv, const do
   d.pad = 0;
 }
 
-static int upload_segs(lm_ctx *c) {
-  // add_halfpix (base_line_triangulator.cc:32-43) is applied when both scene and config are known.
-  CU(cudaStreamSynchronize(c->copy_stream)); // no copy from h_segs may still be in flight
-  c->h_segs = c->h_segs_raw;
-  if (c->have_cfg && c->cfg.add_halfpix)
-    for (double &v : c->h_segs) v += 0.5;
-  if (std::max<size_t>(32, c->h_segs.size() * 8) > c->d_segs.cap) CU(cudaStreamSynchronize(c->stream)); // readers of the old buffer
-  CU(cudaStreamSynchronize(c->copy_stream)); // h_segs is rewritten below: no copy from it may be in flight
-  CU(c->d_segs.ensure(std::max<size_t>(32, c->h_segs.size() * 8)));
-  if (!c->h_segs.empty())
-    CU(cudaMemcpyAsync(c->d_segs.p, c->h_segs.data(), c->h_segs.size() * 8, cudaMemcpyHostToDevice, c->copy_stream));
+static int tri_clear_impl(lm_ctx *c, bool sync_copies);
+static int upload_segs(lm_ctx *c, bool with_node_view) {
+  // add_halfpix (base_line_triangulator.cc:32-43) is applied when both scene and config are known: on the device, from
+  // the raw copy of the caller's segments, in stream order behind that copy.
+  if (c->n_nodes)
+    lm::launch_scene_prepare(c->d_segs_raw.as<double>(), c->n_nodes, (c->have_cfg && c->cfg.add_halfpix) ? 0.5 : 0.0,
+                             c->d_line_off.as<int64_t>(), c->V, c->d_segs.as<double>(),
+                             with_node_view ? c->d_node_view.as<uint16_t>() : nullptr, c->copy_stream);
+  CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev_scene, c->copy_stream));
   return LM_OK;
 }
@@ -408,34 +419,34 @@ int lm_scene_upload(lm_ctx *c, int32_t n_views, const int32_t *img_ids, const in
   c->n_nodes = line_off[n_views];
   if (c->n_nodes >= ((int64_t)1 << 31) - 64) return fail(LM_ERR_INVALID, "more than 2^31 2D lines in one scene");
   std::vector<lm::ViewD> &views = c->h_views;
-  std::vector<uint16_t> &node_view = c->h_node_view;
   views.resize(n_views);
-  node_view.resize(c->n_nodes);
   for (int v = 0; v < n_views; ++v) {
     if (model_ids[v] != 0 && model_ids[v] != 1)
       return fail(LM_ERR_INVALID, "only SIMPLE_PINHOLE / PINHOLE are legal on this path (IsUndistorted check)");
     if (line_off[v + 1] - line_off[v] > 65535) return fail(LM_ERR_INVALID, "more than 65535 lines in one image");
     make_view(model_ids[v], kvec + 4 * v, qvec + 4 * v, tvec + 3 * v, views[v]);
-    for (int64_t l = line_off[v]; l < line_off[v + 1]; ++l) node_view[l] = (uint16_t)v;
   }
-  c->h_segs_raw.assign(segs, segs + 4 * c->n_nodes);
   CU(c->d_views.ensure(sizeof(lm::ViewD) * n_views));
   CU(c->d_node_view.ensure(std::max<size_t>(2, 2 * c->n_nodes)));
   CU(c->d_line_off.ensure(8 * (n_views + 1)));
+  CU(c->d_segs_raw.ensure(std::max<size_t>(32, 32 * (size_t)c->n_nodes)));
+  CU(c->d_segs.ensure(std::max<size_t>(32, 32 * (size_t)c->n_nodes)));
   CU(cudaMemcpyAsync(c->d_views.p, views.data(), sizeof(lm::ViewD) * n_views, cudaMemcpyHostToDevice, c->copy_stream));
-  if (c->n_nodes)
-    CU(cudaMemcpyAsync(c->d_node_view.p, node_view.data(), 2 * c->n_nodes, cudaMemcpyHostToDevice, c->copy_stream));
   CU(cudaMemcpyAsync(c->d_line_off.p, c->line_off.data(), 8 * (n_views + 1), cudaMemcpyHostToDevice, c->copy_stream));
   CU(c->d_img_ids.ensure(4 * n_views));
   CU(cudaMemcpyAsync(c->d_img_ids.p, c->img_ids.data(), 4 * n_views, cudaMemcpyHostToDevice, c->copy_stream));
+  // the 2D segments go up straight from the caller's buffer (a pinned buffer is not staged: it must stay unchanged until
+  // the next call that synchronises, e.g. lm_tri_run; pageable memory is staged by the driver before this returns)
+  if (c->n_nodes)
+    CU(cudaMemcpyAsync(c->d_segs_raw.p, segs, 32 * (size_t)c->n_nodes, cudaMemcpyHostToDevice, c->copy_stream));
   c->have_scene = true;
   c->outside_shard_clean = false;
-  int rc = upload_segs(c);
+  int rc = upload_segs(c, true);
   if (rc) return rc;
   c->image_added.assign(n_views, 0);
   c->image_norder.assign(n_views, 0);
   c->stats.n_nodes = c->n_nodes;
-  return lm_tri_clear(c);
+  return tri_clear_impl(c, false); // (both streams were drained on entry: no match chunk is in flight)
 }
 
 int lm_tri_configure(lm_ctx *c, const lm_tri_config *cfg) {
@@ -446,7 +457,7 @@ int lm_tri_configure(lm_ctx *c, const lm_tri_config *cfg) {
   c->cfg = *cfg;
   c->have_cfg = true;
   c->ran = false;
-  if (c->have_scene && halfpix_changed) return upload_segs(c);
+  if (c->have_scene && halfpix_changed) return upload_segs(c, false);
   return LM_OK;
 }
 int lm_tri_set_ranges(lm_ctx *c, const double lo[3], const double hi[3]) {
@@ -506,11 +517,14 @@ int lm_tri_set_vps(lm_ctx *c, int32_t n_images, const int32_t *img_ids, const in
 
 int lm_tri_clear(lm_ctx *c) {
   if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  return tri_clear_impl(c, true);
+}
+static int tri_clear_impl(lm_ctx *c, bool sync_copies) {
   c->blocks.clear();
   c->raw_uploaded = 0;
   std::fill(c->image_added.begin(), c->image_added.end(), 0);
   std::fill(c->image_norder.begin(), c->image_norder.end(), 0);
-  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->copy_stream && sync_copies) cudaStreamSynchronize(c->copy_stream); // (the chunk events go back to the pool)
   for (auto &ch : c->chunks) c->event_pool.push_back(ch.ev);
   c->chunks.clear();
   c->pairs_rows = 0;
@@ -520,6 +534,11 @@ int lm_tri_clear(lm_ctx *c) {
   c->edges_collected = false;
   c->tracks.clear();
   c->graph_nodes.clear();
+  return LM_OK;
+}
+int lm_tri_set_node_sink(lm_ctx *c, void *host_nodes) {
+  if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
+  c->node_sink = static_cast<char *>(host_nodes);
   return LM_OK;
 }
 int lm_tri_set_pipeline_groups(lm_ctx *c, int32_t n) {
@@ -578,10 +597,12 @@ static int upload_pairs(lm_ctx *c, const int32_t *pairs, int64_t total, bool on_
     c->d_pairs.release();
     c->d_pairs = nbuf;
   }
-  const int64_t kChunk = 2 << 20, kEventEvery = 1; // 16 MB copies, one event each
-  int64_t k = 0;
-  for (int64_t o = 0; o < total; o += kChunk, ++k) {
-    const int64_t n = std::min(kChunk, total - o);
+  // one event per copy; the copies start at 2 MB and double up to 16 MB, so that the first pipeline group of a run (a few
+  // per cent of the rows) does not wait for a full-size chunk
+  const int64_t kChunk = 2 << 20, kEventEvery = 1;
+  int64_t k = 0, step = 256 << 10;
+  for (int64_t o = 0, n = 0; o < total; o += n, ++k, step = std::min(kChunk, step * 2)) {
+    n = std::min(step, total - o);
     CU(cudaMemcpyAsync(c->d_pairs.as<char>() + (c->pairs_rows + o) * 8, pairs + 2 * o, n * 8,
                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->copy_stream));
     if ((k + 1) % kEventEvery == 0 || o + n >= total) {
@@ -797,9 +818,16 @@ int lm_tri_run(lm_ctx *c) {
   cudaEventSynchronize(c->ev0);
   fprintf(stderr, "[lm trace] ev0 executed %.3f ms after run entry\n", lm_ms());
 #endif
+  // Two compute streams: `sp` prepares the rows of a pipeline group (expansion, sort, node offsets), `s` runs the node
+  // kernels. The preparation of group g+1 is queued right behind that of group g, so it executes under the node kernel of
+  // group g; everything `sp` touches is per-group slices, its own scratch, or is read by `s` only after the group's event.
+  cudaStream_t sp = c->prep_stream;
+  CU(cudaEventRecord(c->ev_run_begin, s)); // whatever the caller queued on the engine's stream comes first
+  CU(cudaStreamWaitEvent(sp, c->ev_run_begin, 0));
   // scene tables / VP tables travel on the copy stream (see lm_ctx::ev_scene)
+  CU(cudaStreamWaitEvent(sp, c->ev_scene, 0));
   CU(cudaStreamWaitEvent(s, c->ev_scene, 0));
-  lm::launch_zero_words(c->d_scalars.p, 128, s);
+  lm::launch_zero_words(c->d_scalars.p, 128, sp);
   // block tables, derived on the device from the descriptors uploaded with the matches (no transfer now)
   {
     const int n_all = (int)c->blocks.size();
@@ -808,25 +836,25 @@ int lm_tri_run(lm_ctx *c) {
       CU(c->d_bkey.ensure(4 * n_all)); CU(c->d_bkey2.ensure(4 * n_all));
       CU(c->d_bval.ensure(4 * n_all)); CU(c->d_bval2.ensure(4 * n_all));
       // the descriptors travel on the copy stream ahead of their matches (bulk add: ahead of all matches)
-      if (c->ev_raw) CU(cudaStreamWaitEvent(s, c->ev_raw, 0));
+      if (c->ev_raw) CU(cudaStreamWaitEvent(sp, c->ev_raw, 0));
       lm::launch_block_keys(c->d_raw_blocks.as<lm::RawBlock>(), n_all, vb, ve, exhaustive ? 1 : 0, c->d_bkey.as<uint32_t>(),
-                            c->d_bval.as<uint32_t>(), s);
+                            c->d_bval.as<uint32_t>(), sp);
       cub::DoubleBuffer<uint32_t> bk(c->d_bkey.as<uint32_t>(), c->d_bkey2.as<uint32_t>());
       cub::DoubleBuffer<uint32_t> bv(c->d_bval.as<uint32_t>(), c->d_bval2.as<uint32_t>());
       size_t tmpb = 0;
-      CU(cub::DeviceRadixSort::SortPairs(nullptr, tmpb, bk, bv, n_all, 0, 32, s));
+      CU(cub::DeviceRadixSort::SortPairs(nullptr, tmpb, bk, bv, n_all, 0, 32, sp));
       CU(c->d_sort_tmp.ensure(tmpb));
-      CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, tmpb, bk, bv, n_all, 0, 32, s));
+      CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, tmpb, bk, bv, n_all, 0, 32, sp));
       lm::launch_block_gather(c->d_raw_blocks.as<lm::RawBlock>(), bv.Current(), nb, c->d_blk_src.as<int32_t>(),
-                              c->d_blk_ng.as<int32_t>(), c->d_blk_pair_off.as<int64_t>(), c->d_blk_rows.as<int64_t>(), s);
+                              c->d_blk_ng.as<int32_t>(), c->d_blk_pair_off.as<int64_t>(), c->d_blk_rows.as<int64_t>(), sp);
     } else {
-      lm::launch_zero_words(c->d_blk_rows.p, 4, s);
+      lm::launch_zero_words(c->d_blk_rows.p, 4, sp);
     }
     size_t tmps = 0;
-    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmps, c->d_blk_rows.as<int64_t>(), c->d_blk_row_off.as<int64_t>(), nb + 1, s));
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmps, c->d_blk_rows.as<int64_t>(), c->d_blk_row_off.as<int64_t>(), nb + 1, sp));
     CU(c->d_sort_tmp.ensure(tmps));
     CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmps, c->d_blk_rows.as<int64_t>(), c->d_blk_row_off.as<int64_t>(),
-                                     nb + 1, s));
+                                     nb + 1, sp));
   }
   // d_scalars words: [1] index error, [2] staging overflow, bytes 16..47 counters, words [16 + g] largest node of group g
   int *d_err = c->d_scalars.as<int>() + 1;
@@ -931,13 +959,18 @@ int lm_tri_run(lm_ctx *c) {
     CU(cudaEventCreate(&e));
     c->evk.push_back(e);
   }
+  while ((int)c->evp.size() < n_groups) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->evp.push_back(e);
+  }
   std::vector<int> group_has_kernel(n_groups, 0);
   for (int g = 0; g < n_groups; ++g) {
     // blocks [bg0, bg1) with whole source images, views [gv0, gv1)
     int bg1 = nb, gv1 = ve;
     if (g + 1 < n_groups) {
       // the first group is the smallest: it is the only one whose matches nothing else can hide
-      const int64_t target = (int64_t)((double)n_rows * std::pow((g + 1.0) / n_groups, 1.6));
+      const int64_t target = (int64_t)((double)n_rows * std::pow((g + 1.0) / n_groups, 2.0));
       bg1 = bg0;
       while (bg1 < nb && row_off[bg1] < target) ++bg1;
       while (bg1 < nb && bg1 > 0 && blk[bg1].src_view == blk[bg1 - 1].src_view) ++bg1; // finish the image
@@ -949,36 +982,38 @@ int lm_tri_run(lm_ctx *c) {
       int64_t need = 0;
       for (int b2 = bg0; b2 < bg1; ++b2) need = std::max(need, pair_off[b2] + blk[b2].n_rows);
       for (const auto &ch : c->chunks) // chunks complete in order: wait for the first one that covers `need`
-        if (ch.row_end >= need) { CU(cudaStreamWaitEvent(s, ch.ev, 0)); break; }
+        if (ch.row_end >= need) { CU(cudaStreamWaitEvent(sp, ch.ev, 0)); break; }
     }
     unsigned int *d_max_rows = c->d_scalars.as<unsigned int>() + 16 + g;
     if (re > rb) {
       if (exhaustive)
         lm::launch_expand_exhaustive(c->d_blk_row_off.as<int64_t>(), c->d_blk_src.as<int32_t>(), c->d_blk_ng.as<int32_t>(),
                                      nb, c->d_line_off.as<int64_t>(), n_rows, c->d_key.as<uint32_t>(),
-                                     c->d_val.as<uint32_t>(), s);
+                                     c->d_val.as<uint32_t>(), sp);
       else
         lm::launch_expand_rows(c->d_pairs.as<int32_t>(), c->d_blk_row_off.as<int64_t>(), c->d_blk_src.as<int32_t>(),
                                c->d_blk_ng.as<int32_t>(), c->d_blk_pair_off.as<int64_t>(), nb,
                                c->d_line_off.as<int64_t>(), rb, re, c->d_key.as<uint32_t>(), c->d_val.as<uint32_t>(),
-                               d_err, s);
+                               d_err, sp);
       ++launches;
       // stable LSD radix sort by node id keeps (neighbour, row) order inside every node
       cub::DoubleBuffer<uint32_t> dk(c->d_key.as<uint32_t>() + rb, c->d_key2.as<uint32_t>() + rb);
       cub::DoubleBuffer<uint32_t> dv(c->d_val.as<uint32_t>() + rb, c->d_val2.as<uint32_t>() + rb);
       size_t tmp = 0;
-      CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)(re - rb), 0, nbits, s));
+      CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)(re - rb), 0, nbits, sp));
       CU(c->d_sort_tmp.ensure(tmp));
-      CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, tmp, dk, dv, (int)(re - rb), 0, nbits, s));
+      CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, tmp, dk, dv, (int)(re - rb), 0, nbits, sp));
       launches += (nbits + 7) / 8 + 1;
       if (dk.Current() != c->d_key2.as<uint32_t>() + rb) {
-        CU(cudaMemcpyAsync(c->d_key2.as<uint32_t>() + rb, dk.Current(), 4 * (re - rb), cudaMemcpyDeviceToDevice, s));
-        CU(cudaMemcpyAsync(c->d_val2.as<uint32_t>() + rb, dv.Current(), 4 * (re - rb), cudaMemcpyDeviceToDevice, s));
+        CU(cudaMemcpyAsync(c->d_key2.as<uint32_t>() + rb, dk.Current(), 4 * (re - rb), cudaMemcpyDeviceToDevice, sp));
+        CU(cudaMemcpyAsync(c->d_val2.as<uint32_t>() + rb, dv.Current(), 4 * (re - rb), cudaMemcpyDeviceToDevice, sp));
       }
     }
     lm::launch_node_offsets(c->sorted_key + rb, re - rb, rb, node_lo, node_hi, c->d_node_row_off.as<uint32_t>(),
-                            d_max_rows, s);
+                            d_max_rows, sp);
     ++launches;
+    CU(cudaEventRecord(c->evp[g], sp));
+    CU(cudaStreamWaitEvent(s, c->evp[g], 0));
     p.node_begin = node_lo;
     p.node_end = node_hi;
     const int64_t n_group_nodes = node_hi - node_lo;
@@ -1004,6 +1039,11 @@ int lm_tri_run(lm_ctx *c) {
       CU(cudaEventRecord(c->evk[2 * g + 1], s));
       group_has_kernel[g] = 1;
       ++launches;
+      if (c->node_sink) { // the group's records go to the caller's buffer under the kernels of the later groups
+        CU(cudaStreamWaitEvent(c->out_stream, c->evk[2 * g + 1], 0));
+        CU(cudaMemcpyAsync(c->node_sink + sizeof(lm::NodeRecord) * node_lo, c->d_nodes.as<lm::NodeRecord>() + node_lo,
+                           sizeof(lm::NodeRecord) * n_group_nodes, cudaMemcpyDeviceToHost, c->out_stream));
+      }
     }
     bg0 = bg1;
     gv0 = gv1;
@@ -1036,6 +1076,7 @@ int lm_tri_run(lm_ctx *c) {
   fprintf(stderr, "[lm trace] compute stream drained %.3f ms after run entry\n", lm_ms());
 #endif
   CU(cudaStreamSynchronize(c->copy_stream)); // uploads of images outside this shard may still be in flight
+  if (c->node_sink) CU(cudaStreamSynchronize(c->out_stream));
 #ifdef LM_TRACE
   fprintf(stderr, "[lm trace] copy stream drained %.3f ms after run entry\n", lm_ms());
 #endif
@@ -1372,6 +1413,135 @@ size_t uf_root(size_t i, std::vector<int> &parent) { // base/graph.cc:157-166
 
 } // namespace
 
+// The track graph on the device (graph_kernels.cu): from the directed valid connections in c->d_edges to the graph nodes
+// in FindOrCreateNode order and the edges in the order ComputeLineTrackLabelsGreedy visits them, each edge as
+// (idx0 << 32 | idx1). Two small read-backs; the union-find that follows is sequential by definition.
+static int graph_on_device(lm_ctx *c, int64_t ne, std::vector<int64_t> &gnode, std::vector<uint64_t> &order) {
+  cudaStream_t s = c->stream;
+  gnode.clear();
+  order.clear();
+  if (ne <= 0) return LM_OK;
+  if (ne >= (int64_t)1 << 30) return fail(LM_ERR_INVALID, "too many valid connections for the 32-bit positions of the graph build");
+  auto sort_keys = [&](DevBuf &a, DevBuf &b, int64_t n, uint64_t *&out) -> int {
+    cub::DoubleBuffer<uint64_t> dk(a.as<uint64_t>(), b.as<uint64_t>());
+    size_t tmp = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, dk, (int)n, 0, 64, s));
+    CU(c->d_sort_tmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortKeys(c->d_sort_tmp.p, tmp, dk, (int)n, 0, 64, s));
+    out = dk.Current();
+    return LM_OK;
+  };
+  auto scan_u32 = [&](const uint32_t *in, uint32_t *out, int64_t n) -> int {
+    size_t tmp = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, (int)n, s));
+    CU(c->d_sort_tmp.ensure(tmp));
+    CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp, in, out, (int)n, s));
+    return LM_OK;
+  };
+  int rc;
+  // undirected edge set in std::set order (:243-261)
+  CU(c->d_edge_keys.ensure(8 * ne));
+  CU(c->d_edge_keys2.ensure(8 * ne + 8));
+  lm::launch_undirected_keys(c->d_edges.as<int64_t>(), ne, c->d_edge_keys.as<uint64_t>(), s);
+  uint64_t *sorted = nullptr;
+  if ((rc = sort_keys(c->d_edge_keys, c->d_edge_keys2, ne, sorted))) return rc;
+  uint64_t *ukeys = (sorted == c->d_edge_keys.as<uint64_t>()) ? c->d_edge_keys2.as<uint64_t>() : c->d_edge_keys.as<uint64_t>();
+  CU(c->d_edge_cnt.ensure(16));
+  {
+    size_t tmp = 0;
+    CU(cub::DeviceSelect::Unique(nullptr, tmp, sorted, ukeys, c->d_edge_cnt.as<int64_t>(), (int)ne, s));
+    CU(c->d_sort_tmp.ensure(tmp));
+    CU(cub::DeviceSelect::Unique(c->d_sort_tmp.p, tmp, sorted, ukeys, c->d_edge_cnt.as<int64_t>(), (int)ne, s));
+  }
+  int64_t nu = 0;
+  CU(cudaMemcpyAsync(&nu, c->d_edge_cnt.p, 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  // 3d score of every undirected edge (:263-288)
+  CU(c->d_edges2.ensure(16 * nu));
+  CU(c->d_edge_w.ensure(8 * nu));
+  lm::launch_keys_to_pairs(ukeys, nu, c->d_edges2.as<int64_t>(), s);
+  lm::EdgeParams ep;
+  ep.nodes = c->d_nodes.as<lm::NodeRecord>();
+  ep.edges = c->d_edges2.as<int64_t>();
+  ep.weight = c->d_edge_w.as<double>();
+  ep.n = nu;
+  {
+    lm_linker_config l3 = c->cfg.linker3d; // set_to_spatial_merging (line_linker.h:123-129)
+    l3.use_angle = 1; l3.use_overlap = 1; l3.use_perp = 0; l3.use_innerseg = 1; l3.use_scaleinv = 0;
+    ep.l3d = to_dev<double>(l3);
+  }
+  lm::launch_edge_weights(ep, s);
+  // zero-score edges dropped, order kept (:284-285)
+  CU(c->d_g_flag.ensure(4 * (2 * nu + 2)));
+  CU(c->d_g_pos.ensure(4 * (2 * nu + 2)));
+  CU(c->d_g_kc.ensure(8 * nu + 8));
+  CU(c->d_g_wc.ensure(8 * nu + 8));
+  uint32_t *flag = c->d_g_flag.as<uint32_t>(), *pos = c->d_g_pos.as<uint32_t>();
+  lm::launch_nonzero_flags(c->d_edge_w.as<double>(), nu, flag, s);
+  CU(cudaMemsetAsync(flag + nu, 0, 4, s)); // the scan of n + 1 flags ends with the total
+  if ((rc = scan_u32(flag, pos, nu + 1))) return rc;
+  lm::launch_compact_weighted_edges(ukeys, c->d_edge_w.as<double>(), flag, pos, nu, c->d_g_kc.as<uint64_t>(),
+                                    c->d_g_wc.as<double>(), s);
+  uint32_t n2u = 0;
+  CU(cudaMemcpyAsync(&n2u, pos + nu, 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  const int64_t n2 = n2u;
+  c->stats.n_kernel_launches += 12;
+  if (n2 == 0) return LM_OK;
+  // Graph::FindOrCreateNode numbering: rank of a node's first appearance in u0 v0 u1 v1 ...
+  const int64_t m = 2 * n2;
+  CU(c->d_g_occ.ensure(8 * m));
+  CU(c->d_g_occ2.ensure(8 * m));
+  lm::launch_occurrence_keys(c->d_g_kc.as<uint64_t>(), n2, c->d_g_occ.as<uint64_t>(), s);
+  uint64_t *occ = nullptr;
+  if ((rc = sort_keys(c->d_g_occ, c->d_g_occ2, m, occ))) return rc;
+  lm::launch_occurrence_heads(occ, m, flag, s);
+  CU(cudaMemsetAsync(flag + m, 0, 4, s));
+  if ((rc = scan_u32(flag, pos, m + 1))) return rc;
+  uint32_t ngu = 0;
+  CU(cudaMemcpyAsync(&ngu, pos + m, 4, cudaMemcpyDeviceToHost, s));
+  CU(c->d_g_hk.ensure(8 * m));
+  CU(c->d_g_hk2.ensure(8 * m));
+  lm::launch_head_keys(occ, flag, pos, m, c->d_g_hk.as<uint64_t>(), s);
+  CU(cudaStreamSynchronize(s));
+  const int64_t ng = ngu;
+  uint64_t *hk = nullptr;
+  if ((rc = sort_keys(c->d_g_hk, c->d_g_hk2, ng, hk))) return rc;
+  CU(c->d_g_gidx.ensure(4 * (size_t)std::max<int64_t>(c->n_nodes, 1)));
+  CU(c->d_g_gnode.ensure(4 * ng));
+  lm::launch_graph_index(hk, ng, c->d_g_gidx.as<int32_t>(), c->d_g_gnode.as<int32_t>(), s);
+  // edges in descending (score, idx0, idx1) order: stable LSD, nodes first, score second
+  CU(c->d_g_k1.ensure(8 * n2)); CU(c->d_g_k1b.ensure(8 * n2));
+  CU(c->d_g_k2.ensure(8 * n2)); CU(c->d_g_k2b.ensure(8 * n2));
+  lm::launch_edge_order_keys(c->d_g_kc.as<uint64_t>(), c->d_g_wc.as<double>(), c->d_g_gidx.as<int32_t>(), n2,
+                             c->d_g_k1.as<uint64_t>(), c->d_g_k2.as<uint64_t>(), s);
+  const uint64_t *final_nodes = nullptr;
+  {
+    cub::DoubleBuffer<uint64_t> k(c->d_g_k1.as<uint64_t>(), c->d_g_k1b.as<uint64_t>());
+    cub::DoubleBuffer<uint64_t> v(c->d_g_k2.as<uint64_t>(), c->d_g_k2b.as<uint64_t>());
+    size_t tmp = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k, v, (int)n2, 0, 64, s));
+    CU(c->d_sort_tmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, tmp, k, v, (int)n2, 0, 64, s)); // by (idx0, idx1), scores carried
+    cub::DoubleBuffer<uint64_t> k2(v.Current(), v.Alternate());
+    cub::DoubleBuffer<uint64_t> v2(k.Current(), k.Alternate());
+    size_t tmp2 = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, k2, v2, (int)n2, 0, 64, s));
+    CU(c->d_sort_tmp.ensure(tmp2));
+    CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, tmp2, k2, v2, (int)n2, 0, 64, s)); // by score, stable
+    final_nodes = v2.Current();
+  }
+  std::vector<int32_t> gn32((size_t)ng);
+  order.resize((size_t)n2);
+  CU(cudaMemcpyAsync(gn32.data(), c->d_g_gnode.p, 4 * ng, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(order.data(), final_nodes, 8 * n2, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  c->stats.n_kernel_launches += 16;
+  gnode.assign(gn32.begin(), gn32.end());
+  for (uint64_t &o : order) o = ~o;
+  return LM_OK;
+}
+
 int64_t lm_tri_build_tracks(lm_ctx *c, int64_t *n_support_total) {
   if (!c) return fail(LM_ERR_INVALID, "ctx is NULL");
   int rc = ensure_ran(c);
@@ -1381,10 +1551,19 @@ int64_t lm_tri_build_tracks(lm_ctx *c, int64_t *n_support_total) {
   if ((rc = fetch_nodes(c))) return rc;
   cudaStream_t s = c->stream;
   const int64_t ne = c->n_edges_dev;
+  static const bool trace = getenv("LIMAP_B200_TRACE") != nullptr;
+  const auto tr0 = std::chrono::steady_clock::now();
+  auto tr_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count(); };
   c->tracks.clear();
   c->graph_nodes.clear();
   if (n_support_total) *n_support_total = 0;
   if (ne == 0) return 0;
+  std::vector<int64_t> gnode;
+  std::vector<uint64_t> order; // (idx0 << 32 | idx1) of every graph edge, in the order the greedy labelling visits them
+  if (c->cfg.min_num_outer_edges <= 0) {
+    // (filterNodeByNumOuterEdges keeps every node: the whole graph is built on the device)
+    if ((rc = graph_on_device(c, ne, gnode, order))) return rc;
+  } else {
   std::vector<int64_t> h_edges(2 * ne);
   CU(cudaMemcpyAsync(h_edges.data(), c->d_edges.p, 16 * ne, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -1471,7 +1650,6 @@ int64_t lm_tri_build_tracks(lm_ctx *c, int64_t *n_support_total) {
 
   // Graph::FindOrCreateNode in edge order (base/graph.cc:57-70), zero-score edges dropped first (:284-285)
   std::unordered_map<int64_t, int> node_map;
-  std::vector<int64_t> gnode;
   typedef std::tuple<double, size_t, size_t> edge_tuple;
   std::vector<edge_tuple> edges;
   for (int64_t e = 0; e < nu; ++e) {
@@ -1488,10 +1666,15 @@ int64_t lm_tri_build_tracks(lm_ctx *c, int64_t *n_support_total) {
     }
     edges.push_back(std::make_tuple(w[e], idx[0], idx[1]));
   }
-  const size_t n_gn = gnode.size();
-  // ComputeLineTrackLabelsGreedy (merging/merging.cc:18-103)
+  // ComputeLineTrackLabelsGreedy (merging/merging.cc:18-103): edges by descending (score, node, node)
   std::sort(edges.begin(), edges.end());
   std::reverse(edges.begin(), edges.end());
+  order.reserve(edges.size());
+  for (const edge_tuple &e : edges) order.push_back((uint64_t)std::get<1>(e) << 32 | (uint64_t)std::get<2>(e));
+  } // host graph (min_num_outer_edges > 0)
+  const size_t n_gn = gnode.size();
+  if (trace) fprintf(stderr, "[lm trace] build_tracks: graph (%zu nodes, %zu edges) ready at %.2f ms\n", n_gn, order.size(), tr_ms());
+  if (n_gn == 0) return 0;
   std::vector<int> parent(n_gn, -1);
   std::vector<std::vector<int>> images(n_gn); // sorted distinct image ids of each root's track
   for (size_t i = 0; i < n_gn; ++i) images[i].push_back(0);
@@ -1504,8 +1687,8 @@ int64_t lm_tri_build_tracks(lm_ctx *c, int64_t *n_support_total) {
   }
   // The reference's union_find_get_root compresses recursively (every node on the path points to the
   // root afterwards); uf_root does the same iteratively.
-  for (const edge_tuple &e : edges) {
-    size_t r1 = uf_root(std::get<1>(e), parent), r2 = uf_root(std::get<2>(e), parent);
+  for (const uint64_t e : order) {
+    size_t r1 = uf_root((size_t)(e >> 32), parent), r2 = uf_root((size_t)(e & 0xffffffffull), parent);
     if (r1 == r2) continue;
     size_t dst, srcn;
     if (images[r1].size() < images[r2].size()) { parent[r1] = (int)r2; dst = r2; srcn = r1; }
@@ -1516,6 +1699,7 @@ int64_t lm_tri_build_tracks(lm_ctx *c, int64_t *n_support_total) {
     images[dst].swap(merged);
     std::vector<int>().swap(images[srcn]);
   }
+  if (trace) fprintf(stderr, "[lm trace] build_tracks: union-find done at %.2f ms\n", tr_ms());
   std::vector<int> label(n_gn, -1);
   int n_tracks = 0;
   for (size_t i = 0; i < n_gn; ++i) {
@@ -1547,6 +1731,7 @@ int64_t lm_tri_build_tracks(lm_ctx *c, int64_t *n_support_total) {
   }
   c->graph_nodes.clear();
   if (n_support_total) *n_support_total = support;
+  if (trace) fprintf(stderr, "[lm trace] build_tracks: %d tracks aggregated at %.2f ms\n", n_tracks, tr_ms());
   return n_tracks;
 }
 

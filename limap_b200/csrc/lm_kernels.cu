@@ -278,7 +278,6 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
         double An[10], gn[4], dg[4];
 #pragma unroll
         for (int c = 0; c < 10; ++c) An[c] = ws.N.A[c];
-#pragma unroll
         const double rad_ = radius;
 #pragma unroll
         for (int c = 0; c < 4; ++c) { gn[c] = ws.N.g[c]; dg[c] = ws.diag[c] / rad_; }

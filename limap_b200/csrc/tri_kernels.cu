@@ -1451,6 +1451,28 @@ void launch_edges_for_host(const uint32_t *edge_off, const uint32_t *edge_ng, co
                                                                node_begin, n_nodes_total, node_off, pairs);
 }
 
+// ---- scene preparation: the 2D segments as the kernels read them (add_halfpix, base_line_triangulator.cc:32-43) and the
+// view of every node, derived on the device from what lm_scene_upload copied ------------------------------------------
+__global__ void scene_prepare_kernel(const double *__restrict__ segs_raw, int64_t n_nodes, double add,
+                                     const int64_t *__restrict__ line_off, int n_views, double *__restrict__ segs,
+                                     uint16_t *__restrict__ node_view) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < 4 * n_nodes) segs[i] = segs_raw[i] + add;
+  if (i < n_nodes && node_view) {
+    int lo = 0, hi = n_views; // largest v with line_off[v] <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (line_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    node_view[i] = (uint16_t)lo;
+  }
+}
+void launch_scene_prepare(const double *segs_raw, int64_t n_nodes, double add, const int64_t *line_off, int n_views,
+                          double *segs, uint16_t *node_view, cudaStream_t s) {
+  if (n_nodes <= 0) return;
+  scene_prepare_kernel<<<(int)((4 * n_nodes + 255) / 256), 256, 0, s>>>(segs_raw, n_nodes, add, line_off, n_views, segs, node_view);
+}
+
 // ---- multi-GPU exchange: one fixed-size message per rank ("one all-gather of per-node results") ----
 // message = [int64 n_edges, int64 n_nodes] | NodeRecord[max_nodes] | (uint32 src_node, uint32 dst_node)[cap_edges]
 __global__ void gather_pack_kernel(const NodeRecord *__restrict__ nodes, int64_t node_begin, int64_t n_nodes,

@@ -78,6 +78,8 @@ struct EdgeParams {
 };
 
 size_t tri_smem_bytes(int cap, bool fast);
+void launch_scene_prepare(const double *segs_raw, int64_t n_nodes, double add, const int64_t *line_off, int n_views,
+                          double *segs, uint16_t *node_view, cudaStream_t s);
 cudaError_t launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem, cudaStream_t s);
 void launch_expand_rows(const int32_t *d_pairs, const int64_t *d_blk_row_off, const int32_t *d_blk_src_view,
                         const int32_t *d_blk_ng_view, const int64_t *d_blk_pair_off, int n_blocks,

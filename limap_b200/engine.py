@@ -32,6 +32,7 @@ class TriEngine:
                                     ptr(kvec), ptr(qvec), ptr(tvec), ptr(line_off), ptr(segs)))
         self.img_ids = img_ids
         self.line_off = line_off
+        self._segs_ref = segs  # a pinned buffer is copied asynchronously: keep it alive until the next upload
         self._view = {int(i): v for v, i in enumerate(img_ids)}
 
     def upload(self, scene):
@@ -172,8 +173,19 @@ class TriEngine:
     def set_pipeline_groups(self, n_groups):
         check(lib().lm_tri_set_pipeline_groups(self.ctx.handle, int(n_groups)))
 
-    def run(self):
-        check(lib().lm_tri_run(self.ctx.handle))
+    def run(self, nodes_out=None):
+        """Run the enqueued work. `nodes_out` (a NODE_RECORD_DTYPE array over all 2D lines of the scene, ideally pinned)
+        receives the node records of this run's shard while the run is still going (lm_tri_set_node_sink)."""
+        if nodes_out is not None:
+            if nodes_out.dtype != _cabi.NODE_RECORD_DTYPE or len(nodes_out) != int(self.line_off[-1]) or \
+                    not nodes_out.flags.c_contiguous:
+                raise ValueError("nodes_out must be a contiguous NODE_RECORD_DTYPE array with one record per 2D line")
+            check(lib().lm_tri_set_node_sink(self.ctx.handle, ptr(nodes_out)))
+        try:
+            check(lib().lm_tri_run(self.ctx.handle))
+        finally:
+            if nodes_out is not None:
+                check(lib().lm_tri_set_node_sink(self.ctx.handle, None))
         self.ctx._keep.clear()
         return self.ctx.stats()
 

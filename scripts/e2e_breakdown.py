@@ -18,6 +18,9 @@ bsrc, bng, boff, bpairs = sc.bulk_matches()
 tp = torch.empty(bpairs.shape, dtype=torch.int32, pin_memory=True)
 tp.numpy()[...] = bpairs
 pp = tp.numpy()
+tsegs = torch.empty(sc.segs.shape, dtype=torch.float64, pin_memory=True)
+tsegs.numpy()[...] = sc.segs
+sc.segs = tsegs.numpy()
 eng = TriEngine(dict(DEFAULT_YAML_TRIANGULATION))
 nodes_out = torch.empty(int(sc.line_off[-1]) * NODE_RECORD_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True).numpy().view(NODE_RECORD_DTYPE)
 off_out = torch.empty(int(sc.line_off[-1]) + 1, dtype=torch.int64, pin_memory=True).numpy()
@@ -41,7 +44,7 @@ for k, v in acc.items():
 print("device run ms", st["last_run_ms"], "kernel", st["last_node_kernel_ms"])
 
 # ---- full public-API step (scene up, matches up, run, results down) for several pipeline group counts ----
-for groups in (1, 2, 4, 8):
+for groups in (1, 2, 4, 6, 8, 12):
     eng.set_pipeline_groups(groups)
     tot, dev, ker = [], [], []
     for it in range(7):
@@ -49,8 +52,7 @@ for groups in (1, 2, 4, 8):
         t = time.perf_counter()
         eng.upload(sc); eng.set_ranges(*sc.ranges)
         eng.add_matches_bulk(bsrc, bng, boff, pp)
-        st = eng.run()
-        eng.get_nodes(nodes_out)
+        st = eng.run(nodes_out=nodes_out)
         eng.get_all_valid_edges(off_out, edges_out)
         tot.append((time.perf_counter() - t) * 1e3)
         dev.append(st["last_run_ms"]); ker.append(st["last_node_kernel_ms"])

@@ -186,6 +186,21 @@ def test_bulk_add_and_pipeline_groups_match_per_image_adds():
         assert eng.get_nodes().tobytes() == nodes_ref.tobytes()
         o2, e2 = eng.get_all_valid_edges()
         assert np.array_equal(o2, off_ref) and np.array_equal(e2[: o2[-1]], edges_ref[: off_ref[-1]])
+        # lm_tri_set_node_sink: the records streamed to a (pinned) host buffer during the run are the getter's
+        import torch
+        from limap_b200._cabi import NODE_RECORD_DTYPE
+        sink = torch.empty(len(nodes_ref) * NODE_RECORD_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True).numpy().view(NODE_RECORD_DTYPE)
+        sink.view(np.uint8)[...] = 0xAB
+        eng.run(nodes_out=sink)
+        assert sink.tobytes() == nodes_ref.tobytes()
+        with pytest.raises(ValueError):
+            eng.run(nodes_out=np.zeros(3, NODE_RECORD_DTYPE))
+        # tracks (graph built on the device for min_num_outer_edges = 0; the host-graph path runs in the C++-defaults test)
+        tr = eng.build_tracks()
+        tr_ref = ref.build_tracks()
+        for k in ("track_off", "img_ids", "line_ids", "node_ids"):
+            assert np.array_equal(tr[k], tr_ref[k]), k
+        assert np.array_equal(tr["track_line"], tr_ref["track_line"])
 
 
 def test_full_size_hypersim100_properties():
