@@ -298,7 +298,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lm", action="store_true", help="skip the lm_ba / remerge / jlinkage / sweep500 legs")
-    ap.add_argument("--groups", type=int, default=6, help="pipeline groups of the e2e path (upload/run overlap)")
+    ap.add_argument("--groups", type=int, default=8, help="pipeline groups of the e2e path (upload/run overlap)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     rank = int(os.environ.get("RANK", 0))

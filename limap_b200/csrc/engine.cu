@@ -128,6 +128,7 @@ struct lm_ctx {
   cudaEvent_t ev_run_begin = nullptr;
   cudaStream_t out_stream = nullptr;  // device -> host copies of finished groups (lm_tri_set_node_sink)
   char *node_sink = nullptr;
+  DevBuf d_scan_tmp, d_local_off;
   struct CopyChunk { int64_t row_end; cudaEvent_t ev; };
   std::vector<CopyChunk> chunks;
   std::vector<cudaEvent_t> event_pool;
@@ -307,7 +308,7 @@ int lm_ctx_create(int device, lm_ctx **out) {
     int lo_p = 0, hi_p = 0; // (numerically lowest = greatest priority: the small preparation kernels take the next free SM slots)
     CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
     CU(cudaStreamCreateWithPriority(&c->prep_stream, cudaStreamNonBlocking, hi_p));
-    CU(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithPriority(&c->out_stream, cudaStreamNonBlocking, hi_p));
     CU(cudaEventCreateWithFlags(&c->ev_run_begin, cudaEventDisableTiming));
   }
   CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_pin), 2048, cudaHostAllocDefault));
@@ -326,7 +327,7 @@ void lm_ctx_destroy(lm_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf *bufs[] = {&c->d_segs_raw, &c->d_img_ids, &c->d_host_edges, &c->d_views, &c->d_segs, &c->d_node_view, &c->d_line_off, &c->d_pairs, &c->d_blk_row_off,
+  DevBuf *bufs[] = {&c->d_scan_tmp, &c->d_local_off, &c->d_segs_raw, &c->d_img_ids, &c->d_host_edges, &c->d_views, &c->d_segs, &c->d_node_view, &c->d_line_off, &c->d_pairs, &c->d_blk_row_off,
                     &c->d_blk_src, &c->d_blk_ng, &c->d_blk_pair_off, &c->d_key, &c->d_key2, &c->d_val, &c->d_val2,
                     &c->d_sort_tmp, &c->d_node_row_off, &c->d_scalars, &c->d_nodes, &c->d_row_state, &c->d_row_cand,
                     &c->d_slab, &c->d_edges, &c->d_edges2, &c->d_edge_keys, &c->d_edge_keys2, &c->d_edge_w,
@@ -827,7 +828,7 @@ int lm_tri_run(lm_ctx *c) {
   // scene tables / VP tables travel on the copy stream (see lm_ctx::ev_scene)
   CU(cudaStreamWaitEvent(sp, c->ev_scene, 0));
   CU(cudaStreamWaitEvent(s, c->ev_scene, 0));
-  lm::launch_zero_words(c->d_scalars.p, 128, sp);
+  lm::launch_zero_words(c->d_scalars.p, 256, sp);
   // block tables, derived on the device from the descriptors uploaded with the matches (no transfer now)
   {
     const int n_all = (int)c->blocks.size();
@@ -965,12 +966,18 @@ int lm_tri_run(lm_ctx *c) {
     c->evp.push_back(e);
   }
   std::vector<int> group_has_kernel(n_groups, 0);
+  CU(c->d_nvalid.ensure(4 * (n_shard_nodes + 2)));
+  CU(c->d_local_off.ensure(4 * (n_shard_nodes + 2)));
+  CU(c->d_edge_off.ensure(4 * (n_shard_nodes + 2)));
+  CU(c->d_edge_ng.ensure(4 * std::max<int64_t>(n_rows * ns, 1)));
   for (int g = 0; g < n_groups; ++g) {
     // blocks [bg0, bg1) with whole source images, views [gv0, gv1)
     int bg1 = nb, gv1 = ve;
     if (g + 1 < n_groups) {
-      // the first group is the smallest: it is the only one whose matches nothing else can hide
-      const int64_t target = (int64_t)((double)n_rows * std::pow((g + 1.0) / n_groups, 2.0));
+      // small groups at both ends (smoothstep): the first one is the only one whose matches nothing else can hide, the
+      // last one is the only one whose results nothing else can hide
+      const double tg = (g + 1.0) / n_groups;
+      const int64_t target = (int64_t)((double)n_rows * (tg * tg * (3.0 - 2.0 * tg)));
       bg1 = bg0;
       while (bg1 < nb && row_off[bg1] < target) ++bg1;
       while (bg1 < nb && bg1 > 0 && blk[bg1].src_view == blk[bg1 - 1].src_view) ++bg1; // finish the image
@@ -1039,8 +1046,23 @@ int lm_tri_run(lm_ctx *c) {
       CU(cudaEventRecord(c->evk[2 * g + 1], s));
       group_has_kernel[g] = 1;
       ++launches;
+      // valid_edges_ of the group in compact form: per-node counts -> exclusive scan -> ordered scatter at the global
+      // offsets
+      {
+        cudaStream_t so = c->out_stream; // under the node kernels of the later groups
+        CU(cudaStreamWaitEvent(so, c->evk[2 * g + 1], 0));
+        uint32_t *nv = c->d_nvalid.as<uint32_t>() + (node_lo - c->node_begin);
+        lm::launch_extract_nvalid(p.nodes, node_lo, n_group_nodes, nv, so);
+        size_t tmp = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, nv, c->d_local_off.as<uint32_t>(), (int)(n_group_nodes + 1), so));
+        CU(c->d_scan_tmp.ensure(tmp)); // (not d_sort_tmp: the preparation stream sorts the next group meanwhile)
+        CU(cub::DeviceScan::ExclusiveSum(c->d_scan_tmp.p, tmp, nv, c->d_local_off.as<uint32_t>(), (int)(n_group_nodes + 1), so));
+        lm::launch_group_edges(p.row_state, p.row_ng, p.node_row_off, c->d_local_off.as<uint32_t>(),
+                               c->d_scalars.as<unsigned int>() + 80, g, c->node_begin, node_lo, n_group_nodes, ns,
+                               c->d_edge_off.as<uint32_t>(), c->d_edge_ng.as<uint32_t>(), so);
+        launches += 4;
+      }
       if (c->node_sink) { // the group's records go to the caller's buffer under the kernels of the later groups
-        CU(cudaStreamWaitEvent(c->out_stream, c->evk[2 * g + 1], 0));
         CU(cudaMemcpyAsync(c->node_sink + sizeof(lm::NodeRecord) * node_lo, c->d_nodes.as<lm::NodeRecord>() + node_lo,
                            sizeof(lm::NodeRecord) * n_group_nodes, cudaMemcpyDeviceToHost, c->out_stream));
       }
@@ -1050,23 +1072,10 @@ int lm_tri_run(lm_ctx *c) {
   }
   p.node_begin = c->node_begin;
   p.node_end = c->node_end;
-  // valid_edges_ in compact form: per-node counts -> exclusive scan -> ordered scatter
-  if (n_shard_nodes > 0) {
-    CU(c->d_nvalid.ensure(4 * (n_shard_nodes + 1)));
-    CU(c->d_edge_off.ensure(4 * (n_shard_nodes + 1)));
-    CU(c->d_edge_ng.ensure(4 * std::max<int64_t>(n_rows * ns, 1)));
-    lm::launch_extract_nvalid(p.nodes, c->node_begin, n_shard_nodes, c->d_nvalid.as<uint32_t>(), s);
-    size_t tmp = 0;
-    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_nvalid.as<uint32_t>(), c->d_edge_off.as<uint32_t>(),
-                                     (int)(n_shard_nodes + 1), s));
-    CU(c->d_sort_tmp.ensure(tmp));
-    CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp, c->d_nvalid.as<uint32_t>(), c->d_edge_off.as<uint32_t>(),
-                                     (int)(n_shard_nodes + 1), s));
-    lm::launch_compact_edges_only(p.row_state, p.row_ng, p.node_row_off, c->d_edge_off.as<uint32_t>(), c->node_begin,
-                                  n_shard_nodes, ns, c->d_edge_ng.as<uint32_t>(), s);
-    launches += 4;
-  }
   CU(cudaGetLastError());
+  // the engine's stream ends the run: whatever follows on it (getters, exchange) sees the compact connections
+  CU(cudaEventRecord(c->ev_run_begin, c->out_stream));
+  CU(cudaStreamWaitEvent(s, c->ev_run_begin, 0));
   CU(cudaEventRecord(c->ev1, s));
   // one read-back for the whole run: error / overflow flags, counters, largest node per group
   unsigned int *hs = c->h_pin;
@@ -1076,7 +1085,7 @@ int lm_tri_run(lm_ctx *c) {
   fprintf(stderr, "[lm trace] compute stream drained %.3f ms after run entry\n", lm_ms());
 #endif
   CU(cudaStreamSynchronize(c->copy_stream)); // uploads of images outside this shard may still be in flight
-  if (c->node_sink) CU(cudaStreamSynchronize(c->out_stream));
+  CU(cudaStreamSynchronize(c->out_stream));
 #ifdef LM_TRACE
   fprintf(stderr, "[lm trace] copy stream drained %.3f ms after run entry\n", lm_ms());
 #endif

@@ -1393,6 +1393,45 @@ __global__ void compact_edges_kernel(const uint8_t *__restrict__ row_state, cons
     base += __popc(m);
   }
 }
+// Valid connections of one pipeline group, right after the group's node kernel: global offsets (the groups before it are
+// done: their totals are on the device) and compact (neighbour view << 16 | line) entries in candidate order. One warp
+// per node. (Writing the caller's page-locked result buffers from here over PCIe was measured: 0.25 ms SLOWER per step
+// than one device-to-host copy after the run.)
+__global__ void group_edges_kernel(const uint8_t *__restrict__ row_state, const uint32_t *__restrict__ row_ng,
+                                   const uint32_t *__restrict__ node_row_off, const uint32_t *__restrict__ local_off,
+                                   unsigned int *__restrict__ totals, int g, int64_t shard_node_begin, int64_t node_lo, int64_t n,
+                                   int ns, uint32_t *__restrict__ edge_off, uint32_t *__restrict__ edge_ng) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+  if (i >= n) return;
+  uint32_t before = 0;
+  for (int k = 0; k < g; ++k) before += totals[k];
+  const uint32_t lo = local_off[i], hi = local_off[i + 1];
+  uint32_t base = before + lo;
+  if (lane == 0) {
+    edge_off[node_lo - shard_node_begin + i] = base;
+    if (i == n - 1) {
+      edge_off[node_lo - shard_node_begin + n] = before + local_off[n];
+      totals[g] = local_off[n];
+    }
+  }
+  if (hi == lo) return;
+  const int64_t q0 = (int64_t)node_row_off[node_lo + i] * ns, q1 = (int64_t)node_row_off[node_lo + i + 1] * ns;
+  for (int64_t qb = q0; qb < q1; qb += 32) { // q = row * ns + slot: candidate order
+    const int64_t q = qb + lane;
+    const bool v = (q < q1) && row_state[q] == 2;
+    const unsigned m = __ballot_sync(0xffffffffu, v);
+    if (v) edge_ng[base + __popc(m & ((1u << lane) - 1u))] = row_ng[q / ns];
+    base += __popc(m);
+  }
+}
+void launch_group_edges(const uint8_t *row_state, const uint32_t *row_ng, const uint32_t *node_row_off,
+                        const uint32_t *local_off, unsigned int *totals, int g, int64_t shard_node_begin, int64_t node_lo,
+                        int64_t n, int ns, uint32_t *edge_off, uint32_t *edge_ng, cudaStream_t s) {
+  if (n <= 0) return;
+  group_edges_kernel<<<(int)((n * 32 + 255) / 256), 256, 0, s>>>(row_state, row_ng, node_row_off, local_off, totals, g,
+                                                                 shard_node_begin, node_lo, n, ns, edge_off, edge_ng);
+}
 // directed (src node, dst node) pairs of the compact edge list
 __global__ void edge_pairs_kernel(const uint32_t *__restrict__ edge_off, const uint32_t *__restrict__ edge_ng,
                                   const int64_t *__restrict__ line_off, int64_t node_begin, int64_t n_nodes,

@@ -78,6 +78,9 @@ struct EdgeParams {
 };
 
 size_t tri_smem_bytes(int cap, bool fast);
+void launch_group_edges(const uint8_t *row_state, const uint32_t *row_ng, const uint32_t *node_row_off,
+                        const uint32_t *local_off, unsigned int *totals, int g, int64_t shard_node_begin, int64_t node_lo,
+                        int64_t n, int ns, uint32_t *edge_off, uint32_t *edge_ng, cudaStream_t s);
 void launch_scene_prepare(const double *segs_raw, int64_t n_nodes, double add, const int64_t *line_off, int n_views,
                           double *segs, uint16_t *node_view, cudaStream_t s);
 cudaError_t launch_tri_node_kernel(const TriParams &p, int grid, int block, size_t smem, cudaStream_t s);
