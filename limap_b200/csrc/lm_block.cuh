@@ -66,16 +66,18 @@ LM_HD void householder2(const double x[2], double v[2], double &beta) {
   beta = 2.0 * vp * vp / (sigma + vp * vp);
   v[0] /= vp;
 }
-LM_HD void sphere2_plus(const double x[2], double delta, double out[2]) {
+// hh = {v[0], beta, |x|} of householder2(x) (v[1] is 1), or NULL to compute it here. The solver keeps the triple of the
+// current point: it is a by-product of the line evaluation there (line_from_minimal_col).
+LM_HD void sphere2_plus(const double x[2], double delta, double out[2], const double *hh = nullptr) {
   const double nd = fabs(delta);
   if (nd == 0.0) { out[0] = x[0]; out[1] = x[1]; return; }
-  double v[2], beta;
-  householder2(x, v, beta);
+  double v[2], beta, nx;
+  if (hh) { v[0] = hh[0]; v[1] = 1.0; beta = hh[1]; nx = hh[2]; }
+  else { householder2(x, v, beta); nx = sqrt(x[0] * x[0] + x[1] * x[1]); }
   double sn_, cs_;
   sincos(nd, &sn_, &cs_);
   const double y0 = sn_ / nd * delta, y1 = cs_;
   const double vty = v[0] * y0 + v[1] * y1;
-  const double nx = sqrt(x[0] * x[0] + x[1] * x[1]);
   out[0] = nx * (y0 - v[0] * (beta * vty));
   out[1] = nx * (y1 - v[1] * (beta * vty));
 }
@@ -132,11 +134,13 @@ LM_HD void line_from_minimal(const double x[6], bool want_jac, LineLocal &L) {
 // One tangent column of the same computation (1-wide duals): lane c of a warp takes column c, so the 24 derivatives cost
 // a quarter of the registers of the 4-wide form and a warp computes all of them in one pass. Bit-identical to
 // line_from_minimal: every derivative component is the same expression.
-LM_HD void line_from_minimal_col(const double x[6], int col, bool want_jac, Dual<1> d[3], Dual<1> m[3]) {
+LM_HD void line_from_minimal_col(const double x[6], int col, bool want_jac, Dual<1> d[3], Dual<1> m[3],
+                                 double *hh_out = nullptr) {
   Dual<1> u[4], w[2];
   double v2[2], beta;
   householder2(x + 4, v2, beta);
   const double nx = sqrt(x[4] * x[4] + x[5] * x[5]);
+  if (hh_out) { hh_out[0] = v2[0]; hh_out[1] = beta; hh_out[2] = nx; } // (see sphere2_plus)
   const double Ps[2] = {(-beta * v2[0] * v2[0] + 1.0) * nx, (-beta * v2[0] * v2[1]) * nx};
   // QuaternionPlusJacobian (4x3), column `col` (col 3 belongs to the sphere)
   double pq[4] = {0.0, 0.0, 0.0, 0.0};

@@ -52,6 +52,7 @@ struct WarpState {
   // trust-region scalars (warp-uniform; every lane writes the same value, so no ordering is needed): kept here and
   // accessed through volatile references so that they are not live in registers across the track evaluations
   double cost0, cost, radius, decrease_factor, mcc, sn;
+  double hh_e[3], hh_x[3]; // Householder triple of the sphere part at the last evaluated point / at x (lm_block.cuh)
 };
 
 // Evaluate the whole track at x: cost (always) and, if want_jac, the loss-corrected normal equations with the
@@ -62,15 +63,17 @@ struct WarpState {
 static constexpr int kLmThreads = 128;
 static constexpr int kAccStride = kLmThreads + 1; // doubles between two accumulator rows (bank spread for the row sums)
 LM_D void eval_track(const LMBlockDev *blocks, int S, const double *x, double alpha, double bq, bool want_jac,
-                     const double *scale, LineShared &Ls, Normal *out, double *cn2_out, double *acc) {
+                     const double *scale, LineShared &Ls, Normal *out, double *cn2_out, double *acc, double *hh_out) {
   const int lane = threadIdx.x & 31;
   {
     double xr[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) xr[i] = x[i];
     Dual<1> dd[3], mm[3];
-    line_from_minimal_col(xr, lane & 3, want_jac, dd, mm); // lane c < 4 holds tangent column c (all lanes: the values)
+    double hh[3];
+    line_from_minimal_col(xr, lane & 3, want_jac, dd, mm, hh); // lane c < 4 holds tangent column c (all lanes: the values)
     __syncwarp();
+    if (lane == 4) { hh_out[0] = hh[0]; hh_out[1] = hh[1]; hh_out[2] = hh[2]; }
     if (lane < 4) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -225,11 +228,11 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
   volatile double &cost0 = ws.cost0, &cost = ws.cost, &radius = ws.radius, &decrease_factor = ws.decrease_factor;
   volatile double &mcc = ws.mcc, &sn = ws.sn;
   if (S == 0 || !p.active[t]) {
-    eval_track(blocks, S, ws.x, p.geometric_alpha, bq, false, nullptr, ws.L, &ws.N, nullptr, acc);
+    eval_track(blocks, S, ws.x, p.geometric_alpha, bq, false, nullptr, ws.L, &ws.N, nullptr, acc, ws.hh_e);
     { const double c_ = ws.N.cost; cost0 = c_; cost = c_; }
   } else {
     // iteration 0: evaluate, fix the Jacobi scaling 1/(1+||J_col||)
-    eval_track(blocks, S, ws.x, p.geometric_alpha, bq, true, nullptr, ws.L, &ws.N, ws.cn2, acc);
+    eval_track(blocks, S, ws.x, p.geometric_alpha, bq, true, nullptr, ws.L, &ws.N, ws.cn2, acc, ws.hh_e);
     if (lane == 0) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) ws.scale[c] = 1.0 / (1.0 + sqrt(ws.cn2[c]));
@@ -242,6 +245,8 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) ws.diag[c] = 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ws.hh_x[c] = ws.hh_e[c];
     }
     __syncwarp();
     { const double c_ = ws.N.cost; cost0 = c_; cost = c_; }
@@ -280,7 +285,7 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
         for (int c = 0; c < 10; ++c) An[c] = ws.N.A[c];
         const double rad_ = radius;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { gn[c] = ws.N.g[c]; dg[c] = ws.diag[c] / rad_; }
+        for (int c = 0; c < 4; ++c) { gn[c] = ws.N.g[c]; dg[c] = ws.diag[c] / rad_; } // (4 independent divisions: one latency)
         ok = chol_solve4(An, dg, gn, step);
 #pragma unroll
         for (int c = 0; c < 4; ++c) { step[c] = -step[c]; if (!isfinite(step[c])) ok = false; }
@@ -311,7 +316,7 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
 #pragma unroll
         for (int c = 0; c < 4; ++c) delta[c] = step[c] * ws.scale[c];
         quat_plus(xr, delta, cand);
-        sphere2_plus(xr + 4, delta[3], cand + 4);
+        sphere2_plus(xr + 4, delta[3], cand + 4, ws.hh_x);
 #pragma unroll
         for (int c = 0; c < 6; ++c) snl += (xr[c] - cand[c]) * (xr[c] - cand[c]);
         sn = snl;
@@ -325,7 +330,7 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
       // One evaluation per iteration: the candidate point is evaluated WITH its Jacobian; if the step is accepted the
       // normal equations are already there (a second evaluation at the same point would reproduce them bit for bit:
       // the value parts of the duals do not depend on want_jac).
-      eval_track(blocks, S, ws.cand, p.geometric_alpha, bq, true, ws.scale, ws.L, &ws.Nc, nullptr, acc);
+      eval_track(blocks, S, ws.cand, p.geometric_alpha, bq, true, ws.scale, ws.L, &ws.Nc, nullptr, acc, ws.hh_e);
       const double cost_c = ws.Nc.cost;
       if (!(sqrt(sn) > 0.0)) { term = 5; break; }
       const double cost_x = cost;
@@ -336,6 +341,7 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
         if (lane < 6) ws.x[lane] = ws.cand[lane];
         if (lane < 10) ws.N.A[lane] = ws.Nc.A[lane];
         if (lane < 4) ws.N.g[lane] = ws.Nc.g[lane];
+        if (lane >= 4 && lane < 7) ws.hh_x[lane - 4] = ws.hh_e[lane - 4];
         __syncwarp();
         cost = cost_c;
         const double tq = 2.0 * rel - 1.0;

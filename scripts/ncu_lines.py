@@ -1,6 +1,7 @@
 """Per-source-line table of an ncu --set full --import-source capture: samples, warp instructions and the dominant
 stall reasons, attributed to the OUTERMOST inlined-at line in the given file (so helper code counts for its call site).
-Usage: ncu_lines.py <rep> <kernel-substr> <nvdisasm -gi output> <file.cu> [top=40] [name:lo-hi ...]"""
+With `inner` as an extra argument the INNERMOST location is used instead (file:line of the code itself).
+Usage: ncu_lines.py <rep> <kernel-substr> <nvdisasm -gi output> <file.cu> [top=40] [inner] [name:lo-hi ...]"""
 import csv
 import re
 import subprocess
@@ -10,8 +11,11 @@ from collections import defaultdict
 rep, kern, dis, fname = sys.argv[1:5]
 top = 40
 regions = []
+inner = False
 for a in sys.argv[5:]:
-    if ":" in a:
+    if a == "inner":
+        inner = True
+    elif ":" in a:
         n, r = a.split(":")
         lo, hi = r.split("-")
         regions.append((n, int(lo), int(hi)))
@@ -36,6 +40,7 @@ base = sass[0][0]
 line_of = {}
 infn = False
 cur = None
+in_block = False
 for l in open(dis):
     if l.startswith(".text.") and kern in l:
         infn = True
@@ -46,12 +51,17 @@ for l in open(dis):
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', l)
     if m:
-        if m.group(3) is None:
+        if inner:
+            if not in_block:  # the first annotation line of a block is the innermost location
+                cur = (m.group(1).split("/")[-1] + ":" + m.group(2))
+            in_block = True
+        elif m.group(3) is None:
             cur = int(m.group(2)) if m.group(1).endswith(fname) else None
         continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", l)
     if m:
         line_of[int(m.group(1), 16)] = cur
+        in_block = False
 agg = defaultdict(lambda: [0.0, 0.0, 0.0, [0.0] * len(stall_cols)])
 ts = ti = 0.0
 tot_st = [0.0] * len(stall_cols)
@@ -76,7 +86,7 @@ if regions:
     for n, lo, hi in regions:
         s = [0.0, 0.0, 0.0, [0.0] * len(stall_cols)]
         for ln, a in agg.items():
-            if ln is not None and lo <= ln <= hi:
+            if isinstance(ln, int) and lo <= ln <= hi:
                 s[0] += a[0]; s[1] += a[1]; s[2] += a[2]
                 for k in range(len(stall_cols)):
                     s[3][k] += a[3][k]
