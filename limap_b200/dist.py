@@ -131,6 +131,20 @@ def partition_by_cost(costs, world):
     return [np.asarray(sorted(x), dtype=np.int64) for x in out]
 
 
+def partition_ranges_by_cost(costs, world):
+    """Contiguous ranges [begin, end) of units for `world` ranks with nearly equal total cost (boundaries where the
+    running cost crosses k / world of the total). Contiguous shares of flat per-support arrays are views, not copies."""
+    c = np.asarray(costs, dtype=np.float64)
+    n = len(c)
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    cuts = [0]
+    for k in range(1, max(world, 1)):
+        b = int(np.searchsorted(cum, cum[-1] * k / world, side="left"))
+        cuts.append(min(max(b, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[k], cuts[k + 1]) for k in range(max(world, 1))]
+
+
 def gather_rows(local_index, local_rows, total, group=None):
     """Every rank holds rows of a [total, k] table for its own indices; returns the full table on every rank (one
     padded all-gather of the indices and one of the rows)."""
@@ -161,17 +175,22 @@ def slice_tracks(index, sup_off, *per_support):
 def solve_line_ba_sharded(solve, kvec, qvec, tvec, sup_off, sup_view, segs, line3d, line_init, rank, world, group=None,
                           device="cuda", **kw):
     """Line BA with constant cameras is block-separable per track (hybrid_bundle_adjustment.cc:106-123,156-197):
-    tracks are dealt by #supports, every rank solves its share with `solve` (BAEngine.solve) and the refined lines
-    (+ iteration counts and costs) are all-gathered. Returns dict(line[T,6], iters[T,2], cost[T,2]) on every rank."""
+    every rank solves a contiguous range of tracks with the same number of supports as the others (the share is a view
+    of the caller's flat arrays: nothing is re-packed on the host; inside a rank the kernel's warps fetch tracks
+    dynamically) with `solve` (BAEngine.solve), and the refined lines (+ iteration counts and costs) are all-gathered.
+    Returns dict(line[T,6], iters[T,2], cost[T,2]) on every rank."""
     import torch
     sup_off = np.asarray(sup_off, dtype=np.int64)
     T = len(sup_off) - 1
-    mine = partition_by_cost(sup_off[1:] - sup_off[:-1], world)[rank]
-    off, (sv, sg, l3) = slice_tracks(mine, sup_off, sup_view, segs, line3d)
-    res = solve(kvec, qvec, tvec, off, sv, sg, l3, np.ascontiguousarray(np.asarray(line_init)[mine]), **kw)
-    table = np.concatenate([res["line"], res["iters"].astype(np.float64), res["cost"]], axis=1) if len(mine) else \
+    b, e = partition_ranges_by_cost(sup_off[1:] - sup_off[:-1], world)[rank]
+    s0, s1 = int(sup_off[b]), int(sup_off[e])
+    off = sup_off[b:e + 1] - s0
+    res = solve(kvec, qvec, tvec, off, np.asarray(sup_view)[s0:s1], np.asarray(segs)[s0:s1], np.asarray(line3d)[s0:s1],
+                np.asarray(line_init)[b:e], **kw)
+    table = np.concatenate([res["line"], res["iters"].astype(np.float64), res["cost"]], axis=1) if e > b else \
         np.zeros((0, 10))
-    full = gather_rows(mine, torch.as_tensor(table, dtype=torch.float64, device=device), T, group).cpu().numpy()
+    full = gather_rows(np.arange(b, e, dtype=np.int64), torch.as_tensor(table, dtype=torch.float64, device=device), T,
+                       group).cpu().numpy()
     return dict(line=full[:, :6], iters=full[:, 6:8].astype(np.int32), cost=full[:, 8:10])
 
 

@@ -74,6 +74,20 @@ def test_partition_by_cost_is_balanced_and_complete():
     assert np.array_equal(sub, np.concatenate([flat[sup_off[3]:sup_off[4]], flat[sup_off[10]:sup_off[11]]]))
 
 
+def test_partition_ranges_by_cost_are_contiguous_and_balanced():
+    from limap_b200.dist import partition_ranges_by_cost
+    rng = np.random.default_rng(1)
+    cost = rng.integers(2, 60, 1001)
+    for world in (1, 2, 3, 8):
+        r = partition_ranges_by_cost(cost, world)
+        assert len(r) == world and r[0][0] == 0 and r[-1][1] == 1001
+        assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+        tot = [cost[b:e].sum() for b, e in r]
+        assert max(tot) - min(tot) <= 2 * 60
+    assert partition_ranges_by_cost(np.zeros(0), 3) == [(0, 0)] * 3
+    assert partition_ranges_by_cost([5.0], 2) in ([(0, 0), (0, 1)], [(0, 1), (1, 1)])
+
+
 def _ba_worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -94,6 +108,7 @@ def _ba_worker(rank, world, port, q):
     def fake_solve(kvec, qvec, tvec, off, sv, sg, l3, li, **kw):  # stands in for BAEngine.solve (needs a GPU)
         n = len(off) - 1
         seen["n"] = n
+        seen["s"] = int(off[-1])
         # a function of the track's own data only: line = init + sum of its segments' first coordinate
         s = np.array([sg[off[t]:off[t + 1], 0].sum() for t in range(n)])
         return dict(line=li + s[:, None], iters=np.stack([off[1:] - off[:-1], np.zeros(n, np.int64)], 1).astype(np.int32),
@@ -102,7 +117,7 @@ def _ba_worker(rank, world, port, q):
                                 device="cpu")
     s_all = np.array([segs[sup_off[t]:sup_off[t + 1], 0].sum() for t in range(T)])
     ok = np.allclose(out["line"], init + s_all[:, None]) and np.array_equal(out["iters"][:, 0], cnt)
-    ok &= np.allclose(out["cost"][:, 1], 0.5 * s_all) and abs(seen["n"] - T / world) <= 1
+    ok &= np.allclose(out["cost"][:, 1], 0.5 * s_all) and abs(seen["s"] - S / world) <= 9  # shares are contiguous ranges with equal support counts
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
