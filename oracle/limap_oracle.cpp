@@ -1,5 +1,5 @@
 // oracle/limap_oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
-// PARITY UNPINNED (see orc_geom.h header).
+// PARITY PINNED to oracle/_ref (see orc_geom.h header).
 //
 // C entry points (ctypes) over the fp64 CPU restatement of the limap
 // triangulation / scoring / track-building path. Built by oracle/Makefile into

@@ -1,6 +1,7 @@
 """ctypes wrapper of the CPU oracle (oracle/_build/liblimap_oracle.so). TEST INFRASTRUCTURE ONLY:
 imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
-PARITY UNPINNED -- see oracle/orc_geom.h."""
+Pinning status per component: oracle/orc_geom.h (pinned to oracle/_ref), orc_lm.h (solver loop unpinned), orc_vp.h and
+orc_sfm.cpp (third-party algorithms restated: PARITY UNPINNED)."""
 import ctypes as C
 import os
 import subprocess

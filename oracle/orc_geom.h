@@ -5,12 +5,12 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs may use anything under oracle/.
 //
-// PARITY UNPINNED: the reference cannot be compiled in this image (Eigen,
-// Ceres, COLMAP, JLinkage absent) and its own tests hold a single known-answer
-// vector for this path (tests/base/test_linebase.py:8-17, Line2d length and
-// direction) which tests/test_oracle_kat.py checks. Everything else is pinned
-// only by this restatement, written function-by-function from the files cited
-// below (paths relative to /root/reference/src/limap/).
+// PARITY PINNED to the reference's own compiled code: the reference's build system cannot run in this image (Eigen,
+// Ceres, COLMAP, JLinkage absent), but its hot-path sources compile unchanged against the header shims in
+// oracle/ref_shim/ (oracle/Makefile target `ref` -> oracle/_ref/liblimap_ref.so), and tests/test_ref_pinning.py holds
+// every function of this restatement to that library on seeded inputs. The reference's own tests hold a
+// single known-answer vector for this path (tests/base/test_linebase.py:8-17), checked in tests/test_oracle_kat.py.
+// Written function-by-function from the files cited below (paths relative to /root/reference/src/limap/).
 //
 // No Eigen: the few Eigen operations the reference relies on are restated with
 // the same evaluation structure (normalized(), 3x3 cofactor inverse,

@@ -1,4 +1,4 @@
-// oracle/orc_lm.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE. PARITY UNPINNED (see orc_lm.h).
+// oracle/orc_lm.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE. Pinning status: see orc_lm.h (functors pinned, solver loop unpinned).
 // C entry points of the CPU restatement of the per-track line refinement / line bundle adjustment.
 #include "orc_lm.h"
 #ifdef _OPENMP

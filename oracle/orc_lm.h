@@ -1,6 +1,8 @@
 // oracle/orc_lm.h — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
-// PARITY UNPINNED (see orc_geom.h): additionally, the solver the reference calls (Ceres, version not
-// pinned: cmake/FindDependencies.cmake:19) is absent from /root/reference. The trust-region
+// Residual functors, minimal line and segment cut: PINNED to the reference's compiled code (tests/test_ref_pinning.py:
+// values and 6-column Jacobians of GeometricRefinementFunctor / VPConstraintsFunctor). The SOLVER LOOP is PARITY
+// UNPINNED: the solver the reference calls (Ceres, version not pinned: cmake/FindDependencies.cmake:19) is absent from
+// /root/reference. The trust-region
 // Levenberg-Marquardt below restates the published Ceres algorithm (trust_region_minimizer.cc,
 // levenberg_marquardt_strategy.cc, corrector.cc, manifold.cc of ceres-solver 2.1/2.2, Manifold API:
 // QuaternionManifold + SphereManifold<2>) from the Ceres documentation; anchors are the reference's

@@ -1,7 +1,7 @@
 // orc_merging.cpp — CPU restatement of the post-triangulation track filters and the iterative remerge.
 //
-// TEST INFRASTRUCTURE (oracle). PARITY UNPINNED: the reference cannot be built in this image;
-// this file restates, in plain fp64 C++ and with the reference's loop structure,
+// TEST INFRASTRUCTURE (oracle). PARITY PINNED to the reference's compiled merging_utils.cc / RemergeLineTracks
+// (oracle/_ref, tests/test_ref_pinning.py::test_track_filters_and_remerge). This file restates, in plain fp64 C++ and with the reference's loop structure,
 //   merging::CheckReprojection / FilterSupportingLines     merging/merging_utils.cc:27-87
 //   merging::CheckSensitivity / FilterTracksBySensitivity  merging/merging_utils.cc:89-131
 //   merging::FilterTracksByOverlap                         merging/merging_utils.cc:133-155

@@ -1,5 +1,5 @@
 // oracle/orc_triangulation.h — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
-// PARITY UNPINNED (see orc_geom.h header).
+// PARITY PINNED to the reference's compiled GlobalLineTriangulator (oracle/_ref, tests/test_ref_pinning.py; see orc_geom.h).
 //
 // fp64 CPU restatement of the triangulation / scoring / track-building path of
 // cvg/limap. Loop structure, container choices
