@@ -1773,63 +1773,6 @@ namespace {
 struct V3h { double x, y, z; };
 inline V3h v3(double x, double y, double z) { return V3h{x, y, z}; }
 inline V3h crossh(V3h a, V3h b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-inline double normh(V3h a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
-inline V3h scaleh(V3h a, double s) { return v3(a.x * s, a.y * s, a.z * s); }
-
-// MinimalInfiniteLine3d(InfiniteLine3d(Line3d)) (base/infinite_line.cc:67-71,180-218): orthonormal
-// representation, Q -> quaternion with Eigen's Quaterniond(Matrix3d) (Shepperd).
-void minimal_from_line(const double *l, double out[6]) {
-  V3h s = v3(l[0], l[1], l[2]), e = v3(l[3], l[4], l[5]);
-  V3h a = v3(e.x - s.x, e.y - s.y, e.z - s.z);
-  double an2 = a.x * a.x + a.y * a.y + a.z * a.z;
-  if (an2 > 0) a = scaleh(a, 1.0 / std::sqrt(an2)); // direction() = normalized()
-  V3h b = crossh(s, a);
-  const double bn = normh(b);
-  const double w1 = 1.0, w2 = bn, den = std::sqrt(w1 * w1 + w2 * w2);
-  out[4] = w1 / den;
-  out[5] = w2 / den;
-  V3h q0 = scaleh(a, 1.0 / normh(a)), q1, q2;
-  if (bn > 1e-12) {
-    q1 = scaleh(b, 1.0 / bn);
-    V3h axb = crossh(a, b);
-    q2 = scaleh(axb, 1.0 / normh(axb));
-  } else {
-    const double av[3] = {a.x, a.y, a.z};
-    int best = 0;
-    if (std::fabs(av[1]) > std::fabs(av[0])) best = 1;
-    if (std::fabs(av[2]) > std::fabs(av[best])) best = 2;
-    const int i1 = (best + 1) % 3, i2 = (best + 2) % 3;
-    double bp[3];
-    bp[i1] = 1.0; bp[i2] = 1.0; bp[best] = -(av[i1] * bp[i1] + av[i2] * bp[i2]) / av[best];
-    V3h bprime = v3(bp[0], bp[1], bp[2]);
-    q1 = scaleh(bprime, 1.0 / normh(bprime));
-    V3h axb = crossh(a, bprime);
-    q2 = scaleh(axb, 1.0 / normh(axb));
-  }
-  const double R[3][3] = {{q0.x, q1.x, q2.x}, {q0.y, q1.y, q2.y}, {q0.z, q1.z, q2.z}};
-  double t = R[0][0] + R[1][1] + R[2][2];
-  double q[4];
-  if (t > 0) {
-    t = std::sqrt(t + 1.0);
-    q[0] = 0.5 * t;
-    t = 0.5 / t;
-    q[1] = (R[2][1] - R[1][2]) * t; q[2] = (R[0][2] - R[2][0]) * t; q[3] = (R[1][0] - R[0][1]) * t;
-  } else {
-    int i = 0;
-    if (R[1][1] > R[0][0]) i = 1;
-    if (R[2][2] > R[i][i]) i = 2;
-    const int j = (i + 1) % 3, k = (j + 1) % 3;
-    t = std::sqrt(R[i][i] - R[j][j] - R[k][k] + 1.0);
-    double v[3];
-    v[i] = 0.5 * t;
-    t = 0.5 / t;
-    q[0] = (R[k][j] - R[j][k]) * t;
-    v[j] = (R[j][i] + R[i][j]) * t;
-    v[k] = (R[k][i] + R[i][k]) * t;
-    q[1] = v[0]; q[2] = v[1]; q[3] = v[2];
-  }
-  for (int i = 0; i < 4; ++i) out[i] = q[i];
-}
 
 // MinimalInfiniteLine3d::GetInfiniteLine (:220-231) + GetLineSegmentFromInfiniteLine3d (:265-287)
 void segment_from_minimal(const double x[6], const double *l3d, int64_t n, int num_outliers, double out[6]) {
