@@ -15,14 +15,17 @@ if what == "tri":
     from limap_b200.config import DEFAULT_YAML_TRIANGULATION
     from limap_b200.engine import TriEngine
     from limap_b200.synth import CONFIGS, make_scene
-    sc = make_scene(**CONFIGS[os.environ.get("LM_WORKLOAD", "hypersim100")])
+    cfg_scene = dict(CONFIGS[os.environ.get("LM_WORKLOAD", "hypersim100")])
+    if os.environ.get("LM_K"):  # matches per (line, neighbour): rows per node = N * K (occupancy experiments)
+        cfg_scene["K"] = int(os.environ["LM_K"])
+    sc = make_scene(**cfg_scene)
     eng = TriEngine(dict(DEFAULT_YAML_TRIANGULATION))
     eng.upload(sc)
     eng.set_ranges(*sc.ranges)
     eng.add_matches_bulk(*sc.bulk_matches())
     for _ in range(n):
         st = eng.run()
-    print("tri", st["last_node_kernel_ms"], st["n_candidates"])
+    print("tri", st["last_node_kernel_ms"], st["n_candidates"], "max rows/node", st["max_rows_per_node"])
 elif what == "lm":
     from limap_b200.engine import BAEngine
     from limap_b200.synth import make_tracks
