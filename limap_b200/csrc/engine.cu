@@ -1685,28 +1685,49 @@ int64_t lm_tri_build_tracks(lm_ctx *c, int64_t *n_support_total) {
   if (trace) fprintf(stderr, "[lm trace] build_tracks: graph (%zu nodes, %zu edges) ready at %.2f ms\n", n_gn, order.size(), tr_ms());
   if (n_gn == 0) return 0;
   std::vector<int> parent(n_gn, -1);
-  std::vector<std::vector<int>> images(n_gn); // sorted distinct image ids of each root's track
-  for (size_t i = 0; i < n_gn; ++i) images[i].push_back(0);
-  {
-    // view index of a node id: binary search in line_off
-    for (size_t i = 0; i < n_gn; ++i) {
-      int v = (int)(std::upper_bound(c->line_off.begin(), c->line_off.end(), gnode[i]) - c->line_off.begin()) - 1;
-      images[i][0] = v;
-    }
-  }
+  // view index of a graph node: binary search in line_off
+  std::vector<int> view_of(n_gn);
+  for (size_t i = 0; i < n_gn; ++i)
+    view_of[i] = (int)(std::upper_bound(c->line_off.begin(), c->line_off.end(), gnode[i]) - c->line_off.begin()) - 1;
   // The reference's union_find_get_root compresses recursively (every node on the path points to the
-  // root afterwards); uf_root does the same iteratively.
-  for (const uint64_t e : order) {
-    size_t r1 = uf_root((size_t)(e >> 32), parent), r2 = uf_root((size_t)(e & 0xffffffffull), parent);
-    if (r1 == r2) continue;
-    size_t dst, srcn;
-    if (images[r1].size() < images[r2].size()) { parent[r1] = (int)r2; dst = r2; srcn = r1; }
-    else { parent[r2] = (int)r1; dst = r1; srcn = r2; }
-    std::vector<int> merged;
-    std::set_union(images[dst].begin(), images[dst].end(), images[srcn].begin(), images[srcn].end(),
-                   std::back_inserter(merged));
-    images[dst].swap(merged);
-    std::vector<int>().swap(images[srcn]);
+  // root afterwards); uf_root does the same iteratively. The union direction depends on the number of DISTINCT images
+  // of the two tracks (merging.cc:40-50): a bit set per root when the scene has few views (a union is an OR and a
+  // popcount), sorted id vectors otherwise.
+  const int V = c->V;
+  const char *bs_env = getenv("LIMAP_B200_UF_BITSET_MAX_VIEWS"); // (tests force the vector path with 0)
+  if (V <= (bs_env ? atoi(bs_env) : 1024)) {
+    const size_t W = (size_t)(V + 63) / 64;
+    std::vector<uint64_t> bits(n_gn * W, 0);
+    std::vector<int> n_img(n_gn, 1);
+    for (size_t i = 0; i < n_gn; ++i) bits[i * W + (size_t)view_of[i] / 64] = 1ull << (view_of[i] % 64);
+    for (const uint64_t e : order) {
+      size_t r1 = uf_root((size_t)(e >> 32), parent), r2 = uf_root((size_t)(e & 0xffffffffull), parent);
+      if (r1 == r2) continue;
+      size_t dst, srcn;
+      if (n_img[r1] < n_img[r2]) { parent[r1] = (int)r2; dst = r2; srcn = r1; }
+      else { parent[r2] = (int)r1; dst = r1; srcn = r2; }
+      int cnt = 0;
+      for (size_t w = 0; w < W; ++w) {
+        bits[dst * W + w] |= bits[srcn * W + w];
+        cnt += __builtin_popcountll(bits[dst * W + w]);
+      }
+      n_img[dst] = cnt;
+    }
+  } else {
+    std::vector<std::vector<int>> images(n_gn); // sorted distinct image ids of each root's track
+    for (size_t i = 0; i < n_gn; ++i) images[i].push_back(view_of[i]);
+    for (const uint64_t e : order) {
+      size_t r1 = uf_root((size_t)(e >> 32), parent), r2 = uf_root((size_t)(e & 0xffffffffull), parent);
+      if (r1 == r2) continue;
+      size_t dst, srcn;
+      if (images[r1].size() < images[r2].size()) { parent[r1] = (int)r2; dst = r2; srcn = r1; }
+      else { parent[r2] = (int)r1; dst = r1; srcn = r2; }
+      std::vector<int> merged;
+      std::set_union(images[dst].begin(), images[dst].end(), images[srcn].begin(), images[srcn].end(),
+                     std::back_inserter(merged));
+      images[dst].swap(merged);
+      std::vector<int>().swap(images[srcn]);
+    }
   }
   if (trace) fprintf(stderr, "[lm trace] build_tracks: union-find done at %.2f ms\n", tr_ms());
   std::vector<int> label(n_gn, -1);
@@ -1726,7 +1747,7 @@ int64_t lm_tri_build_tracks(lm_ctx *c, int64_t *n_support_total) {
   for (size_t i = 0; i < n_gn; ++i) {
     if (label[i] < 0) continue;
     Track &t = c->tracks[label[i]];
-    const int v = (int)(std::upper_bound(c->line_off.begin(), c->line_off.end(), gnode[i]) - c->line_off.begin()) - 1;
+    const int v = view_of[i];
     t.img.push_back(c->img_ids[v]);
     t.line.push_back((int)(gnode[i] - c->line_off[v]));
     t.node.push_back((int)i);

@@ -174,16 +174,22 @@ def make_scene(V=10, L=100, N=5, K=4, seed=1234, scale=1.0, noise_px=0.5, G=None
     line_off = np.asarray(line_off, np.int64)
 
     # neighbours: N nearest camera centres
-    D = np.linalg.norm(Cs[:, None, :] - Cs[None, :, :], axis=2)
-    np.fill_diagonal(D, np.inf)
     Nn = min(N, V - 1)
-    nb_idx = np.argsort(D, axis=1)[:, :Nn]
+    if V <= 4096:
+        D = np.linalg.norm(Cs[:, None, :] - Cs[None, :, :], axis=2)
+        np.fill_diagonal(D, np.inf)
+        nb_idx = np.argsort(D, axis=1)[:, :Nn]
+    else:  # Rome16K-sized scenes: no V x V distance matrix
+        from scipy.spatial import cKDTree as _Tree
+        _, nn_c = _Tree(Cs).query(Cs, k=Nn + 1)
+        nb_idx = np.stack([row[row != v][:Nn] for v, row in enumerate(nn_c)])
     neighbors = {int(img_ids[v]): [int(img_ids[u]) for u in nb_idx[v]] for v in range(V)}
 
     # matches with decoys
     from scipy.spatial import cKDTree
     mids = [(s[:, :2] + s[:, 2:]) * 0.5 for s in segs_all]
-    trees = [cKDTree(m) for m in mids]
+    need_tree = set(range(V)) if match_views is None else {int(u) for v in match_views for u in nb_idx[v]}
+    trees = [cKDTree(m) if v in need_tree else None for v, m in enumerate(mids)]
     matches = {}
     for v in (range(V) if match_views is None else match_views):
         mv = {}
@@ -246,6 +252,7 @@ CONFIGS = {
     "hypersim10": dict(V=10, L=800, N=9, K=10, seed=1234),              # configs[0] stand-in
     "hypersim100": dict(V=100, L=1000, N=20, K=10, seed=1235),          # configs[1] (the metric's config)
     "sweep500": dict(V=500, L=400, N=40, K=10, seed=1236),              # configs[2]
+    "rome16k": dict(V=15000, L=300, N=20, K=10, seed=1238),             # configs[4] (generate with match_views=<shard>)
 }
 
 

@@ -99,3 +99,45 @@ def test_line_ba_10k_tracks_x_30_supports(max_iter):
     gi, oi = int(g["iters"][:, 0].sum()), int(o["iters"][:, 0].sum())
     assert 0.8 < gi / oi < 1.25, (gi, oi)
     assert (g["iters"][:, 0] <= max_iter).all()
+
+
+def test_rome16k_shard_one_gpu_share_of_configs4():
+    """BASELINE.json configs[4] (Rome16K shape: V = 15 000 views, L = 300, N = 20, K = 10 = 9e8 match rows on 8 GPUs): the
+    share of ONE GPU -- 1875 source images, 1.125e8 match rows against the replicated 4.5e6-line scene -- through
+    properties that need no oracle at this size, plus the oracle on a few of its source images:
+    counters consistent with the node records, nothing outside the shard, a pipelined second run bit-identical, and
+    node-for-node parity on the first 3 source images."""
+    from limap_b200.engine import TriEngine
+    from oracle import oracle as orc
+    V = CONFIGS["rome16k"]["V"]
+    per = V // 8
+    sc = make_scene(**CONFIGS["rome16k"], match_views=range(per))
+    ids = [int(i) for i in sc.img_ids[:per]]
+    src, ng, off, pairs = sc.bulk_matches(ids)
+    assert len(pairs) == per * 300 * 20 * 10 and int(sc.line_off[-1]) == V * 300
+    cfg = dict(DEFAULT_YAML_TRIANGULATION)
+    eng = TriEngine(cfg)
+    eng.upload(sc)
+    eng.set_ranges(*sc.ranges)
+    eng.add_matches_bulk(src, ng, off, pairs)
+    eng.set_shard(0, per)
+    st = eng.run()
+    nodes = eng.get_nodes().copy()
+    n_shard = int(sc.line_off[per])
+    assert st["n_rows"] == len(pairs) and st["n_nodes"] == V * 300
+    assert int(nodes["n_cand"][:n_shard].sum()) == st["n_candidates"] > 1e6  # (15 000 views: short baselines)
+    assert int(nodes["n_valid"][:n_shard].sum()) == st["n_valid_edges"] > 1e4
+    assert not nodes["n_cand"][n_shard:].any() and not nodes["score"][n_shard:].any()  # outside the shard: empty records
+    has = nodes["n_cand"][:n_shard] > 0
+    assert np.isfinite(nodes["line"][:n_shard][has]).all() and (nodes["n_valid"] <= nodes["n_cand"]).all()
+    eng.set_pipeline_groups(6)
+    st2 = eng.run()
+    assert st2["n_candidates"] == st["n_candidates"] and eng.get_nodes().tobytes() == nodes.tobytes()
+    # the oracle on the first source images of the shard
+    few = ids[:3]
+    o = orc.OracleTri(cfg, threads=orc.usable_cpus(), node_parallel=True)
+    o.upload(sc)
+    o.set_ranges(*sc.ranges)
+    for i in few:
+        o.add_image_matches(i, *sc.flat_matches(i))
+    compare_nodes_fast(few, eng, o)

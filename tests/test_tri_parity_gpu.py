@@ -201,6 +201,15 @@ def test_bulk_add_and_pipeline_groups_match_per_image_adds():
         for k in ("track_off", "img_ids", "line_ids", "node_ids"):
             assert np.array_equal(tr[k], tr_ref[k]), k
         assert np.array_equal(tr["track_line"], tr_ref["track_line"])
+        # distinct-image counts of the union-find: bit sets (few views) and sorted vectors (many views) agree
+        import os
+        os.environ["LIMAP_B200_UF_BITSET_MAX_VIEWS"] = "0"
+        try:
+            tr_vec = eng.build_tracks()
+        finally:
+            del os.environ["LIMAP_B200_UF_BITSET_MAX_VIEWS"]
+        for k in ("track_off", "img_ids", "line_ids", "node_ids", "track_line"):
+            assert np.array_equal(tr_vec[k], tr[k]), k
 
 
 def test_full_size_hypersim100_properties():
