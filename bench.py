@@ -286,6 +286,25 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run on (and therefore allocate pinned host buffers from) the CPU cores next to this rank's
+    GPU, so that N ranks uploading at once do not pull their pages across the socket interconnect. Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -319,6 +338,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: limap_b200 has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL's own log lines (version banner, NCCL_DEBUG output) go to stderr: stdout carries the one JSON line
@@ -552,6 +572,7 @@ def main():
                            "pairs": {"past_3d_gates": int(st["n_pairs_gated"]), "scored_exact_fp64": int(st["n_pairs_exact"])},
                            "parallelism": f"source-image shards x{world}"
                                           + (", one all-gather of node records + valid connections per step" if world > 1 else ""),
+                           "host_cpus_bound_rank0": numa,
                            "l2": "inputs larger than L2 (match rows + sort buffers > 126 MB per step)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "parity": parity}
