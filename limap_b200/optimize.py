@@ -153,11 +153,16 @@ class HybridBAEngine:
         return out
 
     def _resegment(self, num_outliers):
-        saved = self.config_.num_outliers_aggregate
-        self.config_.num_outliers_aggregate = num_outliers
-        self.Solve()
-        self.config_.num_outliers_aggregate = saved
-        return self._res["line"]
+        """GetOutputLineTracks(num_outliers != num_outliers_aggregate): only the segment cut
+        (GetLineSegmentFromInfiniteLine3d, hybrid_bundle_adjustment.cc:288-301) depends on it, so the refined infinite
+        lines are cut again -- a zero-iteration pass over the stored arrays -- instead of solving the problem twice."""
+        ids, _, kvec, qvec, tvec = self._imagecols.arrays()
+        sup_off, sup_view, segs, l3d, _ = self._arr
+        c = self.config_
+        res = self._ba.solve(kvec, qvec, tvec, sup_off, sup_view, segs, l3d, np.ascontiguousarray(self._res["line"]),
+                             max_num_iterations=0, min_num_images=1 << 30, num_outliers=num_outliers,
+                             geometric_alpha=c.geometric_alpha, cauchy_scale=c.line_geometric_loss_scale)
+        return res["line"]
 
     def GetOutputLines(self, num_outliers=2):
         return {k: t.line for k, t in self.GetOutputLineTracks(num_outliers).items()}

@@ -71,6 +71,15 @@ def test_runner_style_triangulation_and_ba():
     moved = np.abs(lines - init).max(1) > 1e-9
     n_img = np.array([t.count_images() for t in linetracks])
     assert moved[n_img >= 4].mean() > 0.9
+    # GetOutputLineTracks with another num_outliers only re-cuts the refined infinite lines (no second solve): the result
+    # is the one a solve configured with that trim gives
+    out0 = ba_engine.GetOutputLineTracks(num_outliers=0)
+    ref0 = orc.refine_tracks(ts, max_num_iterations=200, min_num_images=4, num_outliers=0)
+    lines0 = np.array([np.concatenate([out0[k].line.start, out0[k].line.end]) for k in range(len(linetracks))])
+    d0 = np.minimum(np.abs(lines0 - ref0["line"]).max(1), np.abs(lines0 - ref0["line"][:, [3, 4, 5, 0, 1, 2]]).max(1))
+    ok0 = np.isfinite(ref0["line"]).all(1)
+    assert ok0.sum() > 10 and d0[ok0].max() <= 1e-4
+    assert np.abs(lines0 - lines).max() > 1e-6  # (the untrimmed cut is a different segment)
 
 
 def test_triangulate_image_index_error_and_model_check():
