@@ -105,3 +105,24 @@ def test_runner_mirror_cuda_equals_oracle_backend_hypersim10(tmp_path, monkeypat
     assert d.max() <= 1e-4, d.max()
     assert rep_gpu == _report(cpu_tracks) and rep_gpu[0] == len(m_c)
     assert (tmp_path / "out" / "finaltracks" / "track_0.txt").exists()
+
+
+REF_TEST_LINEBASE = "/root/reference/tests/base/test_linebase.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TEST_LINEBASE), reason="the reference tree is only present in the authoring container")
+def test_reference_own_linebase_test_passes_on_the_mirror():
+    """The one test of the reference's own suite that touches a hot-path type (tests/base/test_linebase.py), loaded by
+    path and run unmodified against `import limap` = this repository's alias package."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_test_linebase", REF_TEST_LINEBASE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    import limap
+    assert mod.limap is limap and limap.base.__name__ == "limap_b200.base"
+    ran = 0
+    for name in dir(mod):
+        if name.startswith("test_"):
+            getattr(mod, name)()
+            ran += 1
+    assert ran >= 1
