@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "ci_workflow: marker of the reference's own tests (loaded by path in test_runner_dropin.py)")
 
 
 @pytest.fixture(scope="session")
