@@ -278,7 +278,7 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
       // the 4x4 solve is warp-uniform: every lane computes it from the shared state (no divergence, no extra issue slots)
       double step[4];
       bool ok;
-      mcc = 0;
+      double mcc_l = 0; // (kept in a register until the test below; the shared copy is written once, for after the evaluation)
       {
         double An[10], gn[4], dg[4];
 #pragma unroll
@@ -299,15 +299,16 @@ template <int MB> __global__ void __launch_bounds__(128, MB) lm_refine_kernel(co
 #pragma unroll
             for (int b = a; b < 4; ++b) { sAs += ((a == b) ? 1.0 : 2.0) * step[a] * step[b] * An[idx]; ++idx; }
           }
-          mcc = -(sg + 0.5 * sAs);
+          mcc_l = -(sg + 0.5 * sAs);
         }
       }
-      if (!ok || !(mcc > 0.0)) {
+      if (!ok || !(mcc_l > 0.0)) {
         if (++invalid >= p.max_invalid) { term = 4; break; }
         { const double r_ = radius, f_ = decrease_factor; __syncwarp(); radius = r_ / f_; decrease_factor = f_ * 2.0; } reuse_diagonal = true;
         continue;
       }
       invalid = 0;
+      mcc = mcc_l; // every lane writes the same value, once per iteration; read after the evaluation's barriers
       {
         double snl = 0;
         double xr[6], delta[4], cand[6];
