@@ -318,6 +318,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lm", action="store_true", help="skip the lm_ba / remerge / jlinkage / sweep500 legs")
     ap.add_argument("--groups", type=int, default=8, help="pipeline groups of the e2e path (upload/run overlap)")
+    ap.add_argument("--value-groups", type=int, default=1,
+                    help="pipeline groups of the device-resident leg (1: the node kernel runs alone and is timed cleanly for the "
+                         "roofline; >1 hides the row preparation of group g+1 under the node kernel of group g)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -386,6 +389,7 @@ def main():
     for i in my_ids:
         eng.add_image_matches(i, *flat[i])
     eng.set_shard(per * rank, per * (rank + 1))
+    eng.set_pipeline_groups(args.value_groups)
     gather = lmdist.NodeGather(eng, world, rank) if world > 1 else None
 
     def step():
@@ -572,7 +576,7 @@ def main():
                            "pairs": {"past_3d_gates": int(st["n_pairs_gated"]), "scored_exact_fp64": int(st["n_pairs_exact"])},
                            "parallelism": f"source-image shards x{world}"
                                           + (", one all-gather of node records + valid connections per step" if world > 1 else ""),
-                           "host_cpus_bound_rank0": numa,
+                           "host_cpus_bound_rank0": numa, "pipeline_groups_resident_leg": args.value_groups,
                            "l2": "inputs larger than L2 (match rows + sort buffers > 126 MB per step)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "parity": parity}
