@@ -20,12 +20,17 @@ class SfmImage:
 
     def __init__(self, filename, width, height, K, R, T):
         self.filename, self.width, self.height = filename, int(width), int(height)
-        self.K = np.asarray(K, np.float64).reshape(3, 3)
-        self.R = np.asarray(R, np.float64).reshape(3, 3)
-        self.T = np.asarray(T, np.float64).reshape(3)
+        # colmap::mvs::Image keeps K, R, T as float (CreateSfmImage converts the doubles it is given)
+        self.K = np.asarray(K, np.float64).reshape(3, 3).astype(np.float32)
+        self.R = np.asarray(R, np.float64).reshape(3, 3).astype(np.float32)
+        self.T = np.asarray(T, np.float64).reshape(3).astype(np.float32)
 
     def centre(self):
-        return -self.R.T @ self.T
+        """Projection centre as colmap::mvs::Model::ComputeTriangulationAngles uses it: C = -R^T T evaluated in float
+        (ComputeProjectionCenter), widened to double."""
+        R, T = self.R, self.T
+        c = [-((R[0, i] * T[0] + R[1, i] * T[1]) + R[2, i] * T[2]) for i in range(3)]
+        return np.asarray(c, np.float32).astype(np.float64)
 
 
 def CreateSfmImage(filename, width, height, K, R, T):
@@ -51,7 +56,8 @@ class SfmModel:
             self.reg_image_ids.append(int(img_id))
 
     def addPoint(self, x, y, z, image_ids):  # sfm_model.cc:25-33 (image_ids are image INDICES, as in the readers)
-        self._xyz.append((float(x), float(y), float(z)))
+        # colmap::mvs::Model::Point keeps float coordinates: the triangulation angles and ranges see the rounded values
+        self._xyz.append((float(np.float32(x)), float(np.float32(y)), float(np.float32(z))))
         self._tracks.append(np.asarray(image_ids, np.int32).reshape(-1))
 
     def GetImageNames(self):

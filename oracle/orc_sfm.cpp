@@ -1,4 +1,8 @@
-// oracle/orc_sfm.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE. PARITY UNPINNED for the COLMAP part.
+// oracle/orc_sfm.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE. The limap part (ranking loops, score formulas, ComputeRanges)
+// is PINNED to the reference's compiled pointsfm/sfm_model.cc (oracle/_ref, tests/test_ref_pinning.py::
+// test_sfm_model_neighbour_ranking_and_ranges); PARITY UNPINNED for the COLMAP part underneath it. The reference sorts with
+// std::sort / std::partial_sort (unstable): among EQUAL scores its order is unspecified; this restatement keeps ascending
+// image index (a stable sort over the std::map order).
 //
 // Visual-neighbour ranking and robust ranges of limap::pointsfm::SfmModel:
 //   GetMaxIoUImages / GetMaxDiceCoeffImages   pointsfm/sfm_model.cc:101-162, 164-226

@@ -83,6 +83,8 @@ def lib():
         L.ref_track_support_flags.argtypes = [C.c_int32, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P] + [C.c_double] * 4 + [_P]
         L.ref_geometric_residual.argtypes = [C.c_int, _P, _P, _P, _P, _P, C.c_double, _P, _P]
         L.ref_vp_residual.argtypes = [C.c_int, _P, _P, _P, _P, _P, _P]
+        L.ref_sfm_rank_neighbors.argtypes = [C.c_int, _P, _P, C.c_int64, _P, _P, _P, C.c_int, C.c_double, C.c_int, _P, _P]
+        L.ref_sfm_robust_ranges.argtypes = [C.c_int64, _P, C.c_double, C.c_double, C.c_double, _P]
         L.ref_remerge_groups.restype = C.c_int64
         L.ref_remerge_groups.argtypes = [C.c_int64, _P, _P, _P, _P]
         _lib = L
@@ -142,3 +144,39 @@ def remerge_groups(track_line, active, linker):
     group = np.arange(len(track_line), dtype=np.int32)
     n = lib().ref_remerge_groups(len(track_line), _p(track_line), _p(active), C.byref(cfg), _p(group))
     return group, int(n)
+
+
+def colmap_float_centres(R, T):
+    """Projection centres as colmap::mvs::Model::ComputeTriangulationAngles derives them from an image built by
+    CreateSfmImage: R and T rounded to float, C = -R^T T evaluated in float, widened to double."""
+    R = np.asarray(R, np.float64).reshape(-1, 3, 3).astype(np.float32)
+    T = np.asarray(T, np.float64).reshape(-1, 3).astype(np.float32)
+    c = np.empty((len(R), 3), np.float32)
+    for i in range(3):
+        c[:, i] = -((R[:, 0, i] * T[:, 0] + R[:, 1, i] * T[:, 1]) + R[:, 2, i] * T[:, 2])
+    return c.astype(np.float64)
+
+
+def sfm_rank_neighbors(R, T, xyz, track_off, track_img, num_images, min_triangulation_angle=1.0, mode=0):
+    """limap::pointsfm::SfmModel::{GetMaxIoUImages, GetMaxDiceCoeffImages, GetMaxOverlapImages} of the reference's compiled
+    sfm_model.cc (COLMAP's mvs::Model statistics come from oracle/ref_shim)."""
+    L = lib()
+    R = np.ascontiguousarray(np.asarray(R, np.float64).reshape(-1, 9))
+    T = np.ascontiguousarray(np.asarray(T, np.float64).reshape(-1, 3))
+    xyz = np.ascontiguousarray(xyz, np.float64)
+    track_off = np.ascontiguousarray(track_off, np.int64)
+    track_img = np.ascontiguousarray(track_img, np.int32)
+    n = len(R)
+    out = np.full((n, int(num_images)), -1, np.int32)
+    cnt = np.zeros(n, np.int32)
+    L.ref_sfm_rank_neighbors(n, _p(R), _p(T), len(xyz), _p(xyz), _p(track_off), _p(track_img), int(num_images),
+                             float(min_triangulation_angle), int(mode), _p(out), _p(cnt))
+    return out, cnt
+
+
+def sfm_robust_ranges(xyz, q_lo, q_hi, kstretch):
+    L = lib()
+    xyz = np.ascontiguousarray(xyz, np.float64)
+    out = np.zeros(6)
+    L.ref_sfm_robust_ranges(len(xyz), _p(xyz), float(q_lo), float(q_hi), float(kstretch), _p(out))
+    return out[:3].copy(), out[3:].copy()

@@ -9,7 +9,10 @@
 //   MinimalInfiniteLine3d, GetLineSegmentFromInfiniteLine3d, CheckReprojection / CheckSensitivity / overlap,
 //   RemergeLineTracks,
 //   optimize/line_refinement/cost_functions.h: GeometricRefinementFunctor / VPConstraintsFunctor evaluated on
-//   ceres::Jet<double, 6> (oracle/ref_shim/ceres: Jet arithmetic restated; the functors are the reference's).
+//   ceres::Jet<double, 6> (oracle/ref_shim/ceres: Jet arithmetic restated; the functors are the reference's),
+//   pointsfm/sfm_model.cc: SfmModel::{GetMaxIoUImages, GetMaxDiceCoeffImages, GetMaxOverlapImages, ComputeRanges} on top
+//   of oracle/ref_shim/colmap/mvs (COLMAP's shared-point / triangulation-angle statistics restated; the ranking loops,
+//   score formulas, sorts and the float range arithmetic are the reference's).
 // Nothing of the product links or loads this library.
 // every standard / third-party header first, with its own access specifiers intact ...
 #include <algorithm>
@@ -47,6 +50,7 @@
 #include "limap/merging/merging.h"
 #include "limap/merging/merging_utils.h"
 #include "limap/optimize/line_refinement/cost_functions.h"
+#include "limap/pointsfm/sfm_model.h"
 #include "limap/triangulation/functions.h"
 #include "limap/triangulation/global_line_triangulator.h"
 #undef private
@@ -504,3 +508,37 @@ void ref_vp_residual(int model, const double *x, const double *vp, const double 
 }
 }
 
+// limap::pointsfm::SfmModel built the way pointsfm/colmap_reader.py builds it (CreateSfmImage + addImage(-1) + addPoint),
+// then one of its neighbour rankings: mode 0 GetMaxIoUImages, 1 GetMaxDiceCoeffImages, 2 GetMaxOverlapImages.
+// out[n_images][num_images] (-1 padded), out_count[n_images]. R row-major 3x3 per image, T 3 per image.
+extern "C" {
+int ref_sfm_rank_neighbors(int n_images, const double *R, const double *T, int64_t n_points, const double *xyz,
+                           const int64_t *track_off, const int32_t *track_img, int num_images,
+                           double min_triangulation_angle_deg, int mode, int32_t *out, int32_t *out_count) {
+  pointsfm::SfmModel model;
+  const std::vector<double> K = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < n_images; ++i)
+    model.addImage(pointsfm::CreateSfmImage("img_" + std::to_string(i), 800, 600, K, std::vector<double>(R + 9 * i, R + 9 * i + 9),
+                                            std::vector<double>(T + 3 * i, T + 3 * i + 3)),
+                   -1);
+  for (int64_t p = 0; p < n_points; ++p)
+    model.addPoint(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2],
+                   std::vector<int>(track_img + track_off[p], track_img + track_off[p + 1]));
+  std::map<int, std::vector<int>> nb;
+  if (mode == 0) nb = model.GetMaxIoUImages((size_t)num_images, min_triangulation_angle_deg);
+  else if (mode == 1) nb = model.GetMaxDiceCoeffImages((size_t)num_images, min_triangulation_angle_deg);
+  else nb = model.GetMaxOverlapImages((size_t)num_images, min_triangulation_angle_deg);
+  for (int i = 0; i < n_images; ++i) {
+    const std::vector<int> &v = nb.at(i);
+    out_count[i] = (int32_t)v.size();
+    for (int k = 0; k < num_images; ++k) out[(int64_t)i * num_images + k] = k < (int)v.size() ? v[k] : -1;
+  }
+  return 0;
+}
+void ref_sfm_robust_ranges(int64_t n_points, const double *xyz, double q_lo, double q_hi, double kstretch, double *out6) {
+  pointsfm::SfmModel model;
+  for (int64_t p = 0; p < n_points; ++p) model.addPoint(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], std::vector<int>());
+  const std::pair<V3D, V3D> r = model.ComputeRanges(std::make_pair(q_lo, q_hi), kstretch);
+  for (int k = 0; k < 3; ++k) { out6[k] = r.first[k]; out6[3 + k] = r.second[k]; }
+}
+}

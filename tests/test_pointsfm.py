@@ -49,7 +49,10 @@ def test_neighbor_ranking_matches_oracle(ntype, mode):
     m = _model(sc, centres, xyz, off, img)
     for n_nb, ang in ((20, 1.0), (5, 8.0)):
         got = pointsfm.compute_neighbors(m, n_nb, min_triangulation_angle=ang, neighbor_type=ntype)
-        exp, cnt = orc.rank_neighbors(centres, xyz, off, img, n_nb, min_triangulation_angle=ang, mode=mode)
+        # the model keeps float poses and points like colmap::mvs::Model: the oracle gets what the model holds
+        c_m = np.stack([im.centre() for im in m.images])
+        xyz_m = m._arrays()[0]
+        exp, cnt = orc.rank_neighbors(c_m, xyz_m, off, img, n_nb, min_triangulation_angle=ang, mode=mode)
         ids = sc.img_ids
         assert sorted(got) == [int(i) for i in ids]
         n_total = 0

@@ -356,3 +356,47 @@ def test_golden_fixtures_are_reproduced_by_the_compiled_reference():
         r = ref.RefTri(cfg, threads=1)
         g._feed(r, z)
         g._check_tri(r, z)
+
+
+def test_sfm_model_neighbour_ranking_and_ranges():
+    """f4: the reference's compiled pointsfm/sfm_model.cc (ranking loops, IoU / Dice formulas, sorts, ComputeRanges float
+    arithmetic; COLMAP's mvs::Model statistics restated in oracle/ref_shim) against the oracle restatement the CUDA path
+    is tested with. The reference orders equal scores with an UNSTABLE sort, the restatement keeps ascending image index:
+    lists are compared exactly where the scores are distinct and by score sequence where they tie."""
+    from limap_b200.base import CameraPose
+    from limap_b200.synth import make_scene, make_sfm_points
+    for seed, V, n_pts in ((71, 30, 4000), (72, 12, 300)):
+        sc = make_scene(V=V, L=10, N=3, K=1, seed=seed)
+        _, xyz, off, img = make_sfm_points(sc, n_points=n_pts, seed=seed)
+        R = np.stack([CameraPose(sc.qvec[v], sc.tvec[v]).R() for v in range(V)])
+        T = sc.tvec
+        centres = ref.colmap_float_centres(R, T)
+        xyz32 = xyz.astype(np.float32).astype(np.float64)  # Model::Point keeps float coordinates
+        # scores per (i, j) for the tie analysis
+        shared = np.zeros((V, V), np.int64)
+        npts = np.bincount(img, minlength=V)
+        for p in range(len(off) - 1):
+            t = img[off[p]:off[p + 1]]
+            shared[np.ix_(t, t)] += 1
+        np.fill_diagonal(shared, 0)
+        for mode in (0, 1, 2):
+            union = npts[:, None] + npts[None, :] - shared
+            score = (shared / np.maximum(union, 1), 2 * shared / np.maximum(union + shared, 1), shared.astype(float))[mode]
+            for n_nb, ang in ((8, 1.0), (100, 0.5), (3, 6.0)):
+                a, ca = orc.rank_neighbors(centres, xyz32, off, img, n_nb, min_triangulation_angle=ang, mode=mode)
+                b, cb = ref.sfm_rank_neighbors(R, T, xyz, off, img, n_nb, min_triangulation_angle=ang, mode=mode)
+                assert np.array_equal(ca, cb), (seed, mode, n_nb, ang)
+                n_exact = 0
+                for i in range(V):
+                    la, lb = a[i, :ca[i]], b[i, :cb[i]]
+                    sa, sb = score[i, la], score[i, lb]
+                    assert np.array_equal(sa, sb), (seed, mode, n_nb, ang, i)  # same scores in the same order
+                    row = score[i, shared[i] > 0]
+                    if all((row == v).sum() == 1 for v in sa):  # no listed score ties with any other co-visible image
+                        assert np.array_equal(la, lb), (seed, mode, n_nb, ang, i)
+                        n_exact += 1
+                assert n_exact > 0 or mode == 2
+        for q in ((0.05, 0.95, 1.25), (0.0, 0.999, 0.5), (0.25, 0.5, 2.0)):
+            lo_a, hi_a = orc.robust_ranges(xyz, *q)
+            lo_b, hi_b = ref.sfm_robust_ranges(xyz, *q)
+            assert np.array_equal(lo_a, lo_b) and np.array_equal(hi_a, hi_b), q  # float arithmetic, bit for bit
