@@ -1,4 +1,4 @@
-// oracle/orc_vp.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE. PARITY UNPINNED (see orc_vp.h).
+// oracle/orc_vp.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE. Pinning status: see orc_vp.h (wrapper pinned, library core unpinned).
 // Built with -ffp-contract=off so the float arithmetic of the consensus test matches the GPU kernel bit for bit.
 #include <array>
 #include "orc_vp.h"

@@ -1,4 +1,6 @@
-// oracle/orc_vp.h — TEST INFRASTRUCTURE, NOT PRODUCT CODE. PARITY UNPINNED (see orc_geom.h), doubly so here:
+// oracle/orc_vp.h — TEST INFRASTRUCTURE, NOT PRODUCT CODE. The reference-side wrapper (length filter, cluster filtering,
+// label renumbering, VP fit) is PINNED to the reference's compiled vplib/JLinkage/JLinkage.cc + base_vp_detector.cc
+// (oracle/_ref over oracle/ref_shim/JLinkage, tests/test_ref_pinning.py). The library core is PARITY UNPINNED:
 // the J-Linkage arithmetic lives in a third-party library that is NOT under /root/reference
 // (B1ueber2y/JLinkage @ 75dadd555f81b1cf1b0f016d8cac76f3b554ba9b, cmake/FindDependencies.cmake:73-77) and
 // draws its 5000 minimal samples from an unseeded RNG, so not even the reference reproduces itself.

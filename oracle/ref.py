@@ -85,6 +85,9 @@ def lib():
         L.ref_vp_residual.argtypes = [C.c_int, _P, _P, _P, _P, _P, _P]
         L.ref_sfm_rank_neighbors.argtypes = [C.c_int, _P, _P, C.c_int64, _P, _P, _P, C.c_int, C.c_double, C.c_int, _P, _P]
         L.ref_sfm_robust_ranges.argtypes = [C.c_int64, _P, C.c_double, C.c_double, C.c_double, _P]
+        L.ref_vp_set_context.argtypes = [C.c_uint64, C.c_uint64]
+        L.ref_vp_associate.restype = C.c_longlong
+        L.ref_vp_associate.argtypes = [C.c_int64, _P, C.c_double, C.c_double, C.c_int, C.c_double, _P, _P, C.c_longlong]
         L.ref_remerge_groups.restype = C.c_int64
         L.ref_remerge_groups.argtypes = [C.c_int64, _P, _P, _P, _P]
         _lib = L
@@ -180,3 +183,17 @@ def sfm_robust_ranges(xyz, q_lo, q_hi, kstretch):
     out = np.zeros(6)
     L.ref_sfm_robust_ranges(len(xyz), _p(xyz), float(q_lo), float(q_hi), float(kstretch), _p(out))
     return out[:3].copy(), out[3:].copy()
+
+
+def vp_associate(segs, seed=0, image_index=0, min_length=40.0, inlier_threshold=1.0, min_num_supports=5,
+                 th_perp_supports=3.0):
+    """vplib::JLinkage::JLinkage::AssociateVPs of the reference's compiled wrapper for ONE image (5000 hypotheses, as the
+    wrapper hard-codes); the JLinkage library underneath it is the oracle's restatement, seeded by (seed, image_index)."""
+    L = lib()
+    segs = np.ascontiguousarray(segs, np.float64).reshape(-1, 4)
+    labels = np.full(len(segs), -1, np.int32)
+    vps = np.zeros((64, 3))
+    L.ref_vp_set_context(int(seed), int(image_index))
+    n = L.ref_vp_associate(len(segs), _p(segs), float(min_length), float(inlier_threshold), int(min_num_supports),
+                           float(th_perp_supports), _p(labels), _p(vps), 64)
+    return labels, vps[:n]

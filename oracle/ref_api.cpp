@@ -10,6 +10,8 @@
 //   RemergeLineTracks,
 //   optimize/line_refinement/cost_functions.h: GeometricRefinementFunctor / VPConstraintsFunctor evaluated on
 //   ceres::Jet<double, 6> (oracle/ref_shim/ceres: Jet arithmetic restated; the functors are the reference's),
+//   vplib/JLinkage/JLinkage.cc + vplib/base_vp_detector.cc: limap's J-Linkage wrapper over oracle/ref_shim/JLinkage (the
+//   library's sampling / clustering forward to the restatement in orc_vp.h),
 //   pointsfm/sfm_model.cc: SfmModel::{GetMaxIoUImages, GetMaxDiceCoeffImages, GetMaxOverlapImages, ComputeRanges} on top
 //   of oracle/ref_shim/colmap/mvs (COLMAP's shared-point / triangulation-angle statistics restated; the ranking loops,
 //   score formulas, sorts and the float range arithmetic are the reference's).
@@ -51,10 +53,12 @@
 #include "limap/merging/merging_utils.h"
 #include "limap/optimize/line_refinement/cost_functions.h"
 #include "limap/pointsfm/sfm_model.h"
+#include "limap/vplib/JLinkage/JLinkage.h"
 #include "limap/triangulation/functions.h"
 #include "limap/triangulation/global_line_triangulator.h"
 #undef private
 #undef protected
+#include "orc_vp.h" // the J-Linkage core the JLinkage-library shim forwards to (namespace orc)
 #include <cstring>
 #include <memory>
 #ifdef _OPENMP
@@ -540,5 +544,63 @@ void ref_sfm_robust_ranges(int64_t n_points, const double *xyz, double q_lo, dou
   for (int64_t p = 0; p < n_points; ++p) model.addPoint(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], std::vector<int>());
   const std::pair<V3D, V3D> r = model.ComputeRanges(std::make_pair(q_lo, q_hi), kstretch);
   for (int k = 0; k < 3; ++k) { out6[k] = r.first[k]; out6[3 + k] = r.second[k]; }
+}
+}
+
+// ---- the JLinkage-library shim (oracle/ref_shim/JLinkage/include): VPSample::run only records the model count, VPCluster::run
+// runs the restated J-Linkage (orc::jlinkage_cluster) with the seed / image index set by ref_vp_set_context -------------------
+namespace {
+thread_local uint64_t g_vp_seed = 0, g_vp_image_index = 0;
+thread_local int g_vp_models = 5000;
+} // namespace
+namespace VPSample {
+std::vector<std::vector<float> *> *run(std::vector<std::vector<float> *> *, int num_models, int, int, int) {
+  g_vp_models = num_models;
+  return new std::vector<std::vector<float> *>();
+}
+} // namespace VPSample
+namespace VPCluster {
+int run(std::vector<unsigned int> &labels, std::vector<unsigned int> &label_count, std::vector<std::vector<float> *> *pts,
+        std::vector<std::vector<float> *> *, float inlier_threshold, int) {
+  std::vector<std::array<float, 4>> p(pts->size());
+  for (size_t i = 0; i < pts->size(); ++i)
+    for (int k = 0; k < 4; ++k) p[i][k] = (*(*pts)[i])[k];
+  orc::VPConfig cfg;
+  cfg.inlier_threshold = inlier_threshold;
+  cfg.n_models = g_vp_models;
+  cfg.seed = g_vp_seed;
+  std::vector<int> lab;
+  const int nc = orc::jlinkage_cluster(p, cfg, g_vp_image_index, lab);
+  labels.assign(lab.begin(), lab.end());
+  label_count.assign((size_t)nc, 0u);
+  for (int l : lab)
+    if (l >= 0) label_count[(size_t)l] += 1;
+  return nc;
+}
+} // namespace VPCluster
+
+extern "C" {
+void ref_vp_set_context(uint64_t seed, uint64_t image_index) { g_vp_seed = seed; g_vp_image_index = image_index; }
+// vplib::JLinkage::JLinkage(config).AssociateVPs(lines) of the reference's compiled wrapper. Returns the number of VPs
+// (may exceed cap); labels[n_lines], vps[cap][3].
+long long ref_vp_associate(int64_t n_lines, const double *segs, double min_length, double inlier_threshold, int min_num_supports,
+                           double th_perp_supports, int32_t *labels, double *vps, long long cap) {
+  vplib::JLinkage::JLinkageConfig cfg;
+  cfg.min_length = min_length;
+  cfg.inlier_threshold = inlier_threshold;
+  cfg.min_num_supports = min_num_supports;
+  cfg.th_perp_supports = th_perp_supports;
+  vplib::JLinkage::JLinkage det(cfg);
+  std::vector<Line2d> lines;
+  for (int64_t l = 0; l < n_lines; ++l)
+    lines.push_back(Line2d(V2D(segs[4 * l], segs[4 * l + 1]), V2D(segs[4 * l + 2], segs[4 * l + 3])));
+  const vplib::VPResult r = det.AssociateVPs(lines);
+  for (int64_t l = 0; l < n_lines && l < (int64_t)r.labels.size(); ++l) labels[l] = r.labels[l];
+  long long n = 0;
+  for (const V3D &v : r.vps) {
+    if (n < cap) { vps[3 * n] = v[0]; vps[3 * n + 1] = v[1]; vps[3 * n + 2] = v[2]; }
+    ++n;
+  }
+  return n;
 }
 }

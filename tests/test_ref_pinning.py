@@ -400,3 +400,26 @@ def test_sfm_model_neighbour_ranking_and_ranges():
             lo_a, hi_a = orc.robust_ranges(xyz, *q)
             lo_b, hi_b = ref.sfm_robust_ranges(xyz, *q)
             assert np.array_equal(lo_a, lo_b) and np.array_equal(hi_a, hi_b), q  # float arithmetic, bit for bit
+
+
+def test_jlinkage_wrapper_filtering_renumbering_and_vp_fit():
+    """a18: limap's own J-Linkage wrapper (vplib/JLinkage/JLinkage.cc + base_vp_detector.cc: min_length filter, the 2 x
+    max(min_num_supports, 10) guard, cluster filtering with count_valid_supports_2d, label renumbering, VP = last right
+    singular vector of the stacked line coordinates) compiled unchanged, over a JLinkage-library shim that forwards the
+    sampling / clustering to the restated core -- against the restatement of the same wrapper in oracle/orc_vp.h.
+    (The JLinkage library itself is an absent submodule: its core stays restated)"""
+    from limap_b200.synth import make_vp_images
+    imgs = make_vp_images(6, 120, seed=81) + make_vp_images(2, 25, seed=82) + [np.zeros((0, 4))]
+    n_vp_total = 0
+    for idx, segs in enumerate(imgs):
+        segs = np.ascontiguousarray(segs, np.float64).reshape(-1, 4)
+        for kw in (dict(), dict(min_length=20.0, min_num_supports=8, th_perp_supports=1.0), dict(inlier_threshold=2.5)):
+            la, va = ref.vp_associate(segs, seed=7, image_index=idx, **kw)
+            off = np.array([0, len(segs)], np.int64)
+            lb, _, vb = orc.detect_vps(off, segs, n_models=5000, seed=7, image_index=[idx], threads=1, **kw)
+            assert np.array_equal(la, lb), (idx, kw)
+            assert len(va) == len(vb)
+            for a, b in zip(va, vb):
+                assert min(np.abs(a - b).max(), np.abs(a + b).max()) < 1e-7, (idx, kw, a, b)  # sign of a singular vector
+            n_vp_total += len(va)
+    assert n_vp_total >= 10
