@@ -88,6 +88,10 @@ def lib():
         L.ref_vp_set_context.argtypes = [C.c_uint64, C.c_uint64]
         L.ref_vp_associate.restype = C.c_longlong
         L.ref_vp_associate.argtypes = [C.c_int64, _P, C.c_double, C.c_double, C.c_int, C.c_double, _P, _P, C.c_longlong]
+        L.ref_linetrack_write.argtypes = [C.c_char_p, _P, C.c_int64, _P, _P, _P, _P, _P, _P]
+        L.ref_linetrack_read.restype = C.c_int64
+        L.ref_linetrack_read.argtypes = [C.c_char_p, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P]
+        L.ref_line_weights.argtypes = [C.c_int64, _P, _P]
         L.ref_remerge_groups.restype = C.c_int64
         L.ref_remerge_groups.argtypes = [C.c_int64, _P, _P, _P, _P]
         _lib = L

@@ -604,3 +604,53 @@ long long ref_vp_associate(int64_t n_lines, const double *segs, double min_lengt
   return n;
 }
 }
+
+// LineTrack::Write / LineTrack::Read (base/linetrack.cc:133-270) and ComputeLineWeights (:315-322) of the reference's
+// compiled code, on flat arrays: line[6]; per supporting line image id, line id, node id, score, line2d[4], line3d[6].
+extern "C" {
+int ref_linetrack_write(const char *path, const double *line, int64_t n, const int32_t *img, const int32_t *lid,
+                        const int32_t *node, const double *score, const double *l2d, const double *l3d) {
+  LineTrack t;
+  t.line = Line3d(V3D(line[0], line[1], line[2]), V3D(line[3], line[4], line[5]));
+  for (int64_t i = 0; i < n; ++i) {
+    t.image_id_list.push_back(img[i]);
+    t.line_id_list.push_back(lid[i]);
+    if (node) t.node_id_list.push_back(node[i]);
+    if (score) t.score_list.push_back(score[i]);
+    t.line2d_list.push_back(Line2d(V2D(l2d[4 * i], l2d[4 * i + 1]), V2D(l2d[4 * i + 2], l2d[4 * i + 3])));
+    if (l3d) t.line3d_list.push_back(Line3d(V3D(l3d[6 * i], l3d[6 * i + 1], l3d[6 * i + 2]), V3D(l3d[6 * i + 3], l3d[6 * i + 4], l3d[6 * i + 5])));
+  }
+  t.Write(std::string(path));
+  return 0;
+}
+// returns the number of supporting lines (arrays sized by the caller: cap entries), -1 when cap is too small
+int64_t ref_linetrack_read(const char *path, int64_t cap, double *line, int32_t *img, int32_t *lid, int32_t *node, double *score,
+                           double *l2d, double *l3d, int32_t *n_images) {
+  LineTrack t;
+  t.Read(std::string(path));
+  const int64_t n = (int64_t)t.count_lines();
+  if (n > cap) return -1;
+  for (int k = 0; k < 3; ++k) { line[k] = t.line.start[k]; line[3 + k] = t.line.end[k]; }
+  for (int64_t i = 0; i < n; ++i) {
+    img[i] = t.image_id_list[i];
+    lid[i] = t.line_id_list[i];
+    node[i] = i < (int64_t)t.node_id_list.size() ? t.node_id_list[i] : -1;
+    score[i] = i < (int64_t)t.score_list.size() ? t.score_list[i] : 0.0;
+    for (int k = 0; k < 2; ++k) { l2d[4 * i + k] = t.line2d_list[i].start[k]; l2d[4 * i + 2 + k] = t.line2d_list[i].end[k]; }
+    if (i < (int64_t)t.line3d_list.size())
+      for (int k = 0; k < 3; ++k) { l3d[6 * i + k] = t.line3d_list[i].start[k]; l3d[6 * i + 3 + k] = t.line3d_list[i].end[k]; }
+  }
+  *n_images = (int32_t)t.count_images();
+  return n;
+}
+void ref_line_weights(int64_t n, const double *l2d, double *out) {
+  LineTrack t;
+  for (int64_t i = 0; i < n; ++i)
+    t.line2d_list.push_back(Line2d(V2D(l2d[4 * i], l2d[4 * i + 1]), V2D(l2d[4 * i + 2], l2d[4 * i + 3])));
+  t.image_id_list.assign((size_t)n, 0);
+  t.line_id_list.assign((size_t)n, 0);
+  std::vector<double> w;
+  ComputeLineWeights(t, w);
+  for (int64_t i = 0; i < n; ++i) out[i] = w[(size_t)i];
+}
+}

@@ -423,3 +423,60 @@ def test_jlinkage_wrapper_filtering_renumbering_and_vp_fit():
                 assert min(np.abs(a - b).max(), np.abs(a + b).max()) < 1e-7, (idx, kw, a, b)  # sign of a singular vector
             n_vp_total += len(va)
     assert n_vp_total >= 10
+
+
+def test_linetrack_file_format_and_line_weights(tmp_path):
+    """a19: LineTrack::Write / LineTrack::Read of the reference's compiled base/linetrack.cc against the Python mirror
+    (limap_b200.base.LineTrack): each side reads the other's file and the mirror's writer reproduces the reference's
+    bytes; ComputeLineWeights (the loss weight of a supporting line in the refinement) = length / 30."""
+    import limap.base as base
+    rng = np.random.default_rng(91)
+    L = ref.lib()
+    p = orc._p
+    for case in range(6):
+        n = int(rng.integers(1, 9))
+        line = rng.normal(size=6) * 3
+        if case == 4:
+            line[1] = np.nan  # written as 0 (linetrack.cc:137-152)
+        img = rng.integers(0, 5, n).astype(np.int32)
+        lid = rng.integers(0, 400, n).astype(np.int32)
+        node = rng.integers(0, 10 ** 6, n).astype(np.int32)
+        score = rng.uniform(0, 5, n)
+        l2d = rng.uniform(0, 800, (n, 4))
+        l3d = rng.normal(size=(n, 6)) * 2
+        aux = case != 5  # case 5: a track without node ids / scores / 3D lines
+        f_ref = str(tmp_path / f"ref_{case}.txt").encode()
+        L.ref_linetrack_write(f_ref, p(line), n, p(img), p(lid), p(node) if aux else None, p(score) if aux else None, p(l2d),
+                              p(l3d) if aux else None)
+        t = base.LineTrack()
+        t.line = base.Line3d(line[:3], line[3:])
+        t.image_id_list, t.line_id_list = img.tolist(), lid.tolist()
+        t.line2d_list = [base.Line2d(r[:2], r[2:]) for r in l2d]
+        if aux:
+            t.node_id_list, t.score_list = node.tolist(), score.tolist()
+            t.line3d_list = [base.Line3d(r[:3], r[3:]) for r in l3d]
+        f_py = str(tmp_path / f"py_{case}.txt")
+        t.Write(f_py)
+        assert open(f_py, "rb").read() == open(f_ref.decode(), "rb").read(), case  # byte for byte
+        # the mirror reads the reference's file
+        t2 = base.LineTrack()
+        t2.Read(f_ref.decode())
+        assert t2.image_id_list == img.tolist() and t2.line_id_list == lid.tolist() and t2.count_images() == len(set(img))
+        assert np.allclose([np.concatenate([l.start, l.end]) for l in t2.line2d_list], l2d, atol=1e-9)
+        if aux:
+            assert t2.node_id_list == node.tolist() and np.allclose(t2.score_list, score, atol=1e-9)
+            assert np.allclose([np.concatenate([l.start, l.end]) for l in t2.line3d_list], l3d, atol=1e-9)
+        # the reference reads the mirror's file
+        o_line, o_img, o_lid, o_node = np.zeros(6), np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        o_score, o_l2d, o_l3d, o_ni = np.zeros(n), np.zeros((n, 4)), np.zeros((n, 6)), np.zeros(1, np.int32)
+        got = L.ref_linetrack_read(f_py.encode(), n, p(o_line), p(o_img), p(o_lid), p(o_node), p(o_score), p(o_l2d), p(o_l3d),
+                                   p(o_ni))
+        assert got == n and np.array_equal(o_img, img) and np.array_equal(o_lid, lid) and o_ni[0] == len(set(img))
+        assert np.allclose(o_line, np.nan_to_num(line), atol=1e-9) and np.allclose(o_l2d, l2d, atol=1e-9)
+        if aux:
+            assert np.array_equal(o_node, node) and np.allclose(o_score, score, atol=1e-9) and np.allclose(o_l3d, l3d, atol=1e-9)
+    segs = rng.uniform(0, 800, (200, 4))
+    w = np.zeros(200)
+    L.ref_line_weights(200, p(segs), p(w))
+    dx, dy = segs[:, 2] - segs[:, 0], segs[:, 3] - segs[:, 1]
+    assert np.allclose(w, np.sqrt(dx * dx + dy * dy) / 30.0, rtol=1e-15, atol=0)
