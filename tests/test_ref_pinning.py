@@ -480,3 +480,53 @@ def test_linetrack_file_format_and_line_weights(tmp_path):
     L.ref_line_weights(200, p(segs), p(w))
     dx, dy = segs[:, 2] - segs[:, 0], segs[:, 3] - segs[:, 1]
     assert np.allclose(w, np.sqrt(dx * dx + dy * dy) / 30.0, rtol=1e-15, atol=0)
+
+
+def test_python_value_types_against_compiled_reference():
+    """a1 / a19: the Python value types of the mirror (limap_b200.base: Camera, CameraPose, CameraView, Line2d, Line3d) --
+    the objects a runner handles -- against the reference's compiled base/{camera,pose,camera_view,linebase}.cc:
+    projection, ray_direction, Line2d length / direction, Line3d sensitivity and uncertainty."""
+    import limap.base as base
+    rng = np.random.default_rng(92)
+    L = ref.lib()
+    L.ref_project_point.argtypes = [C.c_void_p] * 3
+    L.ref_ray_direction.argtypes = [C.c_void_p] * 3
+    L.ref_line2d_length.restype = C.c_double
+    L.ref_line2d_length.argtypes = [C.c_void_p]
+    L.ref_line2d_direction.argtypes = [C.c_void_p] * 2
+    L.ref_line3d_sensitivity.restype = C.c_double
+    L.ref_line3d_sensitivity.argtypes = [C.c_void_p] * 2
+    L.ref_line3d_uncertainty.restype = C.c_double
+    L.ref_line3d_uncertainty.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+    p = orc._p
+    for it in range(3000):
+        model = it & 1
+        f = rng.uniform(300, 900)
+        fy = f if model == 0 else f * rng.uniform(0.9, 1.1)
+        cx, cy = rng.uniform(300, 400), rng.uniform(200, 300)
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        t = rng.normal(size=3) * 3
+        cam_arr = np.array([model, f, fy, cx, cy, *q, *t])
+        cam = base.Camera("SIMPLE_PINHOLE", [f, cx, cy], 0, (600, 800)) if model == 0 else \
+            base.Camera("PINHOLE", [f, fy, cx, cy], 0, (600, 800))
+        view = base.CameraView(cam, base.CameraPose(q, t))
+        X = rng.normal(size=3) * 2 + view.pose.center() + view.R().T @ np.array([0, 0, 6.0])
+        a, b = np.zeros(2), np.zeros(2)
+        L.ref_project_point(p(cam_arr), p(X), p(b))
+        a = np.asarray(view.projection(X))
+        assert np.abs(a - b).max() <= 1e-9 * max(1.0, np.abs(b).max()), (it, a, b)
+        px = rng.uniform(0, 700, 2)
+        r_ref = np.zeros(3)
+        L.ref_ray_direction(p(cam_arr), p(px), p(r_ref))
+        assert np.abs(np.asarray(view.ray_direction(px)) - r_ref).max() <= 1e-12
+        seg = rng.uniform(0, 700, 4)
+        l2 = base.Line2d(seg[:2], seg[2:])
+        d_ref = np.zeros(2)
+        L.ref_line2d_direction(p(seg), p(d_ref))
+        assert abs(l2.length() - L.ref_line2d_length(p(seg))) <= 1e-12 and np.abs(np.asarray(l2.direction()) - d_ref).max() <= 1e-12
+        Y = rng.normal(size=3) * 2 + view.pose.center() + view.R().T @ np.array([0, 0, 7.0])
+        l3_arr = np.array([*X, *Y, view.pose.projdepth(X), view.pose.projdepth(Y), 0.1])
+        l3 = base.Line3d(X, Y, 1.0, float(l3_arr[6]), float(l3_arr[7]), 0.1)
+        assert abs(l3.sensitivity(view) - L.ref_line3d_sensitivity(p(l3_arr), p(cam_arr))) <= 1e-7
+        assert abs(l3.computeUncertainty(view, 5.0) - L.ref_line3d_uncertainty(p(l3_arr), p(cam_arr), 5.0)) <= 1e-10 * max(1.0, abs(l3_arr[6]))
