@@ -92,6 +92,8 @@ def lib():
         L.ref_linetrack_read.restype = C.c_int64
         L.ref_linetrack_read.argtypes = [C.c_char_p, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P]
         L.ref_line_weights.argtypes = [C.c_int64, _P, _P]
+        L.ref_track_filter.restype = C.c_int64
+        L.ref_track_filter.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, _P, C.c_int32, _P, _P, _P, _P, C.c_int64] + [_P] * 18
         L.ref_remerge_groups.restype = C.c_int64
         L.ref_remerge_groups.argtypes = [C.c_int64, _P, _P, _P, _P]
         _lib = L

@@ -654,3 +654,83 @@ void ref_line_weights(int64_t n, const double *l2d, double *out) {
   for (int64_t i = 0; i < n; ++i) out[i] = w[(size_t)i];
 }
 }
+
+// Track-level post-triangulation operators of the reference's compiled merging code on flat track arrays:
+//   op 0 FilterSupportingLines(th_angular2d = a, th_perp2d = b, num_outliers = n)        merging_utils.cc:51-83
+//   op 1 FilterTracksBySensitivity(th_angular3d = a, min_support_ns = n)                 :105-128
+//   op 2 FilterTracksByOverlap(th_overlap = a, min_support_ns = n)                       :130-155
+//   op 3 RemergeLineTracks(linker3d, num_outliers = n), iterated until the track count is stable (merging.py:24-42)
+// Tracks: T, sup_off[T+1]; track_line[T][9] = start, end, depth_start, depth_end, uncertainty; active[T];
+// per supporting line: view index (= image id), line id, node id, score, line2d[4], line3d[9]. Outputs in the same layout
+// (capacities = the inputs' sizes: no operator creates supporting lines). Returns the number of output tracks.
+extern "C" {
+int64_t ref_track_filter(int op, double a, double b, int n, const ref_linker_cfg *lk, int32_t n_views, const int32_t *model_ids,
+                         const double *kvec, const double *qvec, const double *tvec, int64_t T, const int64_t *sup_off,
+                         const double *track_line, const uint8_t *active, const int32_t *sup_view, const int32_t *sup_lid,
+                         const int32_t *sup_node, const double *sup_score, const double *l2d, const double *l3d,
+                         int64_t *o_off, double *o_line, uint8_t *o_active, int32_t *o_view, int32_t *o_lid, int32_t *o_node,
+                         double *o_score, double *o_l2d, double *o_l3d) {
+  std::map<int, Camera> cams;
+  std::map<int, CameraImage> imgs;
+  for (int v = 0; v < n_views; ++v) {
+    const double *k = kvec + 4 * v;
+    const int model = model_ids ? model_ids[v] : 1;
+    std::vector<double> params;
+    if (model == 0) params = {k[0], k[2], k[3]};
+    else params = {k[0], k[1], k[2], k[3]};
+    cams[v] = Camera(model, params, v);
+    imgs[v] = CameraImage(v, CameraPose(V4D(qvec[4 * v], qvec[4 * v + 1], qvec[4 * v + 2], qvec[4 * v + 3]),
+                                        V3D(tvec[3 * v], tvec[3 * v + 1], tvec[3 * v + 2])));
+  }
+  ImageCollection imagecols(cams, imgs);
+  auto mk9 = [](const double *l) { return Line3d(V3D(l[0], l[1], l[2]), V3D(l[3], l[4], l[5]), 1.0, l[6], l[7], l[8]); };
+  std::vector<LineTrack> tracks((size_t)T);
+  for (int64_t t = 0; t < T; ++t) {
+    LineTrack &tr = tracks[(size_t)t];
+    tr.line = mk9(track_line + 9 * t);
+    tr.active = active[t] != 0;
+    for (int64_t s = sup_off[t]; s < sup_off[t + 1]; ++s) {
+      tr.image_id_list.push_back(sup_view[s]);
+      tr.line_id_list.push_back(sup_lid[s]);
+      tr.node_id_list.push_back(sup_node[s]);
+      tr.score_list.push_back(sup_score[s]);
+      tr.line2d_list.push_back(mk2(l2d + 4 * s));
+      tr.line3d_list.push_back(mk9(l3d + 9 * s));
+    }
+  }
+  std::vector<LineTrack> out;
+  if (op == 0) merging::FilterSupportingLines(out, tracks, imagecols, a, b, n);
+  else if (op == 1) merging::FilterTracksBySensitivity(out, tracks, imagecols, a, n);
+  else if (op == 2) merging::FilterTracksByOverlap(out, tracks, imagecols, a, n);
+  else {
+    out = tracks;
+    size_t count = out.size();
+    while (true) {
+      out = merging::RemergeLineTracks(out, LineLinker3d(to_linker3d(*lk)), n);
+      if (out.size() == count) break;
+      count = out.size();
+    }
+  }
+  int64_t k = 0;
+  for (size_t t = 0; t < out.size(); ++t) {
+    const LineTrack &tr = out[t];
+    o_off[t] = k;
+    double *ol = o_line + 9 * t;
+    for (int q = 0; q < 3; ++q) { ol[q] = tr.line.start[q]; ol[3 + q] = tr.line.end[q]; }
+    ol[6] = tr.line.depths[0]; ol[7] = tr.line.depths[1]; ol[8] = tr.line.uncertainty;
+    o_active[t] = tr.active ? 1 : 0;
+    for (size_t s = 0; s < tr.count_lines(); ++s, ++k) {
+      o_view[k] = tr.image_id_list[s];
+      o_lid[k] = tr.line_id_list[s];
+      o_node[k] = tr.node_id_list[s];
+      o_score[k] = tr.score_list[s];
+      for (int q = 0; q < 2; ++q) { o_l2d[4 * k + q] = tr.line2d_list[s].start[q]; o_l2d[4 * k + 2 + q] = tr.line2d_list[s].end[q]; }
+      const Line3d &l = tr.line3d_list[s];
+      for (int q = 0; q < 3; ++q) { o_l3d[9 * k + q] = l.start[q]; o_l3d[9 * k + 3 + q] = l.end[q]; }
+      o_l3d[9 * k + 6] = l.depths[0]; o_l3d[9 * k + 7] = l.depths[1]; o_l3d[9 * k + 8] = l.uncertainty;
+    }
+  }
+  o_off[out.size()] = k;
+  return (int64_t)out.size();
+}
+}

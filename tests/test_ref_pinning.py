@@ -530,3 +530,88 @@ def test_python_value_types_against_compiled_reference():
         l3 = base.Line3d(X, Y, 1.0, float(l3_arr[6]), float(l3_arr[7]), 0.1)
         assert abs(l3.sensitivity(view) - L.ref_line3d_sensitivity(p(l3_arr), p(cam_arr))) <= 1e-7
         assert abs(l3.computeUncertainty(view, 5.0) - L.ref_line3d_uncertainty(p(l3_arr), p(cam_arr), 5.0)) <= 1e-10 * max(1.0, abs(l3_arr[6]))
+
+
+def _flatten_tracks(tracks, view_of):
+    off, tl, act, view, lid, node, score, l2d, l3d = [0], [], [], [], [], [], [], [], []
+    l9 = lambda l: [*l.start, *l.end, l.depths[0], l.depths[1], l.uncertainty]
+    for t in tracks:
+        tl.append(l9(t.line))
+        act.append(1 if t.active else 0)
+        for k in range(t.count_lines()):
+            view.append(view_of[int(t.image_id_list[k])])
+            lid.append(int(t.line_id_list[k]))
+            node.append(int(t.node_id_list[k]))
+            score.append(float(t.score_list[k]))
+            l2d.append([*t.line2d_list[k].start, *t.line2d_list[k].end])
+            l3d.append(l9(t.line3d_list[k]))
+        off.append(len(view))
+    f = lambda a, dt, shp: np.ascontiguousarray(np.asarray(a, dt).reshape(shp))
+    return (f(off, np.int64, -1), f(tl, np.float64, (-1, 9)), f(act, np.uint8, -1), f(view, np.int32, -1), f(lid, np.int32, -1),
+            f(node, np.int32, -1), f(score, np.float64, -1), f(l2d, np.float64, (-1, 4)), f(l3d, np.float64, (-1, 9)))
+
+
+def _ref_track_filter(op, a, b, n, lk, cams, flat):
+    L = ref.lib()
+    p = orc._p
+    off, tl, act, view, lid, node, score, l2d, l3d = flat
+    T, S = len(off) - 1, len(view)
+    o = (np.zeros(T + 1, np.int64), np.zeros((max(T, 1), 9)), np.zeros(max(T, 1), np.uint8), np.zeros(max(S, 1), np.int32),
+         np.zeros(max(S, 1), np.int32), np.zeros(max(S, 1), np.int32), np.zeros(max(S, 1)), np.zeros((max(S, 1), 4)),
+         np.zeros((max(S, 1), 9)))
+    model_ids, kvec, qvec, tvec = cams
+    cfg = ref.linker_cfg(lk or {})
+    To = L.ref_track_filter(op, float(a), float(b), int(n), C.byref(cfg), len(kvec), p(model_ids), p(kvec), p(qvec), p(tvec), T,
+                            p(off), p(tl), p(act), p(view), p(lid), p(node), p(score), p(l2d), p(l3d), *[p(x) for x in o])
+    S_o = int(o[0][To])
+    return (o[0][:To + 1], o[1][:To], o[2][:To], o[3][:S_o], o[4][:S_o], o[5][:S_o], o[6][:S_o], o[7][:S_o], o[8][:S_o])
+
+
+def test_track_level_filters_and_remerge_against_compiled_reference(monkeypatch):
+    """f1 at track level: the mirror's post-triangulation operators (limap_b200.merging: list surgery in Python on top of the
+    engine's per-support predicates, here served by the oracle stand-in so that the test runs without a GPU) against the
+    reference's compiled FilterSupportingLines / FilterTracksBySensitivity / FilterTracksByOverlap / iterated
+    RemergeLineTracks, on the tracks of a triangulated scene: same tracks in the same order, same supports, same lines."""
+    import limap.base as base
+    import limap.merging as merging
+    import limap.triangulation as triangulation
+    from limap_b200.config import DEFAULT_YAML_TRIANGULATION
+    from limap_b200.synth import make_scene
+    from runner_utils import imagecols_of, install_oracle_backend
+    install_oracle_backend(monkeypatch)
+    sc = make_scene(V=10, L=120, N=5, K=4, seed=93, noise_px=1.0, camera_mix=True)
+    imagecols = imagecols_of(sc)
+    tri = triangulation.GlobalLineTriangulator(dict(DEFAULT_YAML_TRIANGULATION))
+    tri.SetRanges(sc.ranges)
+    tri.Init({int(i): [base.Line2d(s[:2], s[2:]) for s in sc.lines_of(v)] for v, i in enumerate(sc.img_ids)}, imagecols)
+    for i in sc.img_ids:
+        tri.TriangulateImage(int(i), sc.matches[int(i)])
+    tracks = tri.ComputeLineTracks()
+    assert len(tracks) > 30
+    view_of = {int(i): v for v, i in enumerate(sc.img_ids)}
+    cams = (np.ascontiguousarray(sc.model_ids, np.int32), sc.kvec, sc.qvec, sc.tvec)
+
+    def same(py_tracks, flat_ref, tag):
+        a = _flatten_tracks(py_tracks, view_of)
+        assert np.array_equal(a[0], flat_ref[0]), tag                       # track boundaries
+        for k in (3, 4, 5):                                                  # views, line ids, node ids in order
+            assert np.array_equal(a[k], flat_ref[k]), (tag, k)
+        assert np.array_equal(a[2], flat_ref[2]), tag                        # active flags
+        assert np.allclose(a[6], flat_ref[6], atol=1e-12) and np.allclose(a[7], flat_ref[7], atol=1e-12)
+        d = np.minimum(np.abs(a[1][:, :6] - flat_ref[1][:, :6]).max(1, initial=0),
+                       np.abs(a[1][:, :6] - flat_ref[1][:, [3, 4, 5, 0, 1, 2]]).max(1, initial=0))
+        assert d.max(initial=0) < 1e-8, (tag, d.max())
+        return len(py_tracks)
+
+    flat = _flatten_tracks(tracks, view_of)
+    n0 = len(tracks)
+    t1 = merging.filter_tracks_by_reprojection(tracks, imagecols, 4.0, 2.0, num_outliers=0)
+    n1 = same(t1, _ref_track_filter(0, 4.0, 2.0, 0, None, cams, flat), "reprojection")
+    lk = dict(score_th=0.5, th_angle=8.0, th_overlap=0.01, th_smartoverlap=0.1, th_smartangle=1.0, th_perp=1.0, th_innerseg=1.0)
+    t2 = merging.remerge(base.LineLinker3d(lk), t1, num_outliers=0)
+    n2 = same(t2, _ref_track_filter(3, 0, 0, 0, lk, cams, _flatten_tracks(t1, view_of)), "remerge")
+    t3 = merging.filter_tracks_by_sensitivity(t2, imagecols, 75.0, 4)
+    n3 = same(t3, _ref_track_filter(1, 75.0, 0, 4, None, cams, _flatten_tracks(t2, view_of)), "sensitivity")
+    t4 = merging.filter_tracks_by_overlap(t3, imagecols, 0.5, 4)
+    n4 = same(t4, _ref_track_filter(2, 0.5, 0, 4, None, cams, _flatten_tracks(t3, view_of)), "overlap")
+    assert n0 >= n1 >= n2 >= n3 >= n4 > 5 and n4 < n0
