@@ -262,7 +262,8 @@ class Camera:
             raise RuntimeError("THROW_CHECK_GT(val, 0)")
         ratio = float(val) / float(max(self.height, self.width))
         if ratio < 1.0:
-            self.resize(int(round(ratio * self.width)), int(round(ratio * self.height)))
+            # C round(): halves away from zero (Python's round() goes to the even neighbour)
+            self.resize(int(np.floor(ratio * self.width + 0.5)), int(np.floor(ratio * self.height + 0.5)))
 
     def kvec(self):  # base/camera_models.h:29-44 ParamsToKvec
         p = self.params

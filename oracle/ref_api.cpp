@@ -734,3 +734,13 @@ int64_t ref_track_filter(int op, double a, double b, int n, const ref_linker_cfg
   return (int64_t)out.size();
 }
 }
+
+// Camera::set_max_image_dim (base/camera.cc:216-226; colmap::Camera::Rescale restated in the shim): params in / out, hw in / out
+extern "C" void ref_camera_set_max_image_dim(int model, double *params, int32_t *hw, int val) {
+  std::vector<double> p(params, params + (model == 0 ? 3 : 4));
+  Camera cam(model, p, 0, std::make_pair(hw[0], hw[1]));
+  cam.set_max_image_dim(val);
+  for (size_t i = 0; i < cam.params.size(); ++i) params[i] = cam.params[i];
+  hw[0] = (int32_t)cam.h();
+  hw[1] = (int32_t)cam.w();
+}

@@ -615,3 +615,28 @@ def test_track_level_filters_and_remerge_against_compiled_reference(monkeypatch)
     t4 = merging.filter_tracks_by_overlap(t3, imagecols, 0.5, 4)
     n4 = same(t4, _ref_track_filter(2, 0.5, 0, 4, None, cams, _flatten_tracks(t3, view_of)), "overlap")
     assert n0 >= n1 >= n2 >= n3 >= n4 > 5 and n4 < n0
+
+
+def test_camera_set_max_image_dim_rounding():
+    """Camera::set_max_image_dim (the runner's max_image_dim): the new size is C round() of ratio * size (halves away from
+    zero, not to even), the intrinsics follow colmap::Camera::Rescale."""
+    import limap.base as base
+    L = ref.lib()
+    L.ref_camera_set_max_image_dim.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(94)
+    cases = [(801, 1602, 801), (600, 800, 400), (1000, 3, 500)]  # (h, w, val): the first has ratio * h == 400.5 exactly
+    cases += [(int(rng.integers(100, 3000)), int(rng.integers(100, 3000)), int(rng.integers(50, 3500))) for _ in range(400)]
+    n_half = 0
+    for h, w, val in cases:
+        for model in (0, 1):
+            params = [612.3, 400.5, 299.25] if model == 0 else [612.3, 640.7, 400.5, 299.25]
+            cam = base.Camera("SIMPLE_PINHOLE" if model == 0 else "PINHOLE", list(params), 0, (h, w))
+            cam.set_max_image_dim(val)
+            pr = np.array(params + [0.0] * (4 - len(params)))
+            hw = np.array([h, w], np.int32)
+            L.ref_camera_set_max_image_dim(model, orc._p(pr), orc._p(hw), val)
+            assert (cam.h(), cam.w()) == (int(hw[0]), int(hw[1])), (h, w, val)
+            assert np.allclose(cam.params, pr[:len(params)], rtol=1e-15, atol=0), (h, w, val)
+        r = val / max(h, w)
+        n_half += r < 1 and (abs(r * h % 1 - 0.5) < 1e-12 or abs(r * w % 1 - 0.5) < 1e-12)
+    assert n_half >= 1
